@@ -1,0 +1,367 @@
+// Linear / 1x1-conv / im2col-conv GEMM on the 5th-gen tensor cores.
+//
+//   out[M,N] = epilogue( A[M,K] (bf16, row-major, lda) * W[N,K]^T (bf16, row-major, ldw) )
+//
+// This is the `nn.Linear` / `nn.Conv2d` arithmetic of the reference forward
+// (qkv/proj/fc1/fc2 in lib/models/mixformer_vit/mixformer.py:45-47,123; value/output/ffn
+// projections of the fusion encoder, deformable_encoder_lnspecific.py:127-155; folded conv+BN
+// of the corner head, lib/models/mixformer_cvt/head.py:7-20) with bias, activation, residual
+// and positional-table adds fused into the epilogue.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor 2D loads of the A (128 x 64) and W (BN x 64)
+//                 K-slices into a multi-stage 128B-swizzled smem ring (mbarrier full/empty).
+//   warp 1      : MMA issuer    - one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4
+//                 per stage into a double-buffered fp32 accumulator in TMEM; tcgen05.commit
+//                 releases smem stages and publishes finished accumulators.
+//   warps 2..5  : epilogue      - tcgen05.ld the accumulator (each warp owns one 32-lane TMEM
+//                 quadrant = 32 output rows), apply bias/act/residual, store bf16 or fp32.
+// The accumulator double buffer lets the epilogue of tile i overlap the MMAs of tile i+1.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "../../include/mmt_b200.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace mmt {
+using namespace ptx;
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+
+struct GemmEpi {
+  const float* bias;      // [N] or nullptr
+  const float* resid;     // fp32 [M, ldr] or nullptr (added after the activation)
+  const float* rowadd;    // fp32 [rowadd_period, N] or nullptr: += rowadd[row % period][n]
+  void* out;              // bf16 or fp32 [M, ldo]
+  int ldr;
+  int rowadd_period;
+  int ldo;
+  int act;                // MMT_ACT_*
+  int out_fp32;
+  int vec_ok;             // all vector-store alignment preconditions hold
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int CH = (BN % 32 == 0) ? 32 : 16;  // epilogue column chunk
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                        : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         int M, int N, int K, GemmEpi ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_tiles = n_tiles * m_tiles;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+          const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16-byte units
+            mma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const float* rowadd_row =
+          ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
+      const float* resid_row = ep.resid ? ep.resid + static_cast<size_t>(row) * ep.ldr : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / Cfg::CH; ++c) {
+        uint32_t v[32];
+        if (Cfg::CH == 32) tmem_ld_32x32(t_row + c * Cfg::CH, v);
+        else tmem_ld_32x16(t_row + c * Cfg::CH, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * Cfg::CH;
+        if (row < M && nb < N) {
+          const bool full = ep.vec_ok && (nb + Cfg::CH <= N);
+          float f[Cfg::CH];
+#pragma unroll
+          for (int j = 0; j < Cfg::CH; ++j) f[j] = __uint_as_float(v[j]);
+          if (full) {
+            if (ep.bias) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+            if (ep.act == MMT_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; ++j) f[j] = gelu_fast(f[j]);
+            } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (rowadd_row) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rowadd_row + nb + j));
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+            if (resid_row) {
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(resid_row + nb + j);
+                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+              }
+            }
+            if (ep.out_fp32) {
+              float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nb;
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nb;
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 8) {
+                uint4 p;
+                p.x = pack_bf16x2(f[j], f[j + 1]);
+                p.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                p.z = pack_bf16x2(f[j + 4], f[j + 5]);
+                p.w = pack_bf16x2(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = p;
+              }
+            }
+          } else {
+            // ragged / unaligned tail: scalar, bounds-checked
+#pragma unroll
+            for (int j = 0; j < Cfg::CH; ++j) {
+              const int n = nb + j;
+              if (n >= N) continue;
+              float x = f[j];
+              if (ep.bias) x += ep.bias[n];
+              if (ep.act == MMT_ACT_GELU) x = gelu_fast(x);
+              else if (ep.act == MMT_ACT_RELU) x = fmaxf(x, 0.f);
+              if (rowadd_row) x += rowadd_row[n];
+              if (resid_row) x += resid_row[n];
+              if (ep.out_fp32) reinterpret_cast<float*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = x;
+              else reinterpret_cast<bf16*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64].
+static int make_tmap_2d(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return MMT_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
+                       int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmB;
+  int rc = make_tmap_2d(&tmB, W, N, K, ldw, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = cdiv(M, GEMM_BM) * cdiv(N, BN);
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  MMT_RETURN_LAST_ERROR();
+}
+
+static int pick_bn(int N) {
+  // widest tile whose padding waste is <= 1/8 of a tile, preferring fewer tiles
+  const int cands[8] = {256, 192, 128, 96, 64, 48, 32, 16};
+  int best = 16;
+  long best_cost = -1;
+  for (int i = 0; i < 8; ++i) {
+    const int bn = cands[i];
+    const long padded = static_cast<long>(cdiv(N, bn)) * bn;
+    // cost = padded MMA columns, with a small penalty for narrow tiles (less operand reuse)
+    const long cost = padded * 16 + (256 - bn);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace mmt
+
+extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                             int act, const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out,
+                             int ldo, int out_fp32, int max_ctas, void* stream) {
+  using namespace mmt;
+  MMT_CHECK_ARG(A && W && out && M > 0 && N > 0 && K > 0);
+  MMT_CHECK_ARG(lda >= K && ldw >= K && ldo >= N);
+  MMT_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0);  // TMA: 16-byte global strides
+  MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  MMT_CHECK_ARG(!rowadd || rowadd_period > 0);
+  MMT_CHECK_ARG(!resid || ldr >= N);
+  GemmEpi ep;
+  ep.bias = bias; ep.resid = resid; ep.rowadd = rowadd; ep.out = out;
+  ep.ldr = ldr; ep.rowadd_period = rowadd_period; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
+  const int out_al = out_fp32 ? 4 : 8;
+  ep.vec_ok = (ldo % out_al == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+              (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+              (!resid || ((ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(resid) & 15) == 0)) &&
+              (!rowadd || ((N % 4 == 0) && (reinterpret_cast<uintptr_t>(rowadd) & 15) == 0));
+  CUtensorMap tmA;
+  int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (pick_bn(N)) {
+    case 256: return launch_gemm<256>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 192: return launch_gemm<192>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 128: return launch_gemm<128>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 96: return launch_gemm<96>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 64: return launch_gemm<64>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 48: return launch_gemm<48>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    case 32: return launch_gemm<32>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+    default: return launch_gemm<16>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
+  }
+}

@@ -1,0 +1,46 @@
+"""Micro-benchmark of the tcgen05 GEMM on the backbone shapes (CUDA events, L2-busting rotation)."""
+import json
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import mmt_b200  # noqa
+from mmt_b200 import ops
+
+
+def bench(M, N, K, act=0, resid=False, iters=20):
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda") if resid else None
+    out = r if resid else torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, bias, act, r, None, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, w, bias, act, r, None, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    # cuBLAS reference for context
+    for _ in range(3):
+        torch.matmul(a, w.t())
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, w.t())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_ref = e0.elapsed_time(e1) / iters
+    return {"M": M, "N": N, "K": K, "act": act, "resid": resid, "ms": round(ms, 4), "tflops": round(tf, 1),
+            "cublas_ms": round(ms_ref, 4), "cublas_tflops": round(2.0 * M * N * K / ms_ref / 1e9, 1)}
+
+
+if __name__ == "__main__":
+    M = 57856
+    for args in [(M, 2304, 768, 0, False), (M, 768, 768, 0, True), (M, 3072, 768, 1, False), (M, 768, 3072, 0, True),
+                 (M // 2, 2304, 768, 0, False), (904, 2304, 768, 0, False)]:
+        print(json.dumps(bench(*args)), flush=True)
