@@ -53,6 +53,128 @@ int mmt_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N,
                  const float* resid, int ldr, const float* rowadd, int rowadd_period, float* out, int ldo,
                  void* stream);
 
+/*
+ * Patch matrix of a Conv2d(Cin, C, P, stride P): img fp32 NCHW [B,Cin,H,W] -> rows of length Cin*P*P
+ * (k = c*P*P + ky*P + kx == weight.view(C,-1) order) written at row b*tok_per_seq + tok_off + patch.
+ * Reference: PatchEmbed.forward lib/models/mixformer_vit/mixformer.py:28-33 (the conv itself is then
+ * mmt_gemm_* with rowadd = pos_embed, :192-203).
+ */
+int mmt_patchify(const float* img, void* out, int B, int Cin, int H, int W, int P, int tok_off, int tok_per_seq,
+                 int out_bf16, void* stream);
+
+/*
+ * LayerNorm over the last dim of fp32 rows [rows, C]; parameter set (g1,b1) is used for rows with
+ * ((row / period) & 1) == 1 (period <= 0 or g1 == NULL: always (g0,b0)).  Writes an fp32 and/or a bf16 copy.
+ * Reference: nn.LayerNorm(eps=1e-6) in Block.forward lib/models/mixformer_vit/mixformer.py:126-129,259;
+ * modality-specific norms lib/models/mixformer_vit_rgbt/mixformer_shared.py:143-157 and
+ * deformable_attention/deformable_encoder_lnspecific.py:143-160 (eps 1e-5).
+ */
+int mmt_layernorm(const float* x, int rows, int C, float eps, const float* g0, const float* b0, const float* g1,
+                  const float* b1, int period, float* out_f32, void* out_bf16, void* stream);
+
+/*
+ * GroupNorm(G, C) of fp32 NHWC rows [B, HW, C] (statistics over HW x C/G per sample and group).
+ * Output row of (b, r) is b*out_seq_rows + out_row_off + r (out_seq_rows <= 0: dense, = HW), so that one modality's
+ * map lands in its half of the [B, 2*HW, C] fusion token tensor.
+ * Reference: nn.GroupNorm(32, .) after the fusion 1x1 convs lib/models/mixformer_vit_rgbt/fusion_utils.py:252-268.
+ */
+int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
+                  float* out_f32, void* out_bf16, int out_seq_rows, int out_row_off, void* stream);
+
+/* dst[s*rows_per_seq + r, :] = T(src[s*seq_stride + row_off + r, :]): e.g. the search tokens of every sequence
+ * out of the [template, online template, search] token layout (torch.split, mixformer.py:208). */
+int mmt_copy_rows(const float* src, int seq_stride, int row_off, int rows_per_seq, int nseq, int C, void* dst,
+                  int out_bf16, void* stream);
+
+/*
+ * Staging of the bimodal deformable-attention inputs from the fusion tokens src fp32 [B, 2L, C]
+ * (first L tokens RGB, last L TIR):  out_val[B*2L, C] = T(src);  out_q[B*L, 2C] = T(cat_c(src_v + pos_v, src_i + pos_i)).
+ * Reference: query_bimodal / with_pos_embed, ms_deform_attn_bimodal.py:97-99, deformable_encoder_lnspecific.py:151.
+ */
+int mmt_fusion_prep(const float* src, const float* pos, int B, int L, int C, void* out_val, void* out_q, int out_bf16,
+                    void* stream);
+
+/*
+ * MultiScaleDeformableAttention forward, reference tensor layout (value [N,S,M,D] T; sampling_loc
+ * [N,Lq,M,L,P,2] fp32 in [0,1]; attn_weight [N,Lq,M,L,P] fp32; out [N,Lq,M*D] T).  level_hw_host is a HOST array
+ * of L (H,W) pairs.  Replaces MSDA.ms_deform_attn_forward (deformable_attention/ops/src/cuda/
+ * ms_deform_attn_cuda.cu:20-80, ms_deform_im2col_cuda.cuh:237-299); no batch % im2col_step restriction.
+ */
+int mmt_msda_fwd(const void* value, const int* level_hw_host, const float* sampling_loc, const float* attn_weight,
+                 void* out, int N, int S, int M, int D, int L, int Lq, int P, int is_bf16, void* stream);
+
+/*
+ * Fused bimodal form used in the RGB-T fusion encoder: value T [B, 2*H*W, M*64]; offw fp32 [B*H*W, ld] holding the
+ * raw projection output [M*2*P*2 sampling offsets | M*2*P attention logits] per position; reference points,
+ * offset normalisation, softmax over the 2*P samples and sampling are fused; the (identical) result is written for
+ * the RGB and the TIR query rows.  Reference: MSDeformAttn_Bimodal.forward ms_deform_attn_bimodal.py:83-130.
+ */
+int mmt_msda_bimodal_fwd(const void* value, const float* offw, int ld_offw, void* out, int B, int H, int W, int M,
+                         int D, int P, int is_bf16, void* stream);
+
+/*
+ * im2col of Conv2d(k=3, pad=1) on NHWC maps with nearest upsampling (+ optional add of a second map) folded in:
+ * in(b,y,x,:) = src1[b, y/s1, x/s1, :] (+ src2[b, y/s2, x/s2, :]);  out[(b*H+y)*W+x, (ky*3+kx)*C + c].
+ * Reference: F.interpolate + add + conv in Pyramid_Corner_Predictor.get_score_map lib/models/mixformer_cvt/head.py:159-198.
+ */
+int mmt_im2col3x3(const void* src1, int ld1, int s1, const void* src2, int ld2, int s2, int B, int H, int W, int C,
+                  void* out, int is_bf16, void* stream);
+
+/*
+ * Corner decode for both corners: score = conv5_1x1(x4) + up4(a3) + up2(a4), softmax over S*S, soft-argmax,
+ * xyxy / img_sz and box_xyxy_to_cxcywh.  score_maps (fp32 [B,2,S*S], raw logits) may be NULL.
+ * Reference: head.py:181,198-212 (coords :138-145), lib/utils/box_ops.py:27-31, forward_box_head mixformer.py:325-338.
+ */
+int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x, int C4, const float* w5_tl, const float* w5_br,
+                      float b5_tl, float b5_br, const void* a3_tl, const void* a3_br, int lda3, const void* a4_tl,
+                      const void* a4_br, int lda4, int B, int S, float stride_px, float img_sz, float* score_maps,
+                      float* xyxy, float* cxcywh, int is_bf16, void* stream);
+
+/*
+ * Asymmetric mixed attention over packed qkv rows [rows, 3C] (q | k | v, head-major 64-wide slices).
+ * tiles_dev: DEVICE array of n_tiles records of 16 int32:
+ *   {q_row0, q_rows(<=64), out_row0, nseg(<=3), k_row0[3], k_len[3], k_buf[3], pad[3]}; key segment i reads rows
+ *   [k_row0[i], +k_len[i]) of qkv0 (k_buf 0) or qkv1 (k_buf 1, e.g. cached template K/V).  max_keys = largest
+ *   total key count of any tile (fp32 mode sizing).  out T [.., ldo], head h at column h*64.
+ * Reference: Attention.forward / forward_test lib/models/mixformer_vit/mixformer.py:51-93; cross-modal
+ * lib/models/mixformer_vit_rgbt/asymmetric_shared.py:55-104, asymmetric_shared_ce.py:146-200.
+ */
+int mmt_mixattn_fwd(const void* qkv0, const void* qkv1, int ld, int C, int heads, const int* tiles_dev, int n_tiles,
+                    int max_keys, void* out, int ldo, float scale, int is_bf16, void* stream);
+
+/*
+ * Candidate-elimination scores [B, 2*Ls] = mean over heads of mean over the 2*Lt template rows of
+ * softmax_{2Ls}([q_mt_V; q_mt_I] [k_s_V; k_s_I]^T * scale), from the modality-major qkv buffer [2B, n_tok, 3C].
+ * partial_ws: fp32 workspace [B * heads * (2*Lt/32) * 2*Ls].  fp32 arithmetic in both modes, deterministic.
+ * Reference: asymmetric_shared_ce.py:202-205 (attn_t2s) and :91-92 (mean(dim=2).mean(dim=1)).
+ */
+int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
+                  float* partial_ws, float* scores, int is_bf16, void* stream);
+
+/*
+ * Per (sequence, modality) descending sort of the Ls scores; order int32 [2B, Ls] (sorted local indices),
+ * gidx_keep fp32 [2B, keep] / gidx_removed fp32 [2B, Ls-keep] = gidx_in gathered in score order.  All [2B, .]
+ * tensors are modality-major (row m*B + b).  Reference: get_token_from_attn asymmetric_shared_ce.py:22-46.
+ */
+int mmt_ce_topk(const float* scores, int B, int Ls, int keep, const float* gidx_in, float* gidx_keep,
+                float* gidx_removed, int* order, void* stream);
+
+/* x_out[s, :Lt] = x[s, :Lt]; x_out[s, Lt+i] = x[s, Lt + order[s][i]], i < keep (tokens.gather, :41-44). */
+int mmt_ce_gather_tokens(const float* x, int nseq, int n_tok, int Lt, const int* order, int Ls, int keep, float* x_out,
+                         int C, void* stream);
+
+/* out[s*Ls0 + int(gidx[s][i]), :] = T(x[s, Lt+i, :]), zeros elsewhere (_recover_search :427-447). */
+int mmt_ce_recover(const float* x, int nseq, int n_tok, int Lt, const float* gidx, int Lk, int Ls0, void* out, int C,
+                   int out_bf16, void* stream);
+
+/*
+ * Precise RoI pooling forward: rois fp32 [R,5] = (batch_idx, x0, y0, x1, y1).  channels_last = 0: feat NCHW,
+ * out [R,C,PH,PW] (the reference op's layout, prroi_pooling_gpu.c:22-44); channels_last = 1: feat NHWC, out
+ * [R, PH*PW, C] (token layout used by the SPM head).  Kernel restated from prroi_pooling_gpu_impl.cu:37-106,149-212.
+ */
+int mmt_prroi_fwd(const float* feat, const float* rois, float* out, int R, int C, int H, int W, int PH, int PW,
+                  float spatial_scale, int channels_last, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,392 @@
+"""Drop-in model builders: same names, signatures, config objects and checkpoint layout as the reference's
+`lib/models` builders, with the forward executed by the sm_100a engine (engine.py) instead of torch ops.
+
+    build_mixformer_vit(cfg, train=False)                lib/models/mixformer_vit/mixformer.py:341-366
+    build_mixformer_vit_rgbt(cfg, train=False)           lib/models/mixformer_vit_rgbt/mixformer.py:433-466
+    build_mixformer_vit_rgbt_shared(cfg, train=False)    lib/models/mixformer_vit_rgbt/mixformer_shared.py:461-507
+    build_mixformer_vit_rgbt_uni(cfg, train=False)       lib/models/mixformer_vit_rgbt/mixformer_unibackbone.py
+    build_asymmetric_shared(cfg, train=False)            lib/models/mixformer_vit_rgbt/asymmetric_shared.py
+    build_asymmetric_shared_ce(cfg, train=False)         lib/models/mixformer_vit_rgbt/asymmetric_shared_ce.py:590-640
+
+The returned nn.Module owns nn.Parameters / buffers under EXACTLY the reference's state_dict keys and shapes, so
+`load_state_dict(torch.load(ckpt)["net"], strict=True)` works on reference checkpoints.  The torch sub-modules
+(nn.Linear, nn.Conv2d, ...) are used purely as named parameter containers - their forward is never called.
+`forward(template, online_template, search, ...)` returns `(out_dict, coords)` like the reference.
+Only inference is supported (train=True raises): training is out of scope of this library.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .pos_embed import sincos_pos_embed_2d
+
+VIT_DIMS = {"base_patch16": dict(dim=768, depth=12, heads=12), "large_patch16": dict(dim=1024, depth=24, heads=16)}
+
+
+# ------------------------------------------------------------------------------------------------ containers
+class _Attention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    """Parameter layout of Block (mixformer.py:112-124) or, with per_modality_ln, Block_Shared /
+    CE_Block_Shared (mixformer_shared.py:113-141, asymmetric_shared_ce.py:210-245)."""
+
+    def __init__(self, dim, per_modality_ln):
+        super().__init__()
+        ln = partial(nn.LayerNorm, eps=1e-6)
+        if per_modality_ln:
+            self.norm1_v, self.norm1_i = ln(dim), ln(dim)
+        else:
+            self.norm1 = ln(dim)
+        self.attn = _Attention(dim)
+        if per_modality_ln:
+            self.norm2_v, self.norm2_i = ln(dim), ln(dim)
+        else:
+            self.norm2 = ln(dim)
+        self.mlp = _Mlp(dim, dim * 4)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, dim, patch=16):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, kernel_size=patch, stride=patch)
+
+
+class _Backbone(nn.Module):
+    """Parameter layout of the MixViT VisionTransformer subclasses.  `timm_leftovers` keeps the unused timm
+    base-class parameters that RGB-only checkpoints still carry (cls_token, pos_embed, norm, head: SURVEY
+    section 7 'State-dict fidelity'); the RGB-T builders drop them (mixformer_vit_rgbt/mixformer.py:329-333)."""
+
+    def __init__(self, vit_type, img_size_s, img_size_t, per_modality_ln=False, timm_leftovers=False):
+        super().__init__()
+        if vit_type not in VIT_DIMS:
+            raise KeyError("VIT_TYPE shoule set to 'large_patch16' or 'base_patch16'")
+        d = VIT_DIMS[vit_type]
+        dim = d["dim"]
+        self.embed_dim, self.depth, self.num_heads = dim, d["depth"], d["heads"]
+        if timm_leftovers:
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+            self.pos_embed = nn.Parameter(torch.zeros(1, (224 // 16) ** 2 + 1, dim))
+            self.norm = nn.LayerNorm(dim, eps=1e-6)
+            self.head = nn.Linear(dim, 1000)
+        self.patch_embed = _PatchEmbed(dim)
+        self.blocks = nn.Sequential(*[_Block(dim, per_modality_ln) for _ in range(d["depth"])])
+        self.grid_size_s, self.grid_size_t = img_size_s // 16, img_size_t // 16
+        self.pos_embed_s = nn.Parameter(torch.zeros(1, self.grid_size_s ** 2, dim), requires_grad=False)
+        self.pos_embed_t = nn.Parameter(torch.zeros(1, self.grid_size_t ** 2, dim), requires_grad=False)
+        self.pos_embed_s.data.copy_(sincos_pos_embed_2d(dim, self.grid_size_s).unsqueeze(0))
+        self.pos_embed_t.data.copy_(sincos_pos_embed_2d(dim, self.grid_size_t).unsqueeze(0))
+        for m in self.modules():      # timm init_weights(''): trunc_normal(.02) linears, unit LayerNorms
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+
+class FrozenBatchNorm2d(nn.Module):
+    """Buffers of lib/models/mixformer_cvt/utils.py:21-45 (no num_batches_tracked)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        state_dict.pop(prefix + "num_batches_tracked", None)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+def _conv(inp, out, freeze_bn):
+    return nn.Sequential(nn.Conv2d(inp, out, kernel_size=3, padding=1, bias=True),
+                         FrozenBatchNorm2d(out) if freeze_bn else nn.BatchNorm2d(out), nn.ReLU(inplace=True))
+
+
+class _CornerHead(nn.Module):
+    """Parameter layout of Corner_Predictor / Pyramid_Corner_Predictor (lib/models/mixformer_cvt/head.py:23-52,
+    97-145).  Unlike the reference it can be constructed without CUDA."""
+
+    def __init__(self, inplanes, channel, feat_sz, stride, freeze_bn, pyramid):
+        super().__init__()
+        self.feat_sz, self.stride, self.img_sz, self.pyramid = feat_sz, stride, feat_sz * stride, pyramid
+        for c in ("tl", "br"):
+            setattr(self, f"conv1_{c}", _conv(inplanes, channel, freeze_bn))
+            setattr(self, f"conv2_{c}", _conv(channel, channel // 2, freeze_bn))
+            setattr(self, f"conv3_{c}", _conv(channel // 2, channel // 4, freeze_bn))
+            setattr(self, f"conv4_{c}", _conv(channel // 4, channel // 8, freeze_bn))
+            setattr(self, f"conv5_{c}", nn.Conv2d(channel // 8, 1, kernel_size=1))
+            if pyramid:
+                setattr(self, f"adjust1_{c}", _conv(inplanes, channel // 2, freeze_bn))
+                setattr(self, f"adjust2_{c}", _conv(inplanes, channel // 4, freeze_bn))
+                setattr(self, f"adjust3_{c}", nn.Sequential(_conv(channel // 2, channel // 4, freeze_bn),
+                                                            _conv(channel // 4, channel // 8, freeze_bn),
+                                                            _conv(channel // 8, 1, freeze_bn)))
+                setattr(self, f"adjust4_{c}", nn.Sequential(_conv(channel // 4, channel // 8, freeze_bn),
+                                                            _conv(channel // 8, 1, freeze_bn)))
+
+
+def build_box_head(cfg):
+    """build_box_head lib/models/mixformer_cvt/head.py:235-258 (corner heads only)."""
+    if "CORNER" not in cfg.MODEL.HEAD_TYPE:
+        raise ValueError("HEAD TYPE %s is not supported." % cfg.MODEL.HEAD_TYPE)
+    channel = cfg.MODEL.get("HEAD_DIM", 384)
+    freeze_bn = cfg.MODEL.get("HEAD_FREEZE_BN", False)
+    if cfg.MODEL.HEAD_TYPE == "CORNER":
+        stride, pyramid = 16, False
+    elif cfg.MODEL.HEAD_TYPE == "CORNER_UP":
+        stride, pyramid = 4, True
+    else:
+        raise ValueError()
+    return _CornerHead(cfg.MODEL.HIDDEN_DIM, channel, int(cfg.DATA.SEARCH.SIZE / stride), stride, freeze_bn, pyramid)
+
+
+class _MSDeformAttnBimodal(nn.Module):
+    def __init__(self, d_model=512, n_levels=2, n_heads=8, n_points=4):
+        super().__init__()
+        self.sampling_offsets = nn.Linear(2 * d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(2 * d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        # MSDeformAttn_Bimodal._reset_parameters ms_deform_attn_bimodal.py:64-81
+        import math
+        nn.init.zeros_(self.sampling_offsets.weight)
+        thetas = torch.arange(n_heads, dtype=torch.float32) * (2.0 * math.pi / n_heads)
+        grid = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(n_heads, 1, 1, 2).repeat(1, n_levels, n_points, 1)
+        for i in range(n_points):
+            grid[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(grid.view(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.zeros_(self.value_proj.bias)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.zeros_(self.output_proj.bias)
+
+
+class _FusionEncoderLayer(nn.Module):
+    def __init__(self, d_model, d_ffn):
+        super().__init__()
+        self.self_attn = _MSDeformAttnBimodal(d_model)
+        self.norm1_v, self.norm1_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.norm2_v, self.norm2_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        nn.init.xavier_uniform_(self.linear1.weight)
+        nn.init.xavier_uniform_(self.linear2.weight)
+
+
+class _FusionEncoder(nn.Module):
+    def __init__(self, d_model, layers):
+        super().__init__()
+        self.layers = nn.ModuleList([_FusionEncoderLayer(d_model, 4 * d_model) for _ in range(layers)])
+
+
+class _FusionAttention(nn.Module):
+    """Parameter layout of DeformableAttentionFusion_LNSpecific (deformable_encoder_lnspecific.py:23-57)."""
+
+    def __init__(self, d_model, layers):
+        super().__init__()
+        self.encoder = _FusionEncoder(d_model, layers)
+        self.level_embed = nn.Parameter(torch.randn(2, d_model))
+
+
+def _conv_gn(inp, out):
+    return nn.Sequential(nn.Conv2d(inp, out, kernel_size=1), nn.GroupNorm(32, out))
+
+
+FUSION_CLASSES = ("Attention_Fusion_Bimodal_LNSpecific", "Attention_Fusion_Bimodal_LNSpecific_Sum",
+                  "Attention_Fusion_Bimodal_LNSpecific_2")
+
+
+class _Fusion(nn.Module):
+    """Parameter layout of Attention_Fusion_Bimodal_LNSpecific{,_Sum,_2} (fusion_utils.py:243-353)."""
+
+    def __init__(self, fusion_class, channels=768, d_model=512, layers=2):
+        super().__init__()
+        if fusion_class not in FUSION_CLASSES:
+            raise KeyError(f"FUSION_CLASS {fusion_class!r} is not on the accelerated path; supported: {FUSION_CLASSES}")
+        self.fusion_class, self.d_model = fusion_class, d_model
+        if fusion_class.endswith("_2"):
+            self.adjust_in = _conv_gn(channels, d_model)
+        else:
+            self.adjust_v = _conv_gn(channels, d_model)
+            self.adjust_i = _conv_gn(channels, d_model)
+        self.fusion_attention = _FusionAttention(d_model, layers)
+        if fusion_class.endswith("_Sum"):
+            self.adjust_sum = _conv_gn(d_model, channels)
+        elif fusion_class.endswith("_2"):
+            self.adjust_out = _conv_gn(d_model, channels)
+        else:
+            self.adjust_cat = _conv_gn(2 * d_model, channels)
+
+
+# ------------------------------------------------------------------------------------------------ models
+class _EngineModule(nn.Module):
+    """Common behaviour: lazily (re)pack weights into the engine's device arena, run the engine forward."""
+
+    variant = ""
+    precision = "bf16"      # "bf16" (tcgen05 path) or "fp32" (parity mode)
+
+    def _init_engine_state(self, cfg):
+        self.head_type = cfg.MODEL.HEAD_TYPE
+        self._cfg = cfg
+        self._engine = None
+        self._packed_version = -1
+        self._version = 0
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._version += 1
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._version += 1      # .cuda()/.to(): weights moved, arena must be rebuilt
+        return r
+
+    def set_precision(self, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(precision)
+        if precision != self.precision:
+            self.precision = precision
+            self._version += 1
+        return self
+
+    def engine(self):
+        from .engine import ForwardEngine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
+            raise NotImplementedError("mmt_b200 models run on CUDA only: call .cuda() first (no CPU fallback)")
+        if self._engine is None or self._packed_version != self._version:
+            self._engine = ForwardEngine(self.variant, self._cfg, self.state_dict(), dev, self.precision)
+            self._packed_version = self._version
+        return self._engine
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("mmt_b200 provides the inference forward only (training is out of scope)")
+        return super().train(False)
+
+    def _finish(self, res, return_features=False):
+        coords = res["pred_boxes"]
+        out_dict = {"pred_boxes": coords}
+        if return_features:
+            eng, B = self._engine, coords.shape[0]
+            sv, si = res["search_rows"]
+            return out_dict, coords, eng.rows_to_map(sv, B), eng.rows_to_map(si, B)
+        return out_dict, coords
+
+
+class MixFormer(_EngineModule):
+    """RGB-only MixViT tracker (lib/models/mixformer_vit/mixformer.py:285-338)."""
+    variant = "mixformer_vit"
+
+    def __init__(self, backbone, box_head, cfg):
+        super().__init__()
+        self.backbone, self.box_head = backbone, box_head
+        self._init_engine_state(cfg)
+
+    @torch.no_grad()
+    def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None):
+        sq = lambda t: t.squeeze(0) if t.dim() == 5 else t
+        return self._finish(self.engine().forward(sq(template), sq(online_template), sq(search)))
+
+    def forward_box_head(self, search):
+        res = self.engine().forward_head_only(search)
+        return {"pred_boxes": res["pred_boxes"]}, res["pred_boxes"]
+
+
+class MixFormer_RGBT(_EngineModule):
+    """RGB-T trackers: two-stream (lib/models/mixformer_vit_rgbt/mixformer.py:350-431) when built with two
+    backbones, batch-stacked shared-backbone family otherwise (mixformer_shared.py:385-459,
+    asymmetric_shared_ce.py:540-588)."""
+
+    def __init__(self, variant, backbone, box_head, fusion_vi, cfg):
+        super().__init__()
+        self.variant = variant
+        if isinstance(backbone, (list, tuple)):
+            self.backbone_v, self.backbone_i = backbone
+        else:
+            self.backbone = backbone
+        self.fusion_vi, self.box_head = fusion_vi, box_head
+        self._init_engine_state(cfg)
+
+    @torch.no_grad()
+    def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None,
+                ce_template_mask=None, ce_keep_rate=None, return_features=False):
+        if ce_template_mask is not None or ce_keep_rate is not None:
+            # training-time CE schedule / template mask (lib/utils/ce_utils.py); the test-time trackers never
+            # pass them (lib/test/tracker/asymmetric_shared_ce.py:96-98)
+            raise NotImplementedError("ce_template_mask / ce_keep_rate are training-only arguments")
+        res = self.engine().forward(list(template), list(online_template), list(search))
+        return self._finish(res, return_features)
+
+
+def _require_inference(train):
+    if train:
+        raise NotImplementedError("mmt_b200 builders construct inference models only: call build_*(cfg, train=False)")
+
+
+def build_mixformer_vit(cfg, train=False) -> MixFormer:
+    _require_inference(train)
+    backbone = _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE, timm_leftovers=True)
+    return MixFormer(backbone, build_box_head(cfg), cfg).eval()
+
+
+def _fusion(cfg):
+    return _Fusion(cfg.MODEL.FUSION_CLASS, 768, 512, cfg.MODEL.FUSION_LAYERS)
+
+
+def build_mixformer_vit_rgbt(cfg, train=False) -> MixFormer_RGBT:
+    _require_inference(train)
+    mk = lambda: _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE)
+    return MixFormer_RGBT("mixformer_vit_rgbt", [mk(), mk()], build_box_head(cfg), _fusion(cfg), cfg).eval()
+
+
+def _build_stacked(variant, cfg, train, per_modality_ln):
+    _require_inference(train)
+    bb = _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE, per_modality_ln=per_modality_ln)
+    return MixFormer_RGBT(variant, bb, build_box_head(cfg), _fusion(cfg), cfg).eval()
+
+
+def build_mixformer_vit_rgbt_shared(cfg, train=False) -> MixFormer_RGBT:
+    return _build_stacked("mixformer_vit_rgbt_shared", cfg, train, True)
+
+
+def build_mixformer_vit_rgbt_uni(cfg, train=False) -> MixFormer_RGBT:
+    return _build_stacked("mixformer_vit_rgbt_unibackbone", cfg, train, False)
+
+
+def build_asymmetric_shared(cfg, train=False) -> MixFormer_RGBT:
+    return _build_stacked("asymmetric_shared", cfg, train, True)
+
+
+def build_asymmetric_shared_ce(cfg, train=False) -> MixFormer_RGBT:
+    return _build_stacked("asymmetric_shared_ce", cfg, train, True)
+
+
+BUILDERS = {
+    "mixformer_vit": build_mixformer_vit,
+    "mixformer_vit_rgbt": build_mixformer_vit_rgbt,
+    "mixformer_vit_rgbt_shared": build_mixformer_vit_rgbt_shared,
+    "mixformer_vit_rgbt_unibackbone": build_mixformer_vit_rgbt_uni,
+    "asymmetric_shared": build_asymmetric_shared,
+    "asymmetric_shared_ce": build_asymmetric_shared_ce,
+}

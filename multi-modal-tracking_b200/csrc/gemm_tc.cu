@@ -8,14 +8,16 @@
 // of the corner head, lib/models/mixformer_cvt/head.py:7-20) with bias, activation, residual
 // and positional-table adds fused into the epilogue.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      : TMA producer  - cp.async.bulk.tensor 2D loads of the A (128 x 64) and W (BN x 64)
 //                 K-slices into a multi-stage 128B-swizzled smem ring (mbarrier full/empty).
 //   warp 1      : MMA issuer    - one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4
 //                 per stage into a double-buffered fp32 accumulator in TMEM; tcgen05.commit
 //                 releases smem stages and publishes finished accumulators.
-//   warps 2..5  : epilogue      - tcgen05.ld the accumulator (each warp owns one 32-lane TMEM
-//                 quadrant = 32 output rows), apply bias/act/residual, store bf16 or fp32.
+//   warps 2..9  : epilogue      - tcgen05.ld the accumulator (warp w may touch TMEM lanes
+//                 32*(w%4)..+31 = 32 output rows; the two warps sharing a quadrant split the
+//                 column chunks), bias/act in registers, then a per-warp smem transpose so that
+//                 residual loads and output stores are row-contiguous (coalesced) in HBM.
 // The accumulator double buffer lets the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -30,8 +32,10 @@ using namespace ptx;
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_SMEM_BUDGET = 192 * 1024;  // operand ring; the rest holds the epilogue staging
+constexpr int GEMM_STAGING_WORDS = 32 * 33;   // per epilogue warp: 32 rows x (32 + 1 pad) words
 
 struct GemmEpi {
   const float* bias;      // [N] or nullptr
@@ -52,7 +56,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_WORDS * 4 +
+                                    1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int CH = (BN % 32 == 0) ? 32 : 16;  // epilogue column chunk
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
@@ -65,7 +70,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = staging_base + GEMM_EPI_WARPS * GEMM_STAGING_WORDS * 4;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -91,7 +97,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -153,94 +159,114 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which of the two warps sharing the quadrant
+    float* stg = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
+                 (warp - 2) * GEMM_STAGING_WORDS;
+    constexpr int CH = Cfg::CH;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
-      const int row = m0 + quad * 32 + lane;
+      const int row0 = m0 + quad * 32;
+      const int row = row0 + lane;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
       const float* rowadd_row =
           ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
-      const float* resid_row = ep.resid ? ep.resid + static_cast<size_t>(row) * ep.ldr : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / Cfg::CH; ++c) {
+      for (int c = half; c < BN / CH; c += 2) {
         uint32_t v[32];
-        if (Cfg::CH == 32) tmem_ld_32x32(t_row + c * Cfg::CH, v);
-        else tmem_ld_32x16(t_row + c * Cfg::CH, v);
+        if (CH == 32) tmem_ld_32x32(t_row + c * CH, v);
+        else tmem_ld_32x16(t_row + c * CH, v);
         tmem_ld_wait();
-        const int nb = n0 + c * Cfg::CH;
-        if (row < M && nb < N) {
-          const bool full = ep.vec_ok && (nb + Cfg::CH <= N);
-          float f[Cfg::CH];
+        const int nb = n0 + c * CH;
+        if (nb >= N) continue;
+        float f[CH];
 #pragma unroll
-          for (int j = 0; j < Cfg::CH; ++j) f[j] = __uint_as_float(v[j]);
-          if (full) {
-            if (ep.bias) {
+        for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full = ep.vec_ok && (nb + CH <= N);
+        if (full) {
+          // ---- thread == output row: bias, activation, positional table
+          if (ep.bias) {
 #pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            for (int j = 0; j < CH; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (ep.act == MMT_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] = gelu_fast(f[j]);
+          } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (rowadd_row && row < M) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(rowadd_row + nb + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          // ---- transpose through smem so that a warp instruction touches contiguous row bytes
+          if (ep.out_fp32) {
+            constexpr int WPR = CH;             // words per row in the staging tile
+            constexpr int RPI = 32 / WPR;       // rows covered by one warp instruction
+#pragma unroll
+            for (int j = 0; j < CH; ++j) stg[lane * (WPR + 1) + j] = f[j];
+            __syncwarp();
+            const int cc = lane % WPR, rr = lane / WPR;
+            float* obase = reinterpret_cast<float*>(ep.out) + nb + cc;
+            const float* rbase = ep.resid ? ep.resid + nb + cc : nullptr;
+#pragma unroll 8
+            for (int it = 0; it < WPR; ++it) {
+              const int r = it * RPI + rr;
+              const int grow = row0 + r;
+              if (grow < M) {
+                float x = stg[r * (WPR + 1) + cc];
+                if (rbase) x += rbase[static_cast<size_t>(grow) * ep.ldr];
+                obase[static_cast<size_t>(grow) * ep.ldo] = x;
               }
             }
-            if (ep.act == MMT_ACT_GELU) {
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; ++j) f[j] = gelu_fast(f[j]);
-            } else if (ep.act == MMT_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (rowadd_row) {
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rowadd_row + nb + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-            if (resid_row) {
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(resid_row + nb + j);
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-            if (ep.out_fp32) {
-              float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nb;
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + nb;
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 8) {
-                uint4 p;
-                p.x = pack_bf16x2(f[j], f[j + 1]);
-                p.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                p.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                p.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = p;
-              }
-            }
+            __syncwarp();
           } else {
-            // ragged / unaligned tail: scalar, bounds-checked
+            constexpr int WPR = CH / 2;         // packed bf16x2 words per row
+            constexpr int RPI = 32 / WPR;
+            uint32_t* stg32 = reinterpret_cast<uint32_t*>(stg);
 #pragma unroll
-            for (int j = 0; j < Cfg::CH; ++j) {
-              const int n = nb + j;
-              if (n >= N) continue;
-              float x = f[j];
-              if (ep.bias) x += ep.bias[n];
-              if (ep.act == MMT_ACT_GELU) x = gelu_fast(x);
-              else if (ep.act == MMT_ACT_RELU) x = fmaxf(x, 0.f);
-              if (rowadd_row) x += rowadd_row[n];
-              if (resid_row) x += resid_row[n];
-              if (ep.out_fp32) reinterpret_cast<float*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = x;
-              else reinterpret_cast<bf16*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = __float2bfloat16_rn(x);
+            for (int j = 0; j < WPR; ++j) stg32[lane * (WPR + 1) + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            __syncwarp();
+            const int cc = lane % WPR, rr = lane / WPR;
+            bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb + 2 * cc;
+#pragma unroll 8
+            for (int it = 0; it < 32 / RPI; ++it) {
+              const int r = it * RPI + rr;
+              const int grow = row0 + r;
+              if (grow < M)
+                *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(grow) * ep.ldo) = stg32[r * (WPR + 1) + cc];
             }
+            __syncwarp();
+          }
+        } else if (row < M) {
+          // ragged / unaligned tail: scalar, bounds-checked, thread == row
+          const float* resid_row = ep.resid ? ep.resid + static_cast<size_t>(row) * ep.ldr : nullptr;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int n = nb + j;
+            if (n >= N) continue;
+            float x = f[j];
+            if (ep.bias) x += ep.bias[n];
+            if (ep.act == MMT_ACT_GELU) x = gelu_fast(x);
+            else if (ep.act == MMT_ACT_RELU) x = fmaxf(x, 0.f);
+            if (rowadd_row) x += rowadd_row[n];
+            if (resid_row) x += resid_row[n];
+            if (ep.out_fp32) reinterpret_cast<float*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = x;
+            else reinterpret_cast<bf16*>(ep.out)[static_cast<size_t>(row) * ep.ldo + n] = __float2bfloat16_rn(x);
           }
         }
       }
@@ -341,14 +367,13 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
   MMT_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0);  // TMA: 16-byte global strides
   MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   MMT_CHECK_ARG(!rowadd || rowadd_period > 0);
-  MMT_CHECK_ARG(!resid || ldr >= N);
+  MMT_CHECK_ARG(!resid || (ldr >= N && out_fp32));  // the residual stream is fp32
   GemmEpi ep;
   ep.bias = bias; ep.resid = resid; ep.rowadd = rowadd; ep.out = out;
   ep.ldr = ldr; ep.rowadd_period = rowadd_period; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
-  const int out_al = out_fp32 ? 4 : 8;
-  ep.vec_ok = (ldo % out_al == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+  // fast path preconditions: float4 loads of bias / rowadd, 4-byte packed bf16x2 stores
+  ep.vec_ok = (out_fp32 || ((ldo % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0))) &&
               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
-              (!resid || ((ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(resid) & 15) == 0)) &&
               (!rowadd || ((N % 4 == 0) && (reinterpret_cast<uintptr_t>(rowadd) & 15) == 0));
   CUtensorMap tmA;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);

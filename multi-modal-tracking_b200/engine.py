@@ -1,0 +1,472 @@
+"""Forward engine: packs a reference-layout state_dict into a device weight arena and runs the per-frame
+tracker forward as a sequence of C-ABI kernel launches (ops.py) on torch's current CUDA stream.
+
+Data layout in HBM (B = sequences in the batched step, N = tokens per sequence-modality):
+  * token tensors are row-major [rows, C]; the residual stream `x` is fp32 [nseq*N, C] with
+    nseq = B (RGB-only) or 2B (RGB-T, modality-major: RGB sequences first, TIR second - the reference's
+    torch.cat([v, i], dim=0), mixformer_shared.py:414-416); inside a sequence the order is
+    [template(64) | online template(64) | search(324)] (mixformer.py:202);
+  * GEMM inputs are `act` dtype = bf16 (fast mode) or fp32 (parity mode); LayerNorm/GroupNorm statistics, the
+    residual stream, softmax state, sampling offsets and the corner soft-argmax are always fp32;
+  * feature maps are NHWC (== token rows); conv weights are packed [O, (ky, kx, c)] with eval-BatchNorm folded;
+  * all workspaces are allocated once per batch size and reused (no allocation inside a step).
+
+No torch compute op is on the path: torch provides memory (torch.empty) and the stream only.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .pos_embed import fusion_pos_table
+
+VIT_DIMS = {"base_patch16": dict(dim=768, depth=12, heads=12), "large_patch16": dict(dim=1024, depth=24, heads=16)}
+STACKED = ("mixformer_vit_rgbt_shared", "mixformer_vit_rgbt_unibackbone", "asymmetric_shared", "asymmetric_shared_ce")
+CROSS_MODAL = ("asymmetric_shared", "asymmetric_shared_ce")
+PER_MODALITY_LN = ("mixformer_vit_rgbt_shared", "asymmetric_shared", "asymmetric_shared_ce")
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class ForwardEngine:
+    def __init__(self, variant, cfg, state_dict, device, precision="bf16"):
+        self.variant = variant
+        self.dev = device
+        self.bf16 = precision == "bf16"
+        self.act = torch.bfloat16 if self.bf16 else torch.float32
+        m = cfg["MODEL"]
+        d = VIT_DIMS[m["VIT_TYPE"]]
+        self.dim, self.depth, self.heads = d["dim"], d["depth"], d["heads"]
+        self.search_size = int(cfg["DATA"]["SEARCH"]["SIZE"])
+        self.template_size = int(cfg["DATA"]["TEMPLATE"]["SIZE"])
+        self.gs, self.gt = self.search_size // 16, self.template_size // 16
+        self.Ls0, self.Lt = self.gs * self.gs, 2 * self.gt * self.gt
+        self.N0 = self.Lt + self.Ls0
+        self.head_type = m["HEAD_TYPE"]
+        if self.head_type != "CORNER_UP":
+            raise NotImplementedError("only the CORNER_UP (pyramid) head - used by every shipped YAML - is on the "
+                                      "accelerated path")
+        self.rgbt = variant != "mixformer_vit"
+        self.fusion_class = m.get("FUSION_CLASS") if self.rgbt else None
+        bb = m.get("BACKBONE", {})
+        self.ce_loc = list(bb["CE_LOC"]) if (variant == "asymmetric_shared_ce" and "CE_LOC" in bb) else []
+        self.ce_keep = list(bb["CE_KEEP_RATIO"]) if self.ce_loc else []
+        self.scale = (self.dim // self.heads) ** -0.5
+        self._ws = {}
+        self._tiles = {}
+        self.aux = {}
+        self._pack(state_dict)
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _w(self, t):
+        return t.detach().to(device=self.dev, dtype=self.act).contiguous()
+
+    def _pack_backbone(self, sd, prefix, per_modality_ln):
+        dev = self.dev
+        g = lambda k: sd[prefix + k]
+        bb = {}
+        bb["pe_w"] = self._w(g("patch_embed.proj.weight").reshape(self.dim, -1))
+        bb["pe_b"] = _f32(g("patch_embed.proj.bias"), dev)
+        pt, ps = g("pos_embed_t")[0], g("pos_embed_s")[0]
+        bb["pos"] = _f32(torch.cat([pt, pt, ps], dim=0), dev)          # [N0, dim]
+        blocks = []
+        for i in range(self.depth):
+            p = f"blocks.{i}."
+            b = {}
+            for j in (1, 2):
+                if per_modality_ln:
+                    b[f"ln{j}"] = (_f32(g(p + f"norm{j}_v.weight"), dev), _f32(g(p + f"norm{j}_v.bias"), dev),
+                                   _f32(g(p + f"norm{j}_i.weight"), dev), _f32(g(p + f"norm{j}_i.bias"), dev))
+                else:
+                    b[f"ln{j}"] = (_f32(g(p + f"norm{j}.weight"), dev), _f32(g(p + f"norm{j}.bias"), dev), None, None)
+            for name, key in (("qkv", "attn.qkv"), ("proj", "attn.proj"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2")):
+                b[name + "_w"] = self._w(g(p + key + ".weight"))
+                b[name + "_b"] = _f32(g(p + key + ".bias"), dev)
+            blocks.append(b)
+        bb["blocks"] = blocks
+        return bb
+
+    @staticmethod
+    def _fold_bn(sd, name):
+        """conv3x3 + eval BatchNorm2d / FrozenBatchNorm2d -> (W[O, (ky,kx,c)], b[O]) fp32
+        (head.py:7-20; utils.py:47-57: scale = w * rsqrt(var + 1e-5))."""
+        w = sd[name + ".0.weight"].detach().float()
+        b = sd[name + ".0.bias"].detach().float()
+        scale = sd[name + ".1.weight"].detach().float() * (sd[name + ".1.running_var"].detach().float() + 1e-5).rsqrt()
+        shift = sd[name + ".1.bias"].detach().float() - sd[name + ".1.running_mean"].detach().float() * scale
+        wp = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        return wp, b * scale + shift
+
+    def _pack_head(self, sd):
+        dev = self.dev
+        H = {}
+        fold = lambda n: self._fold_bn(sd, "box_head." + n)
+        ws, bs, self.s1_cols = [], [], {}
+        col = 0
+        for n in ("conv1_tl", "conv1_br", "adjust1_tl", "adjust1_br", "adjust2_tl", "adjust2_br"):
+            w, b = fold(n)
+            self.s1_cols[n] = (col, col + w.shape[0])
+            col += w.shape[0]
+            ws.append(w)
+            bs.append(b)
+        H["s1_w"], H["s1_b"] = self._w(torch.cat(ws, 0)), _f32(torch.cat(bs, 0), dev)
+        self.s1_width = col
+        for c in ("tl", "br"):
+            for n in (f"conv2_{c}", f"conv3_{c}", f"conv4_{c}", f"adjust3_{c}.0", f"adjust3_{c}.1", f"adjust3_{c}.2",
+                      f"adjust4_{c}.0", f"adjust4_{c}.1"):
+                w, b = fold(n)
+                H[n + "_w"], H[n + "_b"] = self._w(w), _f32(b, dev)
+            H[f"w5_{c}"] = _f32(sd[f"box_head.conv5_{c}.weight"].reshape(-1), dev)
+            H[f"b5_{c}"] = float(sd[f"box_head.conv5_{c}.bias"].detach().float().reshape(-1)[0])
+        self.head_ch = sd["box_head.conv1_tl.0.weight"].shape[0]
+        return H
+
+    def _pack_fusion(self, sd):
+        dev = self.dev
+        F = {}
+        g = lambda k: sd["fusion_vi." + k]
+        cls = self.fusion_class
+        from .builders import FUSION_CLASSES
+        if cls not in FUSION_CLASSES:
+            raise KeyError(f"FUSION_CLASS {cls!r} is not on the accelerated path")
+        self.d_model = g("fusion_attention.level_embed").shape[1]
+        names_in = ("adjust_in", "adjust_in") if cls.endswith("_2") else ("adjust_v", "adjust_i")
+        F["in"] = [dict(w=self._w(g(n + ".0.weight").reshape(self.d_model, -1)), b=_f32(g(n + ".0.bias"), dev),
+                        gn_w=_f32(g(n + ".1.weight"), dev), gn_b=_f32(g(n + ".1.bias"), dev)) for n in names_in]
+        F["pos"] = fusion_pos_table(self.gs, self.gs, self.d_model, g("fusion_attention.level_embed")).to(dev)
+        layers = []
+        i = 0
+        while f"fusion_vi.fusion_attention.encoder.layers.{i}.linear1.weight" in sd:
+            p = f"fusion_attention.encoder.layers.{i}."
+            L = {}
+            L["offw_w"] = self._w(torch.cat([g(p + "self_attn.sampling_offsets.weight"),
+                                             g(p + "self_attn.attention_weights.weight")], 0))
+            L["offw_b"] = _f32(torch.cat([g(p + "self_attn.sampling_offsets.bias"),
+                                          g(p + "self_attn.attention_weights.bias")], 0), dev)
+            for nm, key in (("val", "self_attn.value_proj"), ("out", "self_attn.output_proj"), ("l1", "linear1"),
+                            ("l2", "linear2")):
+                L[nm + "_w"], L[nm + "_b"] = self._w(g(p + key + ".weight")), _f32(g(p + key + ".bias"), dev)
+            for j in (1, 2):
+                L[f"ln{j}"] = tuple(_f32(g(p + f"norm{j}_{mm}.{wb}"), dev) for mm in ("v", "i") for wb in ("weight", "bias"))
+            layers.append(L)
+            i += 1
+        F["layers"] = layers
+        self.n_heads_f = 8
+        self.n_points_f = L["offw_w"].shape[0] // (self.n_heads_f * 2 * 3)
+        self.d_ffn = layers[0]["l1_w"].shape[0]
+        if cls.endswith("_Sum") or cls.endswith("_2"):
+            n = "adjust_sum" if cls.endswith("_Sum") else "adjust_out"
+            w = g(n + ".0.weight").reshape(-1, self.d_model)
+            w = torch.cat([w, w], dim=1)        # conv(out_v + out_i) == [out_v | out_i] @ [W | W]^T
+        else:
+            n = "adjust_cat"
+            w = g(n + ".0.weight").reshape(-1, 2 * self.d_model)
+        F["out"] = dict(w=self._w(w), b=_f32(g(n + ".0.bias"), dev), gn_w=_f32(g(n + ".1.weight"), dev),
+                        gn_b=_f32(g(n + ".1.bias"), dev))
+        return F
+
+    def _pack(self, sd):
+        if self.variant == "mixformer_vit":
+            self.bbs = [self._pack_backbone(sd, "backbone.", False)]
+        elif self.variant == "mixformer_vit_rgbt":
+            self.bbs = [self._pack_backbone(sd, "backbone_v.", False), self._pack_backbone(sd, "backbone_i.", False)]
+        elif self.variant in STACKED:
+            self.bbs = [self._pack_backbone(sd, "backbone.", self.variant in PER_MODALITY_LN)]
+        else:
+            raise KeyError(self.variant)
+        self.head = self._pack_head(sd)
+        self.fusion = self._pack_fusion(sd) if self.rgbt else None
+
+    # ------------------------------------------------------------------------------------------ workspaces
+    def _buf(self, B, name, shape, dtype):
+        key = (B, name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.dev, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def _attn_tiles(self, kind, nseq, N, Ls):
+        """Host-built per-tile key-segment table (see mmt_mixattn_fwd).  kind: 'sym' or 'cross'."""
+        key = (kind, nseq, N, Ls)
+        hit = self._tiles.get(key)
+        if hit is not None:
+            return hit
+        Lt = self.Lt
+        recs = []
+
+        def add(q0, qn, segs):
+            for o in range(0, qn, 64):
+                r = [q0 + o, min(64, qn - o), q0 + o, len(segs)]
+                rows = [s[0] for s in segs] + [0] * (3 - len(segs))
+                lens = [s[1] for s in segs] + [0] * (3 - len(segs))
+                recs.append(r + rows + lens + [0, 0, 0] + [0, 0, 0])
+
+        if kind == "sym":
+            for s in range(nseq):
+                base = s * N
+                add(base, Lt, [(base, Lt)])
+                add(base + Lt, Ls, [(base, Lt + Ls)])
+            max_keys = Lt + Ls
+        else:
+            B = nseq // 2
+            for m in range(2):
+                for b in range(B):
+                    base = (m * B + b) * N
+                    add(base, Lt, [(base, Lt)])
+                    add(base + Lt, Ls, [(b * N, Lt), ((B + b) * N, Lt), (base + Lt, Ls)])
+            max_keys = 2 * Lt + Ls
+        t = torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev)
+        self._tiles[key] = (t, max_keys)
+        return self._tiles[key]
+
+    # ------------------------------------------------------------------------------------------ backbone
+    def _embed(self, bb, B, imgs_t, imgs_ot, imgs_s, x):
+        """Patch-embed the three crops of `B` sequences into x [B*N0, dim] (rows b*N0 + [t | ot | s])."""
+        patches = self._buf(B, "patches", (x.shape[0], 3 * 256), self.act)
+        n_t = self.gt * self.gt
+        ops.patchify(imgs_t, patches, 0, self.N0)
+        ops.patchify(imgs_ot, patches, n_t, self.N0)
+        ops.patchify(imgs_s, patches, 2 * n_t, self.N0)
+        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos"], out=x)
+
+    def _block(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep=None, gidx=None):
+        """One pre-LN block on x [nseq*N, dim] fp32 (in place).  Returns (x, N, Ls, gidx) - changed by CE."""
+        M = nseq * N
+        dim = self.dim
+        h = self._buf(tag, "h", (M, dim), self.act)
+        qkv = self._buf(tag, "qkv", (M, 3 * dim), self.act)
+        att = self._buf(tag, "att", (M, dim), self.act)
+        g0, b0, g1, b1 = blk["ln1"]
+        self._ln(x, g0, b0, g1, b1, ln_period, 1e-6, h)
+        ops.gemm(h, blk["qkv_w"], blk["qkv_b"], out=qkv)
+        tiles, max_keys = self._attn_tiles("cross" if cross else "sym", nseq, N, Ls)
+        ops.mixattn(qkv, None, dim, self.heads, tiles, max_keys, att, self.scale)
+        ops.gemm(att, blk["proj_w"], blk["proj_b"], ops.ACT_NONE, x, None, out=x)
+        if ce_keep is not None:
+            x, N, Ls, gidx = self._candidate_elimination(qkv, x, nseq, N, Ls, ce_keep, gidx, tag)
+            M = nseq * N
+            h = self._buf(tag, "h", (M, dim), self.act)
+        g0, b0, g1, b1 = blk["ln2"]
+        self._ln(x, g0, b0, g1, b1, nseq * N // 2 if ln_period else 0, 1e-6, h)
+        hid = self._buf(tag, "hid", (M, 4 * dim), self.act)
+        ops.gemm(h, blk["fc1_w"], blk["fc1_b"], ops.ACT_GELU, out=hid)
+        ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], ops.ACT_NONE, x, None, out=x)
+        return x, N, Ls, gidx
+
+    def _ln(self, x, g0, b0, g1, b1, period, eps, out):
+        if self.bf16:
+            ops.layernorm(x, g0, b0, g1, b1, period, eps, out_bf16=out)
+        else:
+            ops.layernorm(x, g0, b0, g1, b1, period, eps, out_f32=out)
+
+    def _candidate_elimination(self, qkv, x, nseq, N, Ls, keep_ratio, gidx, tag):
+        """asymmetric_shared_ce.py:49-101 (test-time branch: no template mask)."""
+        keep = math.ceil(keep_ratio * Ls)
+        if keep == Ls:
+            return x, N, Ls, gidx
+        B = nseq // 2
+        nqt = 2 * self.Lt // 32
+        partial = self._buf(tag, "ce_partial", (B * self.heads * nqt * 2 * Ls,), torch.float32)
+        scores = torch.empty((B, 2 * Ls), device=self.dev, dtype=torch.float32)
+        ops.ce_scores(qkv, self.dim, self.heads, B, N, self.Lt, Ls, self.scale, partial, scores)
+        g_keep = torch.empty((nseq, keep), device=self.dev, dtype=torch.float32)
+        g_rem = torch.empty((nseq, Ls - keep), device=self.dev, dtype=torch.float32)
+        order = torch.empty((nseq, Ls), device=self.dev, dtype=torch.int32)
+        ops.ce_topk(scores, B, Ls, keep, gidx, g_keep, g_rem, order)
+        n_new = self.Lt + keep
+        x_new = torch.empty((nseq * n_new, self.dim), device=self.dev, dtype=torch.float32)
+        ops.ce_gather_tokens(x, nseq, N, self.Lt, order, Ls, keep, x_new)
+        self.aux["ce_scores"].append(scores)
+        self.aux["ce_keep"].append(g_keep)
+        self.aux["ce_removed"].append(g_rem)
+        return x_new, n_new, keep, g_keep
+
+    def _run_backbone(self, bb, x, nseq, tag, stacked):
+        """All blocks on x [nseq*N0, dim]; returns the search-token rows [nseq*Ls0, dim] in `act` dtype."""
+        N, Ls = self.N0, self.Ls0
+        cross = stacked and self.variant in CROSS_MODAL
+        per_ln = stacked and self.variant in PER_MODALITY_LN
+        gidx = None
+        if self.ce_loc:
+            gidx = torch.arange(Ls, device=self.dev, dtype=torch.float32).repeat(nseq, 1).contiguous()
+            self.aux.update(ce_scores=[], ce_keep=[], ce_removed=[])
+        ce_i = 0
+        for i, blk in enumerate(bb["blocks"]):
+            ce_keep = None
+            if i in self.ce_loc:
+                ce_keep = self.ce_keep[ce_i]
+                ce_i += 1
+                if not ce_keep < 1:
+                    ce_keep = None
+            x, N, Ls, gidx = self._block(blk, x, nseq, N, Ls, (nseq * N // 2) if per_ln else 0, cross, tag, ce_keep, gidx)
+        feat = self._buf(tag, "search_rows", (nseq * self.Ls0, self.dim), self.act)
+        if Ls != self.Ls0:
+            ops.ce_recover(x, nseq, N, self.Lt, gidx, Ls, self.Ls0, feat)
+        else:
+            ops.copy_rows(x, N, self.Lt, Ls, nseq, feat)
+        return feat
+
+    # ------------------------------------------------------------------------------------------ fusion
+    def _conv1x1_gn(self, a, p, B, HW, out, tag, out_seq_rows=0, out_row_off=0):
+        """Conv2d(k=1) + GroupNorm(32) (fusion_utils.py:252-268); `out` dtype selects the fp32 / bf16 output."""
+        C = p["w"].shape[0]
+        pre = self._buf(tag, "gn_pre", (B * HW, C), torch.float32)
+        ops.gemm(a, p["w"], p["b"], out=pre)
+        if out.dtype == torch.float32:
+            ops.groupnorm(pre, B, HW, 32, p["gn_w"], p["gn_b"], 1e-5, out_f32=out, out_seq_rows=out_seq_rows,
+                          out_row_off=out_row_off)
+        else:
+            ops.groupnorm(pre, B, HW, 32, p["gn_w"], p["gn_b"], 1e-5, out_bf16=out, out_seq_rows=out_seq_rows,
+                          out_row_off=out_row_off)
+
+    def _run_fusion(self, sv, si, B):
+        """fusion_vi (fusion_utils.py:270-279 and variants) on search-token rows sv, si [B*HW, 768] -> [B*HW, 768]."""
+        F_ = self.fusion
+        HW, d, L = self.Ls0, self.d_model, self.Ls0
+        tag = ("fus", B)
+        src = self._buf(tag, "src", (B, 2 * HW, d), torch.float32)
+        # per-modality 1x1 conv + GroupNorm written into the two halves of each sequence's token block
+        for m, a in enumerate((sv, si)):
+            self._conv1x1_gn(a, F_["in"][m], B, HW, src, tag, out_seq_rows=2 * HW, out_row_off=m * HW)
+        src2 = src.view(B * 2 * HW, d)
+        val_in = self._buf(tag, "val_in", (B * 2 * HW, d), self.act)
+        q_in = self._buf(tag, "q_in", (B * HW, 2 * d), self.act)
+        value = self._buf(tag, "value", (B * 2 * HW, d), self.act)
+        offw = self._buf(tag, "offw", (B * HW, F_["layers"][0]["offw_w"].shape[0]), torch.float32)
+        samp = self._buf(tag, "samp", (B * 2 * HW, d), self.act)
+        hid = self._buf(tag, "ffn", (B * 2 * HW, self.d_ffn), self.act)
+        src_act = self._buf(tag, "src_act", (B * 2 * HW, d), self.act)
+        for Lw in F_["layers"]:
+            ops.fusion_prep(src2, F_["pos"], B, HW, val_in, q_in)
+            ops.gemm(val_in, Lw["val_w"], Lw["val_b"], out=value)
+            ops.gemm(q_in, Lw["offw_w"], Lw["offw_b"], out=offw)
+            ops.msda_bimodal(value, offw, samp, B, self.gs, self.gs, self.n_heads_f, d // self.n_heads_f, self.n_points_f)
+            ops.gemm(samp, Lw["out_w"], Lw["out_b"], ops.ACT_NONE, src2, None, out=src2)
+            g0, b0, g1, b1 = Lw["ln1"]
+            if self.bf16:
+                ops.layernorm(src2, g0, b0, g1, b1, HW, 1e-5, out_f32=src2, out_bf16=src_act)
+                a_in = src_act
+            else:
+                ops.layernorm(src2, g0, b0, g1, b1, HW, 1e-5, out_f32=src2)
+                a_in = src2
+            ops.gemm(a_in, Lw["l1_w"], Lw["l1_b"], ops.ACT_RELU, out=hid)
+            ops.gemm(hid, Lw["l2_w"], Lw["l2_b"], ops.ACT_NONE, src2, None, out=src2)
+            g0, b0, g1, b1 = Lw["ln2"]
+            ops.layernorm(src2, g0, b0, g1, b1, HW, 1e-5, out_f32=src2)
+        cat_in = self._buf(tag, "cat_in", (B * HW, 2 * d), self.act)
+        ops.fusion_prep(src2, None, B, HW, None, cat_in)
+        fused = self._buf(tag, "fused", (B * HW, 768), self.act)
+        self._conv1x1_gn(cat_in, F_["out"], B, HW, fused, (tag, "o"))
+        return fused
+
+    # ------------------------------------------------------------------------------------------ head
+    def _run_head(self, feat, B, want_maps=True):
+        """Pyramid corner head on NHWC rows feat [B*gs*gs, C] -> boxes cxcywh [B,4] (+ raw score maps)."""
+        H = self.head
+        gs = self.gs
+        ch = self.head_ch                       # 384
+        C = feat.shape[1]
+        tag = ("head", B)
+        n18, n36, n72 = B * gs * gs, B * 4 * gs * gs, B * 16 * gs * gs
+        colmax = max(n18 * 9 * C, n36 * 9 * (ch // 2), n72 * 9 * (ch // 4))
+        col = self._buf(tag, "col", (colmax,), self.act)
+        view = lambda rows, k: col[: rows * k].view(rows, k)
+        s1 = self._buf(tag, "s1", (n18, self.s1_width), self.act)
+        ops.gemm(ops.im2col3x3(feat, 1, B, gs, gs, C, view(n18, 9 * C)), H["s1_w"], H["s1_b"], ops.ACT_RELU, out=s1)
+        sl = lambda n: s1[:, self.s1_cols[n][0]: self.s1_cols[n][1]]
+        x4s, a3s, a4s = [], [], []
+        for c in ("tl", "br"):
+            x2 = self._buf(tag, "x2" + c, (n18, ch // 2), self.act)
+            ops.gemm(ops.im2col3x3(sl(f"conv1_{c}"), 1, B, gs, gs, ch, view(n18, 9 * ch)), H[f"conv2_{c}_w"],
+                     H[f"conv2_{c}_b"], ops.ACT_RELU, out=x2)
+            # up-1: conv3(up2(adjust1(x)) + up2(x2)) at 2gs x 2gs
+            x3 = self._buf(tag, "x3" + c, (n36, ch // 4), self.act)
+            ops.gemm(ops.im2col3x3(sl(f"adjust1_{c}"), 2, B, 2 * gs, 2 * gs, ch // 2, view(n36, 9 * (ch // 2)), x2, 2),
+                     H[f"conv3_{c}_w"], H[f"conv3_{c}_b"], ops.ACT_RELU, out=x3)
+            # up-2: conv4(up4(adjust2(x)) + up2(x3)) at 4gs x 4gs
+            x4 = self._buf(tag, "x4" + c, (n72, ch // 8), self.act)
+            ops.gemm(ops.im2col3x3(sl(f"adjust2_{c}"), 4, B, 4 * gs, 4 * gs, ch // 4, view(n72, 9 * (ch // 4)), x3, 2),
+                     H[f"conv4_{c}_w"], H[f"conv4_{c}_b"], ops.ACT_RELU, out=x4)
+            # side branches: adjust3 on x2 (gs), adjust4 on x3 (2gs)
+            a = x2
+            for j, co in enumerate((ch // 4, ch // 8, 1)):
+                o = self._buf(tag, f"a3{c}{j}", (n18, co), self.act)
+                ops.gemm(ops.im2col3x3(a, 1, B, gs, gs, a.shape[1], view(n18, 9 * a.shape[1])), H[f"adjust3_{c}.{j}_w"],
+                         H[f"adjust3_{c}.{j}_b"], ops.ACT_RELU, out=o)
+                a = o
+            a3s.append(a)
+            a = x3
+            for j, co in enumerate((ch // 8, 1)):
+                o = self._buf(tag, f"a4{c}{j}", (n36, co), self.act)
+                ops.gemm(ops.im2col3x3(a, 1, B, 2 * gs, 2 * gs, a.shape[1], view(n36, 9 * a.shape[1])),
+                         H[f"adjust4_{c}.{j}_w"], H[f"adjust4_{c}.{j}_b"], ops.ACT_RELU, out=o)
+                a = o
+            a4s.append(a)
+            x4s.append(x4)
+        S = 4 * gs
+        maps = torch.empty((B, 2, S * S), device=self.dev, dtype=torch.float32) if want_maps else None
+        xyxy = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
+        boxes = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
+        ops.corner_decode(x4s, (H["w5_tl"], H["w5_br"]), (H["b5_tl"], H["b5_br"]), a3s, a4s, B, S, 4.0,
+                          float(self.search_size), xyxy, boxes, maps)
+        return boxes, maps
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _check_img(self, t, size):
+        if not t.is_cuda:
+            raise NotImplementedError("mmt_b200 forward is CUDA-only (no CPU fallback)")
+        if t.dim() != 4 or t.shape[1] != 3 or t.shape[2] != size or t.shape[3] != size:
+            raise RuntimeError(f"expected a [B,3,{size},{size}] crop, got {tuple(t.shape)}")
+        return t.float().contiguous() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+    def forward(self, template, online_template, search, want_maps=True):
+        self.aux = {}
+        if not self.rgbt:
+            t, ot, s = (self._check_img(template, self.template_size), self._check_img(online_template, self.template_size),
+                        self._check_img(search, self.search_size))
+            B = s.shape[0]
+            x = self._buf(B, "x", (B * self.N0, self.dim), torch.float32)
+            self._embed(self.bbs[0], B, t, ot, s, x)
+            feat = self._run_backbone(self.bbs[0], x, B, ("bb", B), False)
+            boxes, maps = self._run_head(feat, B, want_maps)
+            return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feat)
+        t = [self._check_img(v, self.template_size) for v in template]
+        ot = [self._check_img(v, self.template_size) for v in online_template]
+        s = [self._check_img(v, self.search_size) for v in search]
+        B = s[0].shape[0]
+        M1 = B * self.N0
+        x = self._buf(B, "x", (2 * M1, self.dim), torch.float32)
+        if self.variant == "mixformer_vit_rgbt":      # two independent streams (mixformer.py:379-380)
+            feats = []
+            for m in range(2):
+                xm = x[m * M1:(m + 1) * M1]
+                self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm)
+                feats.append(self._run_backbone(self.bbs[m], xm, B, ("bb", B, m), False))
+            sv, si = feats
+        else:                                          # batch-stacked modalities, shared weights
+            for m in range(2):
+                self._embed(self.bbs[0], B, t[m], ot[m], s[m], x[m * M1:(m + 1) * M1])
+            f = self._run_backbone(self.bbs[0], x, 2 * B, ("bb", B), True)
+            sv, si = f[: B * self.Ls0], f[B * self.Ls0:]
+        fused = self._run_fusion(sv, si, B)
+        boxes, maps = self._run_head(fused, B, want_maps)
+        res = dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=fused, search_rows=(sv, si), **self.aux)
+        return res
+
+    def forward_head_only(self, search_feat):
+        """Corner head on an NCHW feature map (forward_box_head, mixformer.py:325-338)."""
+        B, C, H, W = search_feat.shape
+        rows = search_feat.permute(0, 2, 3, 1).reshape(B * H * W, C).to(self.act).contiguous()   # layout plumbing
+        boxes, maps = self._run_head(rows, B, True)
+        return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps)
+
+    def rows_to_map(self, rows, B):
+        """Token rows [B*gs*gs, C] -> the reference's [B, C, gs, gs] fp32 feature map (output formatting for
+        return_features=True; not on the box path)."""
+        return rows.view(B, self.gs, self.gs, -1).permute(0, 3, 1, 2).float().contiguous()

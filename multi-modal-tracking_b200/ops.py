@@ -73,3 +73,183 @@ def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_d
                        c_int(out.stride(0)), _stream())
         _lib.check(st, "mmt_gemm_f32")
     return out
+
+
+# --------------------------------------------------------------------------------------------- row kernels
+_patchify = _lib.fn("mmt_patchify")
+_layernorm = _lib.fn("mmt_layernorm")
+_groupnorm = _lib.fn("mmt_groupnorm")
+_copy_rows = _lib.fn("mmt_copy_rows")
+_fusion_prep = _lib.fn("mmt_fusion_prep")
+_im2col3x3 = _lib.fn("mmt_im2col3x3")
+_corner_decode = _lib.fn("mmt_corner_decode")
+_msda = _lib.fn("mmt_msda_fwd")
+_msda_bimodal = _lib.fn("mmt_msda_bimodal_fwd")
+_mixattn = _lib.fn("mmt_mixattn_fwd")
+_ce_scores = _lib.fn("mmt_ce_scores")
+_ce_topk = _lib.fn("mmt_ce_topk")
+_ce_gather = _lib.fn("mmt_ce_gather_tokens")
+_ce_recover = _lib.fn("mmt_ce_recover")
+_prroi = _lib.fn("mmt_prroi_fwd")
+
+
+def _is_bf16(t):
+    if t.dtype == torch.bfloat16:
+        return 1
+    assert t.dtype == torch.float32, t.dtype
+    return 0
+
+
+def patchify(img, out, tok_off, tok_per_seq, patch=16):
+    """img fp32 NCHW [B,Cin,H,W] -> rows of `out` [.., Cin*P*P] at b*tok_per_seq + tok_off + patch index."""
+    _need_cuda(img, out)
+    assert img.dtype == torch.float32 and img.is_contiguous() and out.is_contiguous()
+    B, Cin, H, W = img.shape
+    assert out.shape[1] == Cin * patch * patch
+    _lib.check(_patchify(_ptr(img), _ptr(out), c_int(B), c_int(Cin), c_int(H), c_int(W), c_int(patch),
+                         c_int(tok_off), c_int(tok_per_seq), c_int(_is_bf16(out)), _stream()), "mmt_patchify")
+    return out
+
+
+def layernorm(x, g0, b0, g1=None, b1=None, period=0, eps=1e-6, out_f32=None, out_bf16=None):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    rows, C = x.shape
+    for o in (out_f32, out_bf16):
+        assert o is None or (o.shape == x.shape and o.is_contiguous())
+    assert out_f32 is None or out_f32.dtype == torch.float32
+    assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
+    _lib.check(_layernorm(_ptr(x), c_int(rows), c_int(C), c_float(eps), _ptr(g0), _ptr(b0), _ptr(g1), _ptr(b1),
+                          c_int(period), _ptr(out_f32), _ptr(out_bf16), _stream()), "mmt_layernorm")
+
+
+def groupnorm(x, B, HW, groups, gamma, beta, eps=1e-5, out_f32=None, out_bf16=None, out_seq_rows=0, out_row_off=0):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == B * HW
+    assert out_f32 is None or out_f32.dtype == torch.float32
+    assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
+    C = x.shape[1]
+    _lib.check(_groupnorm(_ptr(x), c_int(B), c_int(HW), c_int(C), c_int(groups), c_float(eps), _ptr(gamma),
+                          _ptr(beta), _ptr(out_f32), _ptr(out_bf16), c_int(out_seq_rows), c_int(out_row_off),
+                          _stream()), "mmt_groupnorm")
+
+
+def copy_rows(src, seq_stride, row_off, rows_per_seq, nseq, dst):
+    _need_cuda(src, dst)
+    assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    C = src.shape[-1]
+    _lib.check(_copy_rows(_ptr(src), c_int(seq_stride), c_int(row_off), c_int(rows_per_seq), c_int(nseq), c_int(C),
+                          _ptr(dst), c_int(_is_bf16(dst)), _stream()), "mmt_copy_rows")
+    return dst
+
+
+def fusion_prep(src, pos, B, L, out_val=None, out_q=None):
+    _need_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    C = src.shape[-1]
+    ref = out_val if out_val is not None else out_q
+    _lib.check(_fusion_prep(_ptr(src), _ptr(pos), c_int(B), c_int(L), c_int(C), _ptr(out_val), _ptr(out_q),
+                            c_int(_is_bf16(ref)), _stream()), "mmt_fusion_prep")
+
+
+def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
+    """src maps are [B*(H/s)*(W/s), ld] row views (channel slices allowed); out [B*H*W, 9*C] contiguous."""
+    _need_cuda(src1, out)
+    assert src1.stride(1) == 1 and out.is_contiguous() and out.shape == (B * H * W, 9 * C)
+    assert src2 is None or (src2.stride(1) == 1 and src2.dtype == src1.dtype)
+    _lib.check(_im2col3x3(_ptr(src1), c_int(src1.stride(0)), c_int(s1), _ptr(src2),
+                          c_int(src2.stride(0) if src2 is not None else 0), c_int(s2), c_int(B), c_int(H), c_int(W),
+                          c_int(C), _ptr(out), c_int(_is_bf16(out)), _stream()), "mmt_im2col3x3")
+    return out
+
+
+def corner_decode(x4, w5, b5, a3, a4, B, S, stride_px, img_sz, xyxy, cxcywh, score_maps=None):
+    """x4/a3/a4: (tl, br) pairs of row views; w5: (tl, br) fp32 [C4]; b5: (tl, br) floats."""
+    _need_cuda(x4[0], xyxy, cxcywh)
+    C4 = w5[0].numel()
+    assert x4[0].stride(0) == x4[1].stride(0) and a3[0].stride(0) == a3[1].stride(0) and a4[0].stride(0) == a4[1].stride(0)
+    _lib.check(_corner_decode(_ptr(x4[0]), _ptr(x4[1]), c_int(x4[0].stride(0)), c_int(C4), _ptr(w5[0]), _ptr(w5[1]),
+                              c_float(b5[0]), c_float(b5[1]), _ptr(a3[0]), _ptr(a3[1]), c_int(a3[0].stride(0)),
+                              _ptr(a4[0]), _ptr(a4[1]), c_int(a4[0].stride(0)), c_int(B), c_int(S),
+                              c_float(stride_px), c_float(img_sz), _ptr(score_maps), _ptr(xyxy), _ptr(cxcywh),
+                              c_int(_is_bf16(x4[0])), _stream()), "mmt_corner_decode")
+
+
+def msda(value, level_hw, sampling_loc, attn_weight, out=None):
+    """Reference-layout MSDA forward: value [N,S,M,D], loc [N,Lq,M,L,P,2], attn [N,Lq,M,L,P] -> [N,Lq,M*D]."""
+    _need_cuda(value, sampling_loc, attn_weight)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    value = value.contiguous()
+    loc = sampling_loc.float().contiguous()
+    aw = attn_weight.float().contiguous()
+    if out is None:
+        out = torch.empty((N, Lq, M * D), device=value.device, dtype=value.dtype)
+    hw = (c_int * (2 * L))(*[int(v) for pair in level_hw for v in pair])
+    _lib.check(_msda(_ptr(value), hw, _ptr(loc), _ptr(aw), _ptr(out), c_int(N), c_int(S), c_int(M), c_int(D),
+                     c_int(L), c_int(Lq), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_fwd")
+    return out
+
+
+def msda_bimodal(value, offw, out, B, H, W, M=8, D=64, P=4):
+    _need_cuda(value, offw, out)
+    assert offw.dtype == torch.float32 and offw.stride(1) == 1 and value.is_contiguous() and out.is_contiguous()
+    _lib.check(_msda_bimodal(_ptr(value), _ptr(offw), c_int(offw.stride(0)), _ptr(out), c_int(B), c_int(H), c_int(W),
+                             c_int(M), c_int(D), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_bimodal_fwd")
+    return out
+
+
+def mixattn(qkv0, qkv1, C, heads, tiles, max_keys, out, scale):
+    _need_cuda(qkv0, tiles, out)
+    assert tiles.dtype == torch.int32 and tiles.is_contiguous() and tiles.shape[1] == 16
+    assert qkv0.stride(1) == 1 and out.stride(1) == 1
+    _lib.check(_mixattn(_ptr(qkv0), _ptr(qkv1), c_int(qkv0.stride(0)), c_int(C), c_int(heads), _ptr(tiles),
+                        c_int(tiles.shape[0]), c_int(max_keys), _ptr(out), c_int(out.stride(0)), c_float(scale),
+                        c_int(_is_bf16(qkv0)), _stream()), "mmt_mixattn_fwd")
+    return out
+
+
+def ce_scores(qkv, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, scores):
+    _need_cuda(qkv, partial_ws, scores)
+    _lib.check(_ce_scores(_ptr(qkv), c_int(qkv.stride(0)), c_int(C), c_int(heads), c_int(B), c_int(n_tok), c_int(Lt),
+                          c_int(Ls), c_float(scale), _ptr(partial_ws), _ptr(scores), c_int(_is_bf16(qkv)), _stream()),
+               "mmt_ce_scores")
+    return scores
+
+
+def ce_topk(scores, B, Ls, keep, gidx_in, gidx_keep, gidx_removed, order):
+    _need_cuda(scores, gidx_in, gidx_keep, gidx_removed, order)
+    assert order.dtype == torch.int32
+    _lib.check(_ce_topk(_ptr(scores), c_int(B), c_int(Ls), c_int(keep), _ptr(gidx_in), _ptr(gidx_keep),
+                        _ptr(gidx_removed), _ptr(order), _stream()), "mmt_ce_topk")
+
+
+def ce_gather_tokens(x, nseq, n_tok, Lt, order, Ls, keep, x_out):
+    _need_cuda(x, order, x_out)
+    _lib.check(_ce_gather(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(order), c_int(Ls), c_int(keep),
+                          _ptr(x_out), c_int(x.shape[-1]), _stream()), "mmt_ce_gather_tokens")
+
+
+def ce_recover(x, nseq, n_tok, Lt, gidx, Lk, Ls0, out):
+    _need_cuda(x, gidx, out)
+    _lib.check(_ce_recover(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(gidx), c_int(Lk), c_int(Ls0),
+                           _ptr(out), c_int(x.shape[-1]), c_int(_is_bf16(out)), _stream()), "mmt_ce_recover")
+
+
+def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None):
+    """feat fp32 [N,C,H,W] (or [N,H,W,C] with channels_last) ; rois fp32 [R,5] -> [R,C,ph,pw] (or [R,ph*pw,C])."""
+    _need_cuda(feat, rois)
+    feat = feat.contiguous()
+    rois = rois.contiguous()
+    assert feat.dtype == torch.float32 and rois.dtype == torch.float32
+    if channels_last:
+        N, H, W, C = feat.shape
+        shape = (rois.shape[0], ph * pw, C)
+    else:
+        N, C, H, W = feat.shape
+        shape = (rois.shape[0], C, ph, pw)
+    if out is None:
+        out = torch.empty(shape, device=feat.device, dtype=torch.float32)
+    _lib.check(_prroi(_ptr(feat), _ptr(rois), _ptr(out), c_int(rois.shape[0]), c_int(C), c_int(H), c_int(W), c_int(ph),
+                      c_int(pw), c_float(spatial_scale), c_int(1 if channels_last else 0), _stream()), "mmt_prroi_fwd")
+    return out

@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE - pins the oracle against the UNMODIFIED reference and writes golden vectors.
+
+Runs only in the build container (needs /root/reference).  For every variant on the accelerated path:
+  1. build the mmt_b200 model with seeded, sharpened weights (multi-modal-tracking_b200/synthetic.py);
+  2. build the reference model from its own shipped YAML (oracle/ref_shims.py) and load OUR state_dict into it
+     with strict=True  -> pins the checkpoint key/shape layout of the drop-in builders;
+  3. run the reference forward and oracle/mixformer_oracle.forward on the same seeded N(0,1) inputs (CPU fp32)
+     and require agreement to float round-off  -> pins the oracle;
+  4. save the REFERENCE's outputs (boxes, corner score maps via a forward hook on the head, CE kept indices via a
+     hook on the CE blocks) to tests/golden/<variant>_b<B>.npz.
+Usage:  python oracle/gen_golden.py [variant ...]
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mmt_b200  # noqa: E402,F401
+from mmt_b200 import synthetic  # noqa: E402
+from oracle import mixformer_oracle as O  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+BATCH = 2
+WEIGHT_SEED, INPUT_SEED = 0, 1
+
+
+def run_reference(variant, sd, inputs):
+    model, rcfg = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant])
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    cap = {}
+    head = model.box_head
+    orig = head.get_score_map
+
+    def hooked(x):
+        tl, br = orig(x)
+        cap["maps"] = torch.stack([tl.flatten(1), br.flatten(1)], dim=1)
+        cap["feat"] = x
+        return tl, br
+
+    head.get_score_map = hooked
+    keeps_v, keeps_i = [], []
+    if variant == "asymmetric_shared_ce":
+        for i, blk in enumerate(model.backbone.blocks):
+            if i in rcfg.MODEL.BACKBONE.CE_LOC:
+                def hook(m, a, out):
+                    keeps_v.append(out[2].clone())
+                    keeps_i.append(out[3].clone())
+                blk.register_forward_hook(hook)
+    with torch.no_grad():
+        out, coords = model(*inputs)
+    res = dict(pred_boxes=out["pred_boxes"], score_maps=cap["maps"], feat=cap["feat"])
+    if keeps_v:
+        res["ce_keep_v"], res["ce_keep_i"] = keeps_v, keeps_i
+    return res
+
+
+def main(variants):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(8)
+    for variant in variants:
+        model, cfg = synthetic.make_model(variant, WEIGHT_SEED)
+        sd = model.state_dict()
+        inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+        ref = run_reference(variant, sd, inputs)
+        ora = O.forward(variant, sd, cfg, *inputs)
+        d_box = (ref["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
+        d_map = (ref["score_maps"] - ora["score_maps"]).abs().max().item()
+        d_feat = (ref["feat"] - ora["feat"]).abs().max().item()
+        print(f"{variant}: oracle vs reference  boxes {d_box:.3e}  score maps {d_map:.3e}  head input {d_feat:.3e}")
+        assert d_box <= 1e-5 and d_map <= 2e-4 and d_feat <= 2e-4, "oracle does not restate the reference"
+        save = dict(pred_boxes=ref["pred_boxes"].numpy(), score_maps=ref["score_maps"].numpy(),
+                    feat_mean_abs=np.float32(ref["feat"].abs().mean().item()))
+        if "ce_keep_v" in ref:
+            for k in ("ce_keep_v", "ce_keep_i"):
+                for j, (a, b) in enumerate(zip(ref[k], ora[k])):
+                    assert torch.equal(a, b[: a.shape[0]]), f"{k}[{j}] differs between oracle and reference"
+                    save[f"{k}_{j}"] = a.numpy().astype(np.int32)
+            for j, s in enumerate(ora["ce_scores"]):
+                save[f"ce_scores_{j}"] = s.numpy()
+        px = ref["pred_boxes"].view(-1, 4) * cfg.DATA.SEARCH.SIZE
+        print("   reference boxes (px, cxcywh):", np.round(px.numpy(), 2).tolist())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}_b{BATCH}.npz"), **save)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(synthetic.DEFAULT_YAML))
