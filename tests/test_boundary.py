@@ -1,0 +1,103 @@
+"""CPU: the drop-in boundary - C-ABI exports, checkpoint layout, config system, loud failure without CUDA."""
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+KEY_COUNTS = {"mixformer_vit": 312, "mixformer_vit_rgbt": 507, "mixformer_vit_rgbt_shared": 407,
+              "mixformer_vit_rgbt_unibackbone": 359, "asymmetric_shared": 407, "asymmetric_shared_ce": 407}
+PARAMS_M = {"mixformer_vit": 98.4, "mixformer_vit_rgbt": 190.7, "mixformer_vit_rgbt_shared": 104.7,
+            "mixformer_vit_rgbt_unibackbone": 104.7, "asymmetric_shared": 104.7, "asymmetric_shared_ce": 104.7}
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    syms = built_lib.declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(built_lib.lib, s), f"{s} declared in include/mmt_b200.h but not exported"
+    import ctypes
+    sm = ctypes.c_int(0)
+    assert built_lib.lib.mmt_abi_version(ctypes.byref(sm)) >= 1 and sm.value == 100
+
+
+@pytest.mark.parametrize("variant", sorted(KEY_COUNTS))
+def test_state_dict_layout(variant):
+    """Key families / counts / parameter totals of SURVEY.md appendix B (probe of the reference builders)."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    model, _ = synthetic.make_model(variant, 0, sharpen=False)
+    sd = model.state_dict()
+    assert len(sd) == KEY_COUNTS[variant]
+    assert abs(sum(p.numel() for p in model.parameters()) / 1e6 - PARAMS_M[variant]) < 0.06
+    if variant == "mixformer_vit":
+        for k in ("backbone.cls_token", "backbone.pos_embed", "backbone.norm.weight", "backbone.head.weight"):
+            assert k in sd                       # timm leftovers that RGB-only checkpoints carry
+    else:
+        assert "fusion_vi.fusion_attention.level_embed" in sd and sd["fusion_vi.adjust_cat.0.weight"].shape == (768, 1024, 1, 1)
+    if variant in ("mixformer_vit_rgbt_shared", "asymmetric_shared", "asymmetric_shared_ce"):
+        assert "backbone.blocks.11.norm2_i.bias" in sd and "backbone.blocks.0.norm1.weight" not in sd
+    assert sd["box_head.conv1_tl.0.weight"].shape == (384, 768, 3, 3)
+    assert "box_head.adjust3_br.2.1.num_batches_tracked" in sd
+    # strict round trip
+    model2, _ = synthetic.make_model(variant, 1, sharpen=False)
+    missing, unexpected = model2.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce"])
+def test_reference_builder_accepts_our_state_dict(variant):
+    """strict=True load of our state_dict INTO the unmodified reference module (and the reverse)."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import ref_shims
+    ours, _ = synthetic.make_model(variant, 0, sharpen=False)
+    ref, _ = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant])
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_reference_yaml_files_load_unchanged():
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import config
+    cfg = config.load_config("asymmetric_shared_ce",
+                             os.path.join(REF, "experiments/asymmetric_shared_ce/attention_lasher_newfusion_2layer.yaml"),
+                             os.path.join(REF, "experiments/tracking.yaml"))
+    assert cfg.MODEL.BACKBONE.CE_LOC == [3, 6, 9] and cfg.MODEL.FUSION_LAYERS == 2
+    assert cfg.TEST.SEARCH_FACTOR == 4.5 and cfg.TEST.UPDATE_INTERVALS.TRACKINGNET == [25]
+    assert cfg.DATA.MAX_SAMPLE_INTERVAL == [1000000000000000000]
+    for variant, sub in [("mixformer_vit", "mixformer_vit/baseline"),
+                         ("mixformer_vit_rgbt", "mixformer_vit_rgbt/attention_lasher_newfusion_2layer")]:
+        c = config.load_config(variant, os.path.join(REF, "experiments", sub + ".yaml"))
+        assert c.MODEL.HEAD_TYPE == "CORNER_UP"
+
+
+def test_config_rejects_unknown_keys(tmp_path):
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import config
+    p = tmp_path / "bad.yaml"
+    p.write_text("MODEL:\n  NOT_A_KEY: 1\n")
+    with pytest.raises(ValueError, match="not exist in config.py"):      # lib/config/*/config.py:124-135
+        config.load_config("mixformer_vit", str(p))
+    with pytest.raises(KeyError):
+        config.default_config("no_such_tracker")
+
+
+def test_training_and_cpu_are_refused():
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import builders, synthetic
+    model, cfg = synthetic.make_model("mixformer_vit", 0, sharpen=False)
+    with pytest.raises(NotImplementedError):
+        builders.build_mixformer_vit(cfg, train=True)
+    with pytest.raises(NotImplementedError):
+        model.train()
+    x = synthetic.make_inputs("mixformer_vit", cfg, 1)
+    with pytest.raises(NotImplementedError):
+        model(*x)                                   # no CPU fallback
+    cfg2 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "RGBT_Fusion_Cat"})
+    with pytest.raises(KeyError):
+        builders.build_mixformer_vit_rgbt(cfg2)
