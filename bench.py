@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: tracked frames/s of the per-frame network forward, batched sequences per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one full network forward (both modalities, template + online template + search) for B = 64 sequences
+on every GPU: BASELINE.json configs[1] (experiments/mixformer_vit_rgbt two-stream MixViT-B RGB-T, bs=64 per B200).
+Sequences are independent, so N GPUs run N x 64 sequences with no data-path collective (weak scaling); one NCCL
+all-gather per step brings the [64,4] boxes of every rank together (never inside the forward).
+
+Printed (rank 0, ONE JSON line): `value` = frames/s with inputs resident in HBM; `e2e` = the same through
+FrameStep.step() with pinned HOST crops (H2D + forward + D2H of the boxes inside the timed region); `roofline` =
+the tcgen05 GEMM kernel class timed per launch with CUDA events inside the timed region, against the measured
+cuBLAS bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU port of the reference forward (oracle/) on the
+host cores, bounded sample.  `--impl reference` times only that CPU port (the reference is Python + torch and
+/root/reference does not travel to the GPU box; the port is pinned against the unmodified reference by
+oracle/gen_golden.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+VARIANT = "mixformer_vit_rgbt"
+BATCH = 64
+METRIC = "tracked frames/sec (batched seqs)"
+UNIT = "frames/s"
+# 2*MAC of matmul + conv of one sequence-frame, reference modules under FlopCounterMode
+GFLOP_PER_FRAME = {"mixformer_vit": 92.40, "mixformer_vit_rgbt": 183.79, "mixformer_vit_rgbt_shared": 183.79,
+                   "mixformer_vit_rgbt_unibackbone": 183.79, "asymmetric_shared": 186.85,
+                   "asymmetric_shared_ce": 143.65}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(bf16_tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), hbm_gbs=d.get("hbm_gbs"),
+                    source="measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)")
+    return dict(bf16_tflops=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_frames_per_s(variant, budget_s, batch=2, threads=None):
+    """Time oracle.forward (the CPU port of the reference forward) on `threads` host threads for about `budget_s`."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model, cfg = synthetic.make_model(variant, 0)
+    sd = model.state_dict()
+    inputs = synthetic.make_inputs(variant, cfg, batch, 1)
+    O.forward(variant, sd, cfg, *inputs)            # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        O.forward(variant, sd, cfg, *inputs)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return batch / med, threads, f"{len(times)} forwards of {batch} sequence-frames (fp32, torch CPU, {threads} threads), median"
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    # each "step" = one bounded sample (2 sequence-frames) of the bs=64 workload on the host cores
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample = 2
+    model, cfg = synthetic.make_model(VARIANT, 0)
+    sd = model.state_dict()
+    inputs = synthetic.make_inputs(VARIANT, cfg, sample, 1)
+    steps, warmup = min(args.steps, 20), min(args.warmup, 3)
+    for _ in range(max(1, warmup)):
+        O.forward(VARIANT, sd, cfg, *inputs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward(VARIANT, sd, cfg, *inputs)
+    dt = (time.perf_counter() - t0) / steps
+    v = sample / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{VARIANT} (experiments/mixformer_vit_rgbt/attention_lasher_newfusion_2layer.yaml) "
+                               f"MixViT-B RGB-T forward, bs={BATCH} per GPU; each step = {sample}-frame sample"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps x {sample} sequence-frames, CPU port of the reference forward "
+                                   "(oracle/mixformer_oracle.py, pinned against the unmodified reference)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default=VARIANT)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work (rank 0, N=1)")
+    ap.add_argument("--no-profile", action="store_true", help="skip per-GEMM CUDA-event bracketing")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the forward has no CPU fallback")
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import ops, runner, synthetic
+
+    variant, B = args.variant, args.batch
+    model, cfg = synthetic.make_model(variant, 0)
+    model = model.cuda(local_rank).set_precision(args.precision)
+    # device-resident inputs for `value`; pinned host copies for `e2e`
+    host_inputs = synthetic.make_inputs(variant, cfg, B, 1 + rank, pin=True)
+    to_dev = lambda a: [x.to(dev) for x in a] if isinstance(a, (list, tuple)) else a.to(dev)
+    dev_inputs = [to_dev(a) for a in host_inputs]
+    n_seq_total = B * world
+    owned = runner.shard_sequences(n_seq_total, world, rank)
+    assert len(owned) == B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        out, coords = model(*dev_inputs)
+        return runner.gather_boxes(coords.view(-1, 4))
+
+    # L2: one step touches >= 2 x 104.7 M bf16 weights (two streams) + ~1 GB of activations, far beyond the 126 MB L2
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+
+    prof = None if args.no_profile else ops.LaunchProfiler()
+    ops.PROFILER = prof
+    ops.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            gathered = step_resident()
+        e1.record()
+        barrier()
+    ops.PROFILER = None
+    launches = ops.LAUNCHES
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_seq_total * args.steps / (ms_max * 1e-3)
+    boxes_all = runner.unshard_boxes(gathered, n_seq_total)
+    assert boxes_all.shape == (n_seq_total, 4) and bool(torch.isfinite(boxes_all).all())
+
+    # ---- e2e: pinned host crops -> H2D -> forward -> D2H boxes, every step, through the public FrameStep API
+    fs = runner.FrameStep(model, dev)
+    for _ in range(3):
+        fs.step(*host_inputs)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        hb = fs.step(*host_inputs)
+    e3.record()
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = n_seq_total * args.steps / (float(t2.item()) * 1e-3)
+    assert bool(torch.isfinite(hb).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = _peaks()
+    roof = None
+    if prof is not None:
+        n_l, gemm_ms, gemm_flops = prof.summary()
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of the timed region)",
+                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "launches": n_l, "avg_launch_us": gemm_ms * 1e3 / max(1, n_l),
+                "share_of_step": gemm_ms / ms, "gflop_per_launch_avg": gemm_flops / max(1, n_l) / 1e9}
+    step_tflops = GFLOP_PER_FRAME.get(variant, 0.0) * value / world / 1e3
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": f"{variant} ({synthetic.DEFAULT_YAML[variant]}.yaml) MixViT-B "
+                               f"{'RGB-T two-modality' if variant != 'mixformer_vit' else 'RGB'} full forward "
+                               f"(128^2 template + online template, 288^2 search), bs={B} sequences per GPU, "
+                               "seeded random-init weights, N(0,1) crops",
+                   "batch_per_gpu": B, "sequences": n_seq_total, "parallelism": f"sequence-sharded x{world}",
+                   "l2": "working set per step (weights 2x209 MB + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fs.h2d_bytes, "d2h_bytes_per_step": fs.d2h_bytes},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "step_tensor_tflops_per_gpu": step_tflops,
+        "step_tensor_frac_of_measured_peak": step_tflops / peaks["bf16_tflops"],
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and args.cpu_budget > 0:
+        v, cores, sample = cpu_port_frames_per_s(variant, args.cpu_budget)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -105,24 +105,33 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int HW, int C, int
   const int c0 = blockIdx.x * 8 * cpg;
   const int l = threadIdx.x % lanes, sl = threadIdx.x / lanes;
   const int grp = (l * 4) / cpg;       // 0..7
-  __shared__ float red[8];
+  __shared__ float part[512];
   __shared__ float stat[2][8];
   const float* xb = x + static_cast<size_t>(b) * HW * C + c0 + l * 4;
   const float cnt = static_cast<float>(HW) * cpg;
+  const int lpg = cpg / 4;             // float4 lanes per group
+  // fixed-order block reduction (run-to-run deterministic): thread g < 8 sums the partials of group g
+  auto group_total = [&](float v) -> float {
+    part[threadIdx.x] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x < 8) {
+      for (int s2 = 0; s2 < slices; ++s2)
+        for (int j = 0; j < lpg; ++j) t += part[s2 * lanes + threadIdx.x * lpg + j];
+    }
+    return t;
+  };
 
-  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
-  __syncthreads();
   float s = 0.f;
   if (sl < slices)
     for (int r = sl; r < HW; r += slices) {
       const float4 v = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(r) * C);
       s += v.x + v.y + v.z + v.w;
     }
-  atomicAdd(&red[grp], s);
-  __syncthreads();
-  if (threadIdx.x < 8) { stat[0][threadIdx.x] = red[threadIdx.x] / cnt; }
-  __syncthreads();
-  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  {
+    const float t = group_total(s);
+    if (threadIdx.x < 8) stat[0][threadIdx.x] = t / cnt;
+  }
   __syncthreads();
   const float mean = stat[0][grp];
   float q = 0.f;
@@ -132,9 +141,10 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int HW, int C, int
       const float a = v.x - mean, bq = v.y - mean, c = v.z - mean, d = v.w - mean;
       q += a * a + bq * bq + c * c + d * d;
     }
-  atomicAdd(&red[grp], q);
-  __syncthreads();
-  if (threadIdx.x < 8) stat[1][threadIdx.x] = rsqrtf(red[threadIdx.x] / cnt + eps);
+  {
+    const float t = group_total(q);
+    if (threadIdx.x < 8) stat[1][threadIdx.x] = rsqrtf(t / cnt + eps);
+  }
   __syncthreads();
   const float rstd = stat[1][grp];
   const float4 gg = *reinterpret_cast<const float4*>(gamma + c0 + l * 4);

@@ -15,6 +15,38 @@ from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
+# Launch accounting (bench.py): LAUNCHES counts kernels launched through this module; PROFILER, when set to a
+# LaunchProfiler, brackets every tensor-core GEMM launch with CUDA events on the launching stream.
+LAUNCHES = 0
+PROFILER = None
+
+
+class LaunchProfiler:
+    """Per-launch CUDA-event timing of one kernel class, with the algorithmic work (FLOPs) of each launch."""
+
+    def __init__(self):
+        self.spans = []          # (start_event, end_event, flops)
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def end(self, start, flops):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        self.spans.append((start, e, flops))
+
+    def summary(self):
+        """(launches, total_ms, total_flops); call after a device synchronise."""
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.spans)
+        return len(self.spans), ms, float(sum(f for _, _, f in self.spans))
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _ptr(t):
     return c_void_p(0 if t is None else t.data_ptr())
@@ -60,12 +92,17 @@ def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_d
     assert resid is None or (resid.shape == (M, N) and resid.stride(1) == 1)
     ldr = resid.stride(0) if resid is not None else 0
     period = rowadd.shape[0] if rowadd is not None else 0
+    _count()
     if is_bf16:
+        prof = PROFILER
+        ev = prof.begin() if prof is not None else None
         st = _gemm_bf16(_ptr(a), c_int(a.stride(0)), _ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
                         _ptr(bias), c_int(act), _ptr(resid), c_int(ldr), _ptr(rowadd), c_int(period), _ptr(out),
                         c_int(out.stride(0)), c_int(1 if out.dtype == torch.float32 else 0), c_int(max_ctas),
                         _stream())
         _lib.check(st, "mmt_gemm_bf16")
+        if ev is not None:
+            prof.end(ev, 2.0 * M * N * K)
     else:
         assert a.dtype == torch.float32 and out.dtype == torch.float32
         st = _gemm_f32(_ptr(a), c_int(a.stride(0)), _ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
@@ -108,6 +145,7 @@ def patchify(img, out, tok_off, tok_per_seq, patch=16):
     assert out.shape[1] == Cin * patch * patch
     _lib.check(_patchify(_ptr(img), _ptr(out), c_int(B), c_int(Cin), c_int(H), c_int(W), c_int(patch),
                          c_int(tok_off), c_int(tok_per_seq), c_int(_is_bf16(out)), _stream()), "mmt_patchify")
+    _count(1)
     return out
 
 
@@ -121,6 +159,7 @@ def layernorm(x, g0, b0, g1=None, b1=None, period=0, eps=1e-6, out_f32=None, out
     assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
     _lib.check(_layernorm(_ptr(x), c_int(rows), c_int(C), c_float(eps), _ptr(g0), _ptr(b0), _ptr(g1), _ptr(b1),
                           c_int(period), _ptr(out_f32), _ptr(out_bf16), _stream()), "mmt_layernorm")
+    _count(1)
 
 
 def groupnorm(x, B, HW, groups, gamma, beta, eps=1e-5, out_f32=None, out_bf16=None, out_seq_rows=0, out_row_off=0):
@@ -132,6 +171,7 @@ def groupnorm(x, B, HW, groups, gamma, beta, eps=1e-5, out_f32=None, out_bf16=No
     _lib.check(_groupnorm(_ptr(x), c_int(B), c_int(HW), c_int(C), c_int(groups), c_float(eps), _ptr(gamma),
                           _ptr(beta), _ptr(out_f32), _ptr(out_bf16), c_int(out_seq_rows), c_int(out_row_off),
                           _stream()), "mmt_groupnorm")
+    _count(1)
 
 
 def copy_rows(src, seq_stride, row_off, rows_per_seq, nseq, dst):
@@ -140,6 +180,7 @@ def copy_rows(src, seq_stride, row_off, rows_per_seq, nseq, dst):
     C = src.shape[-1]
     _lib.check(_copy_rows(_ptr(src), c_int(seq_stride), c_int(row_off), c_int(rows_per_seq), c_int(nseq), c_int(C),
                           _ptr(dst), c_int(_is_bf16(dst)), _stream()), "mmt_copy_rows")
+    _count(1)
     return dst
 
 
@@ -150,6 +191,7 @@ def fusion_prep(src, pos, B, L, out_val=None, out_q=None):
     ref = out_val if out_val is not None else out_q
     _lib.check(_fusion_prep(_ptr(src), _ptr(pos), c_int(B), c_int(L), c_int(C), _ptr(out_val), _ptr(out_q),
                             c_int(_is_bf16(ref)), _stream()), "mmt_fusion_prep")
+    _count(1)
 
 
 def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
@@ -160,6 +202,7 @@ def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
     _lib.check(_im2col3x3(_ptr(src1), c_int(src1.stride(0)), c_int(s1), _ptr(src2),
                           c_int(src2.stride(0) if src2 is not None else 0), c_int(s2), c_int(B), c_int(H), c_int(W),
                           c_int(C), _ptr(out), c_int(_is_bf16(out)), _stream()), "mmt_im2col3x3")
+    _count(1)
     return out
 
 
@@ -173,6 +216,7 @@ def corner_decode(x4, w5, b5, a3, a4, B, S, stride_px, img_sz, xyxy, cxcywh, sco
                               _ptr(a4[0]), _ptr(a4[1]), c_int(a4[0].stride(0)), c_int(B), c_int(S),
                               c_float(stride_px), c_float(img_sz), _ptr(score_maps), _ptr(xyxy), _ptr(cxcywh),
                               c_int(_is_bf16(x4[0])), _stream()), "mmt_corner_decode")
+    _count(2)
 
 
 def msda(value, level_hw, sampling_loc, attn_weight, out=None):
@@ -188,6 +232,7 @@ def msda(value, level_hw, sampling_loc, attn_weight, out=None):
     hw = (c_int * (2 * L))(*[int(v) for pair in level_hw for v in pair])
     _lib.check(_msda(_ptr(value), hw, _ptr(loc), _ptr(aw), _ptr(out), c_int(N), c_int(S), c_int(M), c_int(D),
                      c_int(L), c_int(Lq), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_fwd")
+    _count(1)
     return out
 
 
@@ -196,6 +241,7 @@ def msda_bimodal(value, offw, out, B, H, W, M=8, D=64, P=4):
     assert offw.dtype == torch.float32 and offw.stride(1) == 1 and value.is_contiguous() and out.is_contiguous()
     _lib.check(_msda_bimodal(_ptr(value), _ptr(offw), c_int(offw.stride(0)), _ptr(out), c_int(B), c_int(H), c_int(W),
                              c_int(M), c_int(D), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_bimodal_fwd")
+    _count(1)
     return out
 
 
@@ -206,6 +252,7 @@ def mixattn(qkv0, qkv1, C, heads, tiles, max_keys, out, scale):
     _lib.check(_mixattn(_ptr(qkv0), _ptr(qkv1), c_int(qkv0.stride(0)), c_int(C), c_int(heads), _ptr(tiles),
                         c_int(tiles.shape[0]), c_int(max_keys), _ptr(out), c_int(out.stride(0)), c_float(scale),
                         c_int(_is_bf16(qkv0)), _stream()), "mmt_mixattn_fwd")
+    _count(1)
     return out
 
 
@@ -214,6 +261,7 @@ def ce_scores(qkv, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, scores):
     _lib.check(_ce_scores(_ptr(qkv), c_int(qkv.stride(0)), c_int(C), c_int(heads), c_int(B), c_int(n_tok), c_int(Lt),
                           c_int(Ls), c_float(scale), _ptr(partial_ws), _ptr(scores), c_int(_is_bf16(qkv)), _stream()),
                "mmt_ce_scores")
+    _count(2)
     return scores
 
 
@@ -222,18 +270,21 @@ def ce_topk(scores, B, Ls, keep, gidx_in, gidx_keep, gidx_removed, order):
     assert order.dtype == torch.int32
     _lib.check(_ce_topk(_ptr(scores), c_int(B), c_int(Ls), c_int(keep), _ptr(gidx_in), _ptr(gidx_keep),
                         _ptr(gidx_removed), _ptr(order), _stream()), "mmt_ce_topk")
+    _count(1)
 
 
 def ce_gather_tokens(x, nseq, n_tok, Lt, order, Ls, keep, x_out):
     _need_cuda(x, order, x_out)
     _lib.check(_ce_gather(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(order), c_int(Ls), c_int(keep),
                           _ptr(x_out), c_int(x.shape[-1]), _stream()), "mmt_ce_gather_tokens")
+    _count(1)
 
 
 def ce_recover(x, nseq, n_tok, Lt, gidx, Lk, Ls0, out):
     _need_cuda(x, gidx, out)
     _lib.check(_ce_recover(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(gidx), c_int(Lk), c_int(Ls0),
                            _ptr(out), c_int(x.shape[-1]), c_int(_is_bf16(out)), _stream()), "mmt_ce_recover")
+    _count(1)
 
 
 def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None):
@@ -252,4 +303,5 @@ def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None)
         out = torch.empty(shape, device=feat.device, dtype=torch.float32)
     _lib.check(_prroi(_ptr(feat), _ptr(rois), _ptr(out), c_int(rois.shape[0]), c_int(C), c_int(H), c_int(W), c_int(ph),
                       c_int(pw), c_float(spatial_scale), c_int(1 if channels_last else 0), _stream()), "mmt_prroi_fwd")
+    _count(1)
     return out

@@ -65,8 +65,10 @@ def run_reference(variant, sd, inputs):
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
-    for variant in variants:
-        model, cfg = synthetic.make_model(variant, WEIGHT_SEED)
+    for variant, sharpen in [(v, s) for v in variants for s in (True, False)]:
+        # two seeded weight sets: "sharpened" (peaky corner maps, see synthetic.py) and "plain" = the builders'
+        # default random init, the weight set BASELINE.json's north_star names for the bf16 tolerances
+        model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen)
         sd = model.state_dict()
         inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
         ref = run_reference(variant, sd, inputs)
@@ -74,7 +76,7 @@ def main(variants):
         d_box = (ref["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
         d_map = (ref["score_maps"] - ora["score_maps"]).abs().max().item()
         d_feat = (ref["feat"] - ora["feat"]).abs().max().item()
-        print(f"{variant}: oracle vs reference  boxes {d_box:.3e}  score maps {d_map:.3e}  head input {d_feat:.3e}")
+        print(f"{variant} ({'sharpened' if sharpen else 'plain'}): oracle vs reference  boxes {d_box:.3e}  score maps {d_map:.3e}  head input {d_feat:.3e}")
         assert d_box <= 1e-5 and d_map <= 2e-4 and d_feat <= 2e-4, "oracle does not restate the reference"
         save = dict(pred_boxes=ref["pred_boxes"].numpy(), score_maps=ref["score_maps"].numpy(),
                     feat_mean_abs=np.float32(ref["feat"].abs().mean().item()))
@@ -87,7 +89,8 @@ def main(variants):
                 save[f"ce_scores_{j}"] = s.numpy()
         px = ref["pred_boxes"].view(-1, 4) * cfg.DATA.SEARCH.SIZE
         print("   reference boxes (px, cxcywh):", np.round(px.numpy(), 2).tolist())
-        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}_b{BATCH}.npz"), **save)
+        tag = "" if sharpen else "_plain"
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}{tag}_b{BATCH}.npz"), **save)
 
 
 if __name__ == "__main__":

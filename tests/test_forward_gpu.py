@@ -18,62 +18,101 @@ VARIANTS = ["mixformer_vit", "mixformer_vit_rgbt", "mixformer_vit_rgbt_shared", 
             "asymmetric_shared", "asymmetric_shared_ce"]
 
 
-def _run(variant, precision, batch=2):
+def _run(variant, precision, batch=2, sharpen=True):
     from mmt_b200 import synthetic
-    model, cfg = synthetic.make_model(variant, 0)
+    model, cfg = synthetic.make_model(variant, 0, sharpen=sharpen)
     model = model.cuda().set_precision(precision)
     inputs = synthetic.make_inputs(variant, cfg, batch, 1, device="cuda")
     out, coords = model(*inputs)
     torch.cuda.synchronize()
     res = model._engine.forward(*inputs)      # same call, with the auxiliary outputs (score maps, CE indices)
     torch.cuda.synchronize()
-    assert torch.equal(res["pred_boxes"], coords), "forward is not deterministic"
+    assert torch.equal(res["pred_boxes"], coords), "forward is not run-to-run deterministic"
     assert out["pred_boxes"].shape == (batch, 1, 4)
     return res, cfg
 
 
+def _golden(variant, sharpen):
+    return np.load(os.path.join(GOLDEN, f"{variant}{'' if sharpen else '_plain'}_b2.npz"))
+
+
+def _ce_stage_matches(keeps_mine, g, j, m, B):
+    """Kept global indices of CE stage j, modality m: identical to the reference's, or differing only where the
+    reference's own scores of the swapped tokens are closer than 1e-7 relative (CE bit-exactness)."""
+    key = ("ce_keep_v", "ce_keep_i")[m]
+    ref = g[f"{key}_{j}"]
+    mine = keeps_mine[j][m * B:(m + 1) * B]
+    if np.array_equal(mine, ref):
+        return True
+    sc = g[f"ce_scores_{j}"]                       # [B, 2*Ls_j], indexed by the token's LOCAL position at stage j
+    Ls = sc.shape[1] // 2
+    for b in range(B):
+        if j == 0:
+            local = {int(t): int(t) for t in range(Ls)}
+        else:
+            local = {int(t): i for i, t in enumerate(g[f"{key}_{j - 1}"][b])}
+        for a, r in zip(mine[b], ref[b]):
+            if a != r:
+                if int(a) not in local:
+                    return False
+                sa, sr = sc[b, m * Ls + local[int(a)]], sc[b, m * Ls + local[int(r)]]
+                if abs(sa - sr) > 1e-7 * max(abs(sa), abs(sr)):
+                    return False
+    return True
+
+
+@pytest.mark.parametrize("sharpen", [True, False], ids=["sharpened", "plain"])
 @pytest.mark.parametrize("variant", VARIANTS)
-def test_fp32_mode_matches_reference_golden(built_lib, variant):
-    res, cfg = _run(variant, "fp32")
-    g = np.load(os.path.join(GOLDEN, f"{variant}_b2.npz"))
-    boxes = res["pred_boxes"].cpu().numpy()
-    maps = res["score_maps"].cpu().numpy()
-    d_box = np.abs(boxes - g["pred_boxes"]).max()
-    d_map = np.abs(maps - g["score_maps"]).max()
+def test_fp32_mode_matches_reference_golden(built_lib, variant, sharpen):
+    res, cfg = _run(variant, "fp32", sharpen=sharpen)
+    g = _golden(variant, sharpen)
+    d_box = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max()
+    d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
     print(f"{variant} fp32: boxes {d_box:.3e} (norm.)  score maps {d_map:.3e}")
-    assert d_box <= 1e-4, d_box
-    assert d_map <= 1e-3 * max(1.0, np.abs(g["score_maps"]).max()), d_map   # logits reach |20|: 1e-4 relative-ish
+    assert d_box <= 1e-4, d_box          # north star, fp32 mode: 1e-4 (boxes: 1e-4 normalised = 0.03 px)
+    assert d_map <= 1e-4, d_map          # absolute, on raw corner logits that reach |12| on the sharpened set
     if variant == "asymmetric_shared_ce":
         B = 2
+        keeps = [k.cpu().numpy().astype(np.int32) for k in res["ce_keep"]]      # [2B, keep], modality-major
         for j in range(3):
-            keep = res["ce_keep"][j].cpu().numpy().astype(np.int32)   # [2B, keep], modality-major
-            sc = g[f"ce_scores_{j}"]
-            for m, key in enumerate(("ce_keep_v", "ce_keep_i")):
-                ref = g[f"{key}_{j}"]
-                mine = keep[m * B:(m + 1) * B]
-                assert sorted(map(tuple, np.sort(mine, 1))) == sorted(map(tuple, np.sort(ref, 1))) or \
-                    _only_near_ties(mine, ref, sc, m), f"CE stage {j} kept set differs"
-                if not np.array_equal(mine, ref):
-                    assert _only_near_ties(mine, ref, sc, m), f"CE stage {j} order differs beyond near-ties"
-
-
-def _only_near_ties(mine, ref, scores, m):
-    """True if every position where the two orders differ involves scores within 1e-7 relative."""
-    return True if np.array_equal(mine, ref) else bool(np.all(np.sort(mine, 1) == np.sort(ref, 1)))
+            for m in range(2):
+                assert _ce_stage_matches(keeps, g, j, m, B), f"CE stage {j} modality {m}: kept indices differ"
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
-def test_bf16_mode_within_tolerance(built_lib, variant):
-    res, cfg = _run(variant, "bf16")
-    g = np.load(os.path.join(GOLDEN, f"{variant}_b2.npz"))
+def test_bf16_mode_north_star_tolerance(built_lib, variant):
+    """North-star bound, on the weight set it names (the builders' random init): boxes <= 0.5 px and corner score
+    maps <= 1e-2 abs against the fp32 reference."""
+    res, cfg = _run(variant, "bf16", sharpen=False)
+    g = _golden(variant, False)
     size = cfg.DATA.SEARCH.SIZE
     d_box_px = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * size
     d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
-    print(f"{variant} bf16: boxes {d_box_px:.3f} px  score maps {d_map:.3e}")
-    # CE in bf16 may legitimately keep a different token set (scores are 1e-9 apart), which moves the maps
+    print(f"{variant} bf16 (plain init): boxes {d_box_px:.3f} px  score maps {d_map:.3e}")
+    assert d_box_px <= 0.5, d_box_px
     if variant != "asymmetric_shared_ce":
-        assert d_box_px <= 0.5, d_box_px
-        assert d_map <= 1e-2 * max(1.0, np.abs(g["score_maps"]).max()), d_map
+        assert d_map <= 1e-2, d_map
+    else:
+        # bf16 qkv moves a few of the 1e-9-apart CE scores across the keep boundary: a different token is zeroed
+        # in the recovered 18x18 map, which shifts single logits (the boxes still agree to 0.5 px)
+        assert d_map <= 0.2, d_map
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_bf16_mode_sharpened_weights(built_lib, variant):
+    """Stress set: head gain x24 makes the corner logits reach |12| and amplifies every bf16 rounding.  The
+    reference itself under torch.autocast(bfloat16) is 1.5 px / 0.17 away from its fp32 self on this set
+    (DESIGN.md 'bf16 error budget'), so the bound here is 2 px and 2% of the logit range, not the north-star one.
+    CE in bf16 may legitimately keep a different token set (scores 1e-9 apart), which moves the maps."""
+    res, cfg = _run(variant, "bf16", sharpen=True)
+    g = _golden(variant, True)
+    size = cfg.DATA.SEARCH.SIZE
+    d_box_px = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * size
+    d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
+    print(f"{variant} bf16 (sharpened): boxes {d_box_px:.3f} px  score maps {d_map:.3e}")
+    if variant != "asymmetric_shared_ce":
+        assert d_box_px <= 2.0, d_box_px
+        assert d_map <= 2e-2 * np.abs(g["score_maps"]).max(), d_map
 
 
 def test_live_oracle_ragged_batch(built_lib):
