@@ -35,7 +35,7 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SMEM_BUDGET = 192 * 1024;  // operand ring; the rest holds the epilogue staging
-constexpr int GEMM_STAGING_WORDS = 32 * 33;   // per epilogue warp: 32 rows x (32 + 1 pad) words
+constexpr int GEMM_STAGING_WORDS = 32 * 32;   // per epilogue warp: 32 rows x 128 B, XOR-swizzled 16-byte vectors
 
 struct GemmEpi {
   const float* bias;      // [N] or nullptr
@@ -160,11 +160,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Each warp owns 32 output rows (its TMEM lane quadrant) and walks them in CH-column chunks.  A chunk is
+    // read from TMEM with thread == row, bias/activation/positional add happen in registers, then the chunk is
+    // transposed through a per-warp XOR-swizzled staging tile so that HBM sees 16-byte vectors with a warp
+    // instruction covering whole row segments (coalesced), for the residual read as well as the store.  The
+    // residual vectors of the NEXT chunk are requested before the current chunk is processed, so one chunk of
+    // loads (up to 4 KB per warp) is always in flight.
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // which of the two warps sharing the quadrant
-    float* stg = reinterpret_cast<float*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
-                 (warp - 2) * GEMM_STAGING_WORDS;
+    uint4* stg4 = reinterpret_cast<uint4*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
+                  (warp - 2) * (GEMM_STAGING_WORDS / 4);
     constexpr int CH = Cfg::CH;
+    constexpr int NCH = BN / CH;
+    // staging geometry: fp32 rows are CH*4 bytes (CPR_F 16-byte vectors), bf16 rows CH*2 bytes (CPR_H vectors)
+    constexpr int CPR_F = CH / 4, CPR_H = CH / 8;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
@@ -173,16 +182,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = (tile % n_tiles) * BN;
       const int row0 = m0 + quad * 32;
       const int row = row0 + lane;
+      const float* rowadd_row =
+          ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
+      // residual prefetch state: vector it of chunk c belongs to row row0 + it*(32/CPR_F) + lane/CPR_F
+      const int rr_f = lane / CPR_F, cc_f = lane % CPR_F;
+      float4 rv[CPR_F];
+#pragma unroll
+      for (int it = 0; it < CPR_F; ++it) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch_resid = [&](int c) {
+        const int nb = n0 + c * CH;
+        const bool ok = ep.vec_ok && ep.resid && (nb + CH <= N);
+#pragma unroll
+        for (int it = 0; it < CPR_F; ++it) {
+          const int grow = row0 + it * (32 / CPR_F) + rr_f;
+          rv[it] = (ok && grow < M)
+                       ? __ldcs(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(grow) * ep.ldr + nb) + cc_f)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (ep.resid) prefetch_resid(half);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
-      const float* rowadd_row =
-          ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
 #pragma unroll 1
-      for (int c = half; c < BN / CH; c += 2) {
+      for (int c = half; c < NCH; c += 2) {
         uint32_t v[32];
         if (CH == 32) tmem_ld_32x32(t_row + c * CH, v);
         else tmem_ld_32x16(t_row + c * CH, v);
+        float4 rcur[CPR_F];
+#pragma unroll
+        for (int it = 0; it < CPR_F; ++it) rcur[it] = rv[it];
+        if (ep.resid && c + 2 < NCH) prefetch_resid(c + 2);
         tmem_ld_wait();
         const int nb = n0 + c * CH;
         if (nb >= N) continue;
@@ -213,42 +243,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
             }
           }
-          // ---- transpose through smem so that a warp instruction touches contiguous row bytes
           if (ep.out_fp32) {
-            constexpr int WPR = CH;             // words per row in the staging tile
-            constexpr int RPI = 32 / WPR;       // rows covered by one warp instruction
+            // row `lane` -> CPR_F vectors, vector j stored at slot j ^ key(lane): conflict-free both ways
+            constexpr int KEYDIV = 8 / CPR_F > 0 ? 8 / CPR_F : 1;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) stg[lane * (WPR + 1) + j] = f[j];
+            for (int j = 0; j < CPR_F; ++j) {
+              uint4 w;
+              w.x = __float_as_uint(f[4 * j]); w.y = __float_as_uint(f[4 * j + 1]);
+              w.z = __float_as_uint(f[4 * j + 2]); w.w = __float_as_uint(f[4 * j + 3]);
+              stg4[lane * CPR_F + (j ^ ((lane / KEYDIV) & (CPR_F - 1)))] = w;
+            }
             __syncwarp();
-            const int cc = lane % WPR, rr = lane / WPR;
-            float* obase = reinterpret_cast<float*>(ep.out) + nb + cc;
-            const float* rbase = ep.resid ? ep.resid + nb + cc : nullptr;
-#pragma unroll 8
-            for (int it = 0; it < WPR; ++it) {
-              const int r = it * RPI + rr;
+            float* obase = reinterpret_cast<float*>(ep.out) + nb;
+#pragma unroll
+            for (int it = 0; it < CPR_F; ++it) {
+              const int r = it * (32 / CPR_F) + rr_f;
               const int grow = row0 + r;
-              if (grow < M) {
-                float x = stg[r * (WPR + 1) + cc];
-                if (rbase) x += rbase[static_cast<size_t>(grow) * ep.ldr];
-                obase[static_cast<size_t>(grow) * ep.ldo] = x;
-              }
+              const uint4 w = stg4[r * CPR_F + (cc_f ^ ((r / KEYDIV) & (CPR_F - 1)))];
+              float4 x;
+              x.x = __uint_as_float(w.x) + rcur[it].x; x.y = __uint_as_float(w.y) + rcur[it].y;
+              x.z = __uint_as_float(w.z) + rcur[it].z; x.w = __uint_as_float(w.w) + rcur[it].w;
+              if (grow < M) reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_f] = x;
             }
             __syncwarp();
           } else {
-            constexpr int WPR = CH / 2;         // packed bf16x2 words per row
-            constexpr int RPI = 32 / WPR;
-            uint32_t* stg32 = reinterpret_cast<uint32_t*>(stg);
+            constexpr int KEYDIV = 8 / CPR_H > 0 ? 8 / CPR_H : 1;
+            const int rr_h = lane / CPR_H, cc_h = lane % CPR_H;
 #pragma unroll
-            for (int j = 0; j < WPR; ++j) stg32[lane * (WPR + 1) + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            for (int j = 0; j < CPR_H; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              stg4[lane * CPR_H + (j ^ ((lane / KEYDIV) & (CPR_H - 1)))] = w;
+            }
             __syncwarp();
-            const int cc = lane % WPR, rr = lane / WPR;
-            bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb + 2 * cc;
-#pragma unroll 8
-            for (int it = 0; it < 32 / RPI; ++it) {
-              const int r = it * RPI + rr;
+            bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb;
+#pragma unroll
+            for (int it = 0; it < CPR_H; ++it) {
+              const int r = it * (32 / CPR_H) + rr_h;
               const int grow = row0 + r;
-              if (grow < M)
-                *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(grow) * ep.ldo) = stg32[r * (WPR + 1) + cc];
+              const uint4 w = stg4[r * CPR_H + (cc_h ^ ((r / KEYDIV) & (CPR_H - 1)))];
+              if (grow < M) reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_h] = w;
             }
             __syncwarp();
           }
@@ -371,10 +406,10 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
   GemmEpi ep;
   ep.bias = bias; ep.resid = resid; ep.rowadd = rowadd; ep.out = out;
   ep.ldr = ldr; ep.rowadd_period = rowadd_period; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
-  // fast path preconditions: float4 loads of bias / rowadd, 4-byte packed bf16x2 stores
-  ep.vec_ok = (out_fp32 || ((ldo % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0))) &&
-              (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
-              (!rowadd || ((N % 4 == 0) && (reinterpret_cast<uintptr_t>(rowadd) & 15) == 0));
+  // fast path preconditions: 16-byte vector loads of bias / rowadd / resid and 16-byte vector stores
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  ep.vec_ok = al16(out) && (out_fp32 ? (ldo % 4 == 0) : (ldo % 8 == 0)) && (!bias || al16(bias)) &&
+              (!rowadd || ((N % 4 == 0) && al16(rowadd))) && (!resid || (al16(resid) && ldr % 4 == 0));
   CUtensorMap tmA;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
   if (rc) return rc;
