@@ -160,20 +160,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
-    // Each warp owns 32 output rows (its TMEM lane quadrant) and walks them in CH-column chunks.  A chunk is
-    // read from TMEM with thread == row, bias/activation/positional add happen in registers, then the chunk is
-    // transposed through a per-warp XOR-swizzled staging tile so that HBM sees 16-byte vectors with a warp
-    // instruction covering whole row segments (coalesced), for the residual read as well as the store.  The
-    // residual vectors of the NEXT chunk are requested before the current chunk is processed, so one chunk of
-    // loads (up to 4 KB per warp) is always in flight.
+    // Each warp owns 32 output rows (its TMEM lane quadrant) and walks them in CH-column chunks:
+    //   1. tcgen05.ld the raw fp32 accumulators (thread == row) and write them to a per-warp, XOR-swizzled
+    //      fp32 staging tile with 16-byte shared stores (conflict-free);
+    //   2. read the tile back TRANSPOSED - a lane now owns a fixed group of 4 (fp32 out) or 8 (bf16 out)
+    //      consecutive columns of several rows - so bias is ONE register vector per lane and chunk, and every
+    //      HBM access (residual read, positional-table read, output store) is a 16-byte vector with a warp
+    //      instruction covering whole row segments;
+    //   3. bias, activation, positional add, residual add and the store happen in that layout.
+    // The bias / residual vectors of the NEXT chunk are requested before the current chunk is processed, so their
+    // latency hides behind the TMEM load and the math of the current one.
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // which of the two warps sharing the quadrant
     uint4* stg4 = reinterpret_cast<uint4*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
                   (warp - 2) * (GEMM_STAGING_WORDS / 4);
     constexpr int CH = Cfg::CH;
     constexpr int NCH = BN / CH;
-    // staging geometry: fp32 rows are CH*4 bytes (CPR_F 16-byte vectors), bf16 rows CH*2 bytes (CPR_H vectors)
-    constexpr int CPR_F = CH / 4, CPR_H = CH / 8;
+    constexpr int VPR = CH / 4;                 // 16-byte fp32 vectors per staged row (8 or 4)
+    constexpr int KEYDIV = 8 / VPR;             // rows sharing a swizzle key
+    constexpr int IT_F = VPR;                   // fp32 out: 32/VPR rows per instruction, VPR instructions
+    constexpr int LPR_H = CH / 8;               // bf16 out: lanes per row (8 columns each)
+    constexpr int IT_H = LPR_H;
+    auto key_of = [](int r) { return (r / KEYDIV) & (VPR - 1); };
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
@@ -181,26 +189,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int row0 = m0 + quad * 32;
-      const int row = row0 + lane;
-      const float* rowadd_row =
-          ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
-      // residual prefetch state: vector it of chunk c belongs to row row0 + it*(32/CPR_F) + lane/CPR_F
-      const int rr_f = lane / CPR_F, cc_f = lane % CPR_F;
-      float4 rv[CPR_F];
+      const int rr_f = lane / VPR, cc_f = lane % VPR;          // fp32-out lane -> (row in group, vector)
+      const int rr_h = lane / LPR_H, cc_h = lane % LPR_H;      // bf16-out lane -> (row in group, 8-column group)
+      // per-chunk prefetch registers
+      float4 rv[IT_F];          // residual vectors (fp32 out only)
+      float4 bv[2];             // bias: [0] = this lane's 4 columns (fp32 out) / first 4 of its 8 (bf16), [1] = last 4
 #pragma unroll
-      for (int it = 0; it < CPR_F; ++it) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto prefetch_resid = [&](int c) {
+      for (int it = 0; it < IT_F; ++it) rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bv[0] = bv[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch = [&](int c) {
         const int nb = n0 + c * CH;
-        const bool ok = ep.vec_ok && ep.resid && (nb + CH <= N);
+        const bool full = ep.vec_ok && (nb + CH <= N);
+        if (!full) return;
+        if (ep.bias) {
+          if (ep.out_fp32) bv[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + cc_f);
+          else {
+            bv[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + 2 * cc_h);
+            bv[1] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + 2 * cc_h + 1);
+          }
+        }
+        if (ep.resid) {
 #pragma unroll
-        for (int it = 0; it < CPR_F; ++it) {
-          const int grow = row0 + it * (32 / CPR_F) + rr_f;
-          rv[it] = (ok && grow < M)
-                       ? __ldcs(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(grow) * ep.ldr + nb) + cc_f)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int it = 0; it < IT_F; ++it) {
+            const int grow = row0 + it * (32 / VPR) + rr_f;
+            if (grow < M)
+              rv[it] = __ldcs(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(grow) * ep.ldr + nb) + cc_f);
+          }
         }
       };
-      if (ep.resid) prefetch_resid(half);
+      prefetch(half);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -209,92 +226,93 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint32_t v[32];
         if (CH == 32) tmem_ld_32x32(t_row + c * CH, v);
         else tmem_ld_32x16(t_row + c * CH, v);
-        float4 rcur[CPR_F];
+        float4 rcur[IT_F];
 #pragma unroll
-        for (int it = 0; it < CPR_F; ++it) rcur[it] = rv[it];
-        if (ep.resid && c + 2 < NCH) prefetch_resid(c + 2);
+        for (int it = 0; it < IT_F; ++it) rcur[it] = rv[it];
+        const float4 b0 = bv[0], b1 = bv[1];
+        if (c + 2 < NCH) prefetch(c + 2);
         tmem_ld_wait();
         const int nb = n0 + c * CH;
         if (nb >= N) continue;
-        float f[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
         const bool full = ep.vec_ok && (nb + CH <= N);
         if (full) {
-          // ---- thread == output row: bias, activation, positional table
-          if (ep.bias) {
+          // ---- 1. stage raw accumulators: row `lane`, vector j at slot j ^ key(lane)
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
-          if (ep.act == MMT_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) f[j] = gelu_fast(f[j]);
-          } else if (ep.act == MMT_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (rowadd_row && row < M) {
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(rowadd_row + nb + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          }
+          for (int j = 0; j < VPR; ++j)
+            stg4[lane * VPR + (j ^ key_of(lane))] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
           if (ep.out_fp32) {
-            // row `lane` -> CPR_F vectors, vector j stored at slot j ^ key(lane): conflict-free both ways
-            constexpr int KEYDIV = 8 / CPR_F > 0 ? 8 / CPR_F : 1;
-#pragma unroll
-            for (int j = 0; j < CPR_F; ++j) {
-              uint4 w;
-              w.x = __float_as_uint(f[4 * j]); w.y = __float_as_uint(f[4 * j + 1]);
-              w.z = __float_as_uint(f[4 * j + 2]); w.w = __float_as_uint(f[4 * j + 3]);
-              stg4[lane * CPR_F + (j ^ ((lane / KEYDIV) & (CPR_F - 1)))] = w;
-            }
-            __syncwarp();
             float* obase = reinterpret_cast<float*>(ep.out) + nb;
 #pragma unroll
-            for (int it = 0; it < CPR_F; ++it) {
-              const int r = it * (32 / CPR_F) + rr_f;
+            for (int it = 0; it < IT_F; ++it) {
+              const int r = it * (32 / VPR) + rr_f;
               const int grow = row0 + r;
-              const uint4 w = stg4[r * CPR_F + (cc_f ^ ((r / KEYDIV) & (CPR_F - 1)))];
-              float4 x;
-              x.x = __uint_as_float(w.x) + rcur[it].x; x.y = __uint_as_float(w.y) + rcur[it].y;
-              x.z = __uint_as_float(w.z) + rcur[it].z; x.w = __uint_as_float(w.w) + rcur[it].w;
-              if (grow < M) reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_f] = x;
-            }
-            __syncwarp();
-          } else {
-            constexpr int KEYDIV = 8 / CPR_H > 0 ? 8 / CPR_H : 1;
-            const int rr_h = lane / CPR_H, cc_h = lane % CPR_H;
+              const uint4 w = stg4[r * VPR + (cc_f ^ key_of(r))];
+              float x[4] = {__uint_as_float(w.x) + b0.x, __uint_as_float(w.y) + b0.y, __uint_as_float(w.z) + b0.z,
+                            __uint_as_float(w.w) + b0.w};
+              if (ep.act == MMT_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < CPR_H; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              stg4[lane * CPR_H + (j ^ ((lane / KEYDIV) & (CPR_H - 1)))] = w;
+                for (int k = 0; k < 4; ++k) x[k] = gelu_fast(x[k]);
+              } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
+              }
+              if (grow < M) {
+                if (ep.rowadd) {
+                  const float4 p = __ldg(reinterpret_cast<const float4*>(
+                                             ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb) + cc_f);
+                  x[0] += p.x; x[1] += p.y; x[2] += p.z; x[3] += p.w;
+                }
+                float4 o;
+                o.x = x[0] + rcur[it].x; o.y = x[1] + rcur[it].y; o.z = x[2] + rcur[it].z; o.w = x[3] + rcur[it].w;
+                reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_f] = o;
+              }
             }
-            __syncwarp();
+          } else {
             bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb;
 #pragma unroll
-            for (int it = 0; it < CPR_H; ++it) {
-              const int r = it * (32 / CPR_H) + rr_h;
+            for (int it = 0; it < IT_H; ++it) {
+              const int r = it * (32 / LPR_H) + rr_h;
               const int grow = row0 + r;
-              const uint4 w = stg4[r * CPR_H + (cc_h ^ ((r / KEYDIV) & (CPR_H - 1)))];
-              if (grow < M) reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_h] = w;
+              const uint4 w0 = stg4[r * VPR + ((2 * cc_h) ^ key_of(r))];
+              const uint4 w1 = stg4[r * VPR + ((2 * cc_h + 1) ^ key_of(r))];
+              float x[8] = {__uint_as_float(w0.x) + b0.x, __uint_as_float(w0.y) + b0.y, __uint_as_float(w0.z) + b0.z,
+                            __uint_as_float(w0.w) + b0.w, __uint_as_float(w1.x) + b1.x, __uint_as_float(w1.y) + b1.y,
+                            __uint_as_float(w1.z) + b1.z, __uint_as_float(w1.w) + b1.w};
+              if (ep.act == MMT_ACT_GELU) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = gelu_fast(x[k]);
+              } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k], 0.f);
+              }
+              if (grow < M) {
+                if (ep.rowadd) {
+                  const float4* pr = reinterpret_cast<const float4*>(
+                      ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb) + 2 * cc_h;
+                  const float4 p0 = __ldg(pr), p1 = __ldg(pr + 1);
+                  x[0] += p0.x; x[1] += p0.y; x[2] += p0.z; x[3] += p0.w;
+                  x[4] += p1.x; x[5] += p1.y; x[6] += p1.z; x[7] += p1.w;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+                o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+                reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_h] = o;
+              }
             }
-            __syncwarp();
           }
-        } else if (row < M) {
+          __syncwarp();
+        } else if (row0 + lane < M) {
           // ragged / unaligned tail: scalar, bounds-checked, thread == row
+          const int row = row0 + lane;
           const float* resid_row = ep.resid ? ep.resid + static_cast<size_t>(row) * ep.ldr : nullptr;
+          const float* rowadd_row =
+              ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             const int n = nb + j;
             if (n >= N) continue;
-            float x = f[j];
+            float x = __uint_as_float(v[j]);
             if (ep.bias) x += ep.bias[n];
             if (ep.act == MMT_ACT_GELU) x = gelu_fast(x);
             else if (ep.act == MMT_ACT_RELU) x = fmaxf(x, 0.f);

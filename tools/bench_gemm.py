@@ -41,6 +41,11 @@ def bench(M, N, K, act=0, resid=False, iters=20):
 
 if __name__ == "__main__":
     M = 57856
+    if len(sys.argv) > 1:      # single case for ncu: qkv | proj | fc1 | fc2
+        case = {"qkv": (M, 2304, 768, 0, False), "proj": (M, 768, 768, 0, True), "fc1": (M, 3072, 768, 1, False),
+                "fc2": (M, 768, 3072, 0, True)}[sys.argv[1]]
+        print(json.dumps(bench(*case, iters=3)), flush=True)
+        sys.exit(0)
     for args in [(M, 2304, 768, 0, False), (M, 768, 768, 0, True), (M, 3072, 768, 1, False), (M, 768, 3072, 0, True),
                  (M // 2, 2304, 768, 0, False), (904, 2304, 768, 0, False)]:
         print(json.dumps(bench(*args)), flush=True)
