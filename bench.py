@@ -66,7 +66,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -163,7 +163,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default=VARIANT)
@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work (rank 0, N=1)")
     ap.add_argument("--no-profile", action="store_true", help="skip per-GEMM CUDA-event bracketing")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="developer aid: after the timed regions, run 3 more steps with EVERY op bracketed by CUDA "
+                         "events and print the per-class table to stderr")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -263,6 +266,20 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = n_seq_total * args.steps / (float(t2.item()) * 1e-3)
     assert bool(torch.isfinite(hb).all())
+
+    if args.breakdown and rank == 0:
+        bp = ops.LaunchProfiler(all_ops=True)
+        ops.PROFILER = bp
+        for _ in range(3):
+            step_resident()
+        torch.cuda.synchronize()
+        ops.PROFILER = None
+        tab = bp.table()
+        tot = sum(v["ms"] for v in tab.values())
+        for k, v in sorted(tab.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write(f"  {k:22s} {v['ms'] / 3:8.3f} ms/step  {v['launches'] // 3:4d} launches  "
+                             f"{100 * v['ms'] / tot:5.1f}%\n")
+        sys.stderr.write(f"  sum of bracketed ops   {tot / 3:8.3f} ms/step\n")
 
     if rank != 0:
         if world > 1:

@@ -133,14 +133,16 @@ int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x, int C4, co
 /*
  * Asymmetric mixed attention over packed qkv rows [rows, 3C] (q | k | v, head-major 64-wide slices).
  * tiles_dev: DEVICE array of n_tiles records of 16 int32:
- *   {q_row0, q_rows(<=64), out_row0, nseg(<=3), k_row0[3], k_len[3], k_buf[3], pad[3]}; key segment i reads rows
- *   [k_row0[i], +k_len[i]) of qkv0 (k_buf 0) or qkv1 (k_buf 1, e.g. cached template K/V).  max_keys = largest
- *   total key count of any tile (fp32 mode sizing).  out T [.., ldo], head h at column h*64.
+ *   {q_row0, q_rows(<=128), out_row0, nseg(<=3), k_row0[3], k_len[3], k_buf[3], pad[3]}; key segment i reads rows
+ *   [k_row0[i], +k_len[i]) of qkv0 (k_buf 0, rows0 rows) or qkv1 (k_buf 1, rows1 rows, e.g. cached template K/V).
+ *   max_keys = largest total key count of any tile (fp32 mode sizing).  out T [.., ldo], head h at column h*64.
+ *   bf16 mode: tcgen05 / TMEM kernel fed by TMA straight from the qkv buffer (csrc/attention_tc.cu).
  * Reference: Attention.forward / forward_test lib/models/mixformer_vit/mixformer.py:51-93; cross-modal
  * lib/models/mixformer_vit_rgbt/asymmetric_shared.py:55-104, asymmetric_shared_ce.py:146-200.
  */
-int mmt_mixattn_fwd(const void* qkv0, const void* qkv1, int ld, int C, int heads, const int* tiles_dev, int n_tiles,
-                    int max_keys, void* out, int ldo, float scale, int is_bf16, void* stream);
+int mmt_mixattn_fwd(const void* qkv0, int rows0, const void* qkv1, int rows1, int ld, int C, int heads,
+                    const int* tiles_dev, int n_tiles, int max_keys, void* out, int ldo, float scale, int is_bf16,
+                    void* stream);
 
 /*
  * Candidate-elimination scores [B, 2*Ls] = mean over heads of mean over the 2*Lt template rows of

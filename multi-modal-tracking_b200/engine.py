@@ -201,8 +201,8 @@ class ForwardEngine:
         recs = []
 
         def add(q0, qn, segs):
-            for o in range(0, qn, 64):
-                r = [q0 + o, min(64, qn - o), q0 + o, len(segs)]
+            for o in range(0, qn, 128):
+                r = [q0 + o, min(128, qn - o), q0 + o, len(segs)]
                 rows = [s[0] for s in segs] + [0] * (3 - len(segs))
                 lens = [s[1] for s in segs] + [0] * (3 - len(segs))
                 recs.append(r + rows + lens + [0, 0, 0] + [0, 0, 0])

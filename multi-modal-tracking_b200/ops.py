@@ -22,30 +22,43 @@ PROFILER = None
 
 
 class LaunchProfiler:
-    """Per-launch CUDA-event timing of one kernel class, with the algorithmic work (FLOPs) of each launch."""
+    """Per-launch CUDA-event timing by kernel class, with the algorithmic work (FLOPs) of each GEMM launch.
+    all_ops=False brackets only the tensor-core GEMM (the roofline kernel of bench.py); True brackets every op."""
 
-    def __init__(self):
-        self.spans = []          # (start_event, end_event, flops)
+    def __init__(self, all_ops=False):
+        self.all_ops = all_ops
+        self.spans = {}          # class name -> [(start_event, end_event, flops)]
 
     def begin(self):
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream())
         return e
 
-    def end(self, start, flops):
+    def end(self, start, flops, name="gemm_bf16"):
         e = torch.cuda.Event(enable_timing=True)
         e.record(torch.cuda.current_stream())
-        self.spans.append((start, e, flops))
+        self.spans.setdefault(name, []).append((start, e, flops))
 
-    def summary(self):
-        """(launches, total_ms, total_flops); call after a device synchronise."""
-        ms = sum(a.elapsed_time(b) for a, b, _ in self.spans)
-        return len(self.spans), ms, float(sum(f for _, _, f in self.spans))
+    def summary(self, name="gemm_bf16"):
+        """(launches, total_ms, total_flops) of one class; call after a device synchronise."""
+        sp = self.spans.get(name, [])
+        ms = sum(a.elapsed_time(b) for a, b, _ in sp)
+        return len(sp), ms, float(sum(f for _, _, f in sp))
+
+    def table(self):
+        return {k: dict(zip(("launches", "ms", "flops"), self.summary(k))) for k in self.spans}
 
 
-def _count(n=1):
+def _begin():
+    p = PROFILER
+    return p.begin() if (p is not None and p.all_ops) else None
+
+
+def _count(n=1, name=None, ev=None):
     global LAUNCHES
     LAUNCHES += n
+    if ev is not None:
+        PROFILER.end(ev, 0.0, name)
 
 
 def _ptr(t):
@@ -143,9 +156,10 @@ def patchify(img, out, tok_off, tok_per_seq, patch=16):
     assert img.dtype == torch.float32 and img.is_contiguous() and out.is_contiguous()
     B, Cin, H, W = img.shape
     assert out.shape[1] == Cin * patch * patch
+    _ev = _begin()
     _lib.check(_patchify(_ptr(img), _ptr(out), c_int(B), c_int(Cin), c_int(H), c_int(W), c_int(patch),
                          c_int(tok_off), c_int(tok_per_seq), c_int(_is_bf16(out)), _stream()), "mmt_patchify")
-    _count(1)
+    _count(1, "patchify", _ev)
     return out
 
 
@@ -157,9 +171,10 @@ def layernorm(x, g0, b0, g1=None, b1=None, period=0, eps=1e-6, out_f32=None, out
         assert o is None or (o.shape == x.shape and o.is_contiguous())
     assert out_f32 is None or out_f32.dtype == torch.float32
     assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
+    _ev = _begin()
     _lib.check(_layernorm(_ptr(x), c_int(rows), c_int(C), c_float(eps), _ptr(g0), _ptr(b0), _ptr(g1), _ptr(b1),
                           c_int(period), _ptr(out_f32), _ptr(out_bf16), _stream()), "mmt_layernorm")
-    _count(1)
+    _count(1, "layernorm", _ev)
 
 
 def groupnorm(x, B, HW, groups, gamma, beta, eps=1e-5, out_f32=None, out_bf16=None, out_seq_rows=0, out_row_off=0):
@@ -168,19 +183,21 @@ def groupnorm(x, B, HW, groups, gamma, beta, eps=1e-5, out_f32=None, out_bf16=No
     assert out_f32 is None or out_f32.dtype == torch.float32
     assert out_bf16 is None or out_bf16.dtype == torch.bfloat16
     C = x.shape[1]
+    _ev = _begin()
     _lib.check(_groupnorm(_ptr(x), c_int(B), c_int(HW), c_int(C), c_int(groups), c_float(eps), _ptr(gamma),
                           _ptr(beta), _ptr(out_f32), _ptr(out_bf16), c_int(out_seq_rows), c_int(out_row_off),
                           _stream()), "mmt_groupnorm")
-    _count(1)
+    _count(1, "groupnorm", _ev)
 
 
 def copy_rows(src, seq_stride, row_off, rows_per_seq, nseq, dst):
     _need_cuda(src, dst)
     assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
     C = src.shape[-1]
+    _ev = _begin()
     _lib.check(_copy_rows(_ptr(src), c_int(seq_stride), c_int(row_off), c_int(rows_per_seq), c_int(nseq), c_int(C),
                           _ptr(dst), c_int(_is_bf16(dst)), _stream()), "mmt_copy_rows")
-    _count(1)
+    _count(1, "copy_rows", _ev)
     return dst
 
 
@@ -189,9 +206,10 @@ def fusion_prep(src, pos, B, L, out_val=None, out_q=None):
     assert src.dtype == torch.float32 and src.is_contiguous()
     C = src.shape[-1]
     ref = out_val if out_val is not None else out_q
+    _ev = _begin()
     _lib.check(_fusion_prep(_ptr(src), _ptr(pos), c_int(B), c_int(L), c_int(C), _ptr(out_val), _ptr(out_q),
                             c_int(_is_bf16(ref)), _stream()), "mmt_fusion_prep")
-    _count(1)
+    _count(1, "fusion_prep", _ev)
 
 
 def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
@@ -199,10 +217,11 @@ def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
     _need_cuda(src1, out)
     assert src1.stride(1) == 1 and out.is_contiguous() and out.shape == (B * H * W, 9 * C)
     assert src2 is None or (src2.stride(1) == 1 and src2.dtype == src1.dtype)
+    _ev = _begin()
     _lib.check(_im2col3x3(_ptr(src1), c_int(src1.stride(0)), c_int(s1), _ptr(src2),
                           c_int(src2.stride(0) if src2 is not None else 0), c_int(s2), c_int(B), c_int(H), c_int(W),
                           c_int(C), _ptr(out), c_int(_is_bf16(out)), _stream()), "mmt_im2col3x3")
-    _count(1)
+    _count(1, "im2col3x3", _ev)
     return out
 
 
@@ -211,12 +230,13 @@ def corner_decode(x4, w5, b5, a3, a4, B, S, stride_px, img_sz, xyxy, cxcywh, sco
     _need_cuda(x4[0], xyxy, cxcywh)
     C4 = w5[0].numel()
     assert x4[0].stride(0) == x4[1].stride(0) and a3[0].stride(0) == a3[1].stride(0) and a4[0].stride(0) == a4[1].stride(0)
+    _ev = _begin()
     _lib.check(_corner_decode(_ptr(x4[0]), _ptr(x4[1]), c_int(x4[0].stride(0)), c_int(C4), _ptr(w5[0]), _ptr(w5[1]),
                               c_float(b5[0]), c_float(b5[1]), _ptr(a3[0]), _ptr(a3[1]), c_int(a3[0].stride(0)),
                               _ptr(a4[0]), _ptr(a4[1]), c_int(a4[0].stride(0)), c_int(B), c_int(S),
                               c_float(stride_px), c_float(img_sz), _ptr(score_maps), _ptr(xyxy), _ptr(cxcywh),
                               c_int(_is_bf16(x4[0])), _stream()), "mmt_corner_decode")
-    _count(2)
+    _count(2, "corner_decode", _ev)
 
 
 def msda(value, level_hw, sampling_loc, attn_weight, out=None):
@@ -230,18 +250,20 @@ def msda(value, level_hw, sampling_loc, attn_weight, out=None):
     if out is None:
         out = torch.empty((N, Lq, M * D), device=value.device, dtype=value.dtype)
     hw = (c_int * (2 * L))(*[int(v) for pair in level_hw for v in pair])
+    _ev = _begin()
     _lib.check(_msda(_ptr(value), hw, _ptr(loc), _ptr(aw), _ptr(out), c_int(N), c_int(S), c_int(M), c_int(D),
                      c_int(L), c_int(Lq), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_fwd")
-    _count(1)
+    _count(1, "msda", _ev)
     return out
 
 
 def msda_bimodal(value, offw, out, B, H, W, M=8, D=64, P=4):
     _need_cuda(value, offw, out)
     assert offw.dtype == torch.float32 and offw.stride(1) == 1 and value.is_contiguous() and out.is_contiguous()
+    _ev = _begin()
     _lib.check(_msda_bimodal(_ptr(value), _ptr(offw), c_int(offw.stride(0)), _ptr(out), c_int(B), c_int(H), c_int(W),
                              c_int(M), c_int(D), c_int(P), c_int(_is_bf16(value)), _stream()), "mmt_msda_bimodal_fwd")
-    _count(1)
+    _count(1, "msda_bimodal", _ev)
     return out
 
 
@@ -249,42 +271,50 @@ def mixattn(qkv0, qkv1, C, heads, tiles, max_keys, out, scale):
     _need_cuda(qkv0, tiles, out)
     assert tiles.dtype == torch.int32 and tiles.is_contiguous() and tiles.shape[1] == 16
     assert qkv0.stride(1) == 1 and out.stride(1) == 1
-    _lib.check(_mixattn(_ptr(qkv0), _ptr(qkv1), c_int(qkv0.stride(0)), c_int(C), c_int(heads), _ptr(tiles),
+    rows1 = qkv1.shape[0] if qkv1 is not None else 0
+    assert qkv1 is None or qkv1.stride(0) == qkv0.stride(0)
+    _ev = _begin()
+    _lib.check(_mixattn(_ptr(qkv0), c_int(qkv0.shape[0]), _ptr(qkv1), c_int(rows1), c_int(qkv0.stride(0)), c_int(C),
+                        c_int(heads), _ptr(tiles),
                         c_int(tiles.shape[0]), c_int(max_keys), _ptr(out), c_int(out.stride(0)), c_float(scale),
                         c_int(_is_bf16(qkv0)), _stream()), "mmt_mixattn_fwd")
-    _count(1)
+    _count(1, "mixattn", _ev)
     return out
 
 
 def ce_scores(qkv, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, scores):
     _need_cuda(qkv, partial_ws, scores)
+    _ev = _begin()
     _lib.check(_ce_scores(_ptr(qkv), c_int(qkv.stride(0)), c_int(C), c_int(heads), c_int(B), c_int(n_tok), c_int(Lt),
                           c_int(Ls), c_float(scale), _ptr(partial_ws), _ptr(scores), c_int(_is_bf16(qkv)), _stream()),
                "mmt_ce_scores")
-    _count(2)
+    _count(2, "ce_scores", _ev)
     return scores
 
 
 def ce_topk(scores, B, Ls, keep, gidx_in, gidx_keep, gidx_removed, order):
     _need_cuda(scores, gidx_in, gidx_keep, gidx_removed, order)
     assert order.dtype == torch.int32
+    _ev = _begin()
     _lib.check(_ce_topk(_ptr(scores), c_int(B), c_int(Ls), c_int(keep), _ptr(gidx_in), _ptr(gidx_keep),
                         _ptr(gidx_removed), _ptr(order), _stream()), "mmt_ce_topk")
-    _count(1)
+    _count(1, "ce_topk", _ev)
 
 
 def ce_gather_tokens(x, nseq, n_tok, Lt, order, Ls, keep, x_out):
     _need_cuda(x, order, x_out)
+    _ev = _begin()
     _lib.check(_ce_gather(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(order), c_int(Ls), c_int(keep),
                           _ptr(x_out), c_int(x.shape[-1]), _stream()), "mmt_ce_gather_tokens")
-    _count(1)
+    _count(1, "ce_gather_tokens", _ev)
 
 
 def ce_recover(x, nseq, n_tok, Lt, gidx, Lk, Ls0, out):
     _need_cuda(x, gidx, out)
+    _ev = _begin()
     _lib.check(_ce_recover(_ptr(x), c_int(nseq), c_int(n_tok), c_int(Lt), _ptr(gidx), c_int(Lk), c_int(Ls0),
                            _ptr(out), c_int(x.shape[-1]), c_int(_is_bf16(out)), _stream()), "mmt_ce_recover")
-    _count(1)
+    _count(1, "ce_recover", _ev)
 
 
 def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None):
@@ -301,7 +331,8 @@ def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None)
         shape = (rois.shape[0], C, ph, pw)
     if out is None:
         out = torch.empty(shape, device=feat.device, dtype=torch.float32)
+    _ev = _begin()
     _lib.check(_prroi(_ptr(feat), _ptr(rois), _ptr(out), c_int(rois.shape[0]), c_int(C), c_int(H), c_int(W), c_int(ph),
                       c_int(pw), c_float(spatial_scale), c_int(1 if channels_last else 0), _stream()), "mmt_prroi_fwd")
-    _count(1)
+    _count(1, "prroi_pool", _ev)
     return out
