@@ -5,16 +5,19 @@
 //   out[q, h*64:(h+1)*64] = softmax_k( q . k * scale ) v     over the key rows listed for the query tile
 // (the template/search asymmetry is WHICH key rows a query tile lists - there is no mask tensor).
 //
-// One CTA = one query tile (<= 128 rows) of one head; 2 CTAs are resident per SM (81 KB smem, 256 TMEM columns)
-// so that the softmax of one overlaps the loads / MMAs / epilogue of the other.  Keys are walked in 64-row blocks.
-//   warp 0     TMA producer : Q tile (2 x [64 x 64] boxes) and a 4-stage ring of K / V blocks, straight out of the
+// One CTA = one query tile (<= 128 rows) of one head; 2 CTAs are resident per SM (51 KB smem, 256 TMEM columns)
+// so that the softmax of one overlaps the loads / MMAs / epilogue of the other.  Keys are walked in super-blocks
+// of 128 (two 64-row TMA boxes); per-block fixed costs (barrier round trips, TMEM load latency, proxy fence)
+// dominate this small problem, so blocks are as large as TMEM allows with two CTAs per SM.
+//   warp 0     TMA producer : Q tile (2 x [64 x 64] boxes) and a ring of 2 x 2 K / V boxes, straight out of the
 //              packed qkv buffer (cp.async.bulk.tensor, 128B swizzle).
-//   warp 1     MMA issuer   : S = Q K^T  (tcgen05.mma M128 N64 K16 x4, both operands K-major) into a
-//              double-buffered TMEM tile; O += P V (A = P from smem, K-major; B = V block, MN-major) into TMEM.
-//   warps 2-5  softmax      : thread == query row.  EXACT two-pass softmax: pass 1 reads every S block for the row
-//              maximum; pass 2 recomputes S (tensor time is cheap here, the exponentials are the bound), forms
-//              p = exp2((s - max) * scale * log2 e), accumulates the row sum in fp32, writes P as bf16 into a
-//              double-buffered swizzled smem tile (the A operand of the PV MMA) - so O never needs rescaling.
+//   warp 1     MMA issuer   : S = Q K^T  (tcgen05.mma M128 N128 K16 x4, both operands K-major smem) into TMEM;
+//              O += P V with A = P read from TENSOR MEMORY and B = the V boxes in smem, MN-major (the probabilities
+//              never touch shared memory: operand reads from smem, not the MMA rate, bound an SS-mode PV here).
+//   warps 2-9  softmax      : two threads per query row (one 64-key box of the super-block each).  EXACT two-pass
+//              softmax: pass 1 reads every S block for the row maximum; pass 2 recomputes S (tensor time is cheap
+//              here), forms p = exp2((s - max) * scale * log2 e), accumulates the row sum and writes P as packed
+//              bf16 into TMEM with tcgen05.st (the A operand of the PV MMA) - O never needs rescaling.
 //              Epilogue: O * (1 / row sum) -> bf16 -> out.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -40,10 +43,9 @@ constexpr int ATC_KB = 64;                          // keys per block
 constexpr int ATC_STAGES = 4;
 constexpr int ATC_BLK_BYTES = ATC_KB * ATC_HD * 2;  // 8 KB
 constexpr int ATC_Q_BYTES = 128 * ATC_HD * 2;       // 16 KB
-constexpr int ATC_P_BYTES = 128 * ATC_KB * 2;       // 16 KB
-constexpr int ATC_THREADS = 192;
-constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 2 * ATC_P_BYTES + 1024 + 256;
-constexpr uint32_t ATC_TMEM_COLS = 256;             // O: [0,64)  S0: [64,128)  S1: [128,192)
+constexpr int ATC_THREADS = 320;
+constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 1280;
+constexpr uint32_t ATC_TMEM_COLS = 256;             // O: [0,64)  S: [64,192)  P: [192,256) (128 keys, bf16x2 per column)
 
 // kind::f16 instruction descriptor with B taken MN-major (bit 16): V blocks are [key][d] with d contiguous.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32_bmn(int m, int n) {
@@ -60,26 +62,48 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic for 2^f
+// (relative error 6e-4, far below the bf16 rounding of P), exponent patched in with an integer add.  Every fourth
+// probability takes this path so that the MUFU unit - the bound of the softmax - gets 25% less work.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;              // 1.5 * 2^23: integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// DBG: developer build of the same kernel that records clock64() at phase boundaries of the first softmax thread
+// (8 stamps per CTA) into `dbg`; the production instantiation (DBG = false) carries none of it.
+template <bool DBG>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int C,
-               const AttnTileTC* __restrict__ tiles, bf16* __restrict__ out, int ldo, float scale_log2e) {
+               const AttnTileTC* __restrict__ tiles, bf16* __restrict__ out, int ldo, float scale_log2e,
+               long long* __restrict__ dbg) {
+  auto stamp = [&](int slot) {
+    if (DBG && threadIdx.x == 64)
+      dbg[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = clock64();
+  };
+  stamp(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = smem_base;
   const uint32_t ring_smem = q_smem + ATC_Q_BYTES;
-  const uint32_t p_smem = ring_smem + ATC_STAGES * ATC_BLK_BYTES;
-  const uint32_t bar_base = p_smem + 2 * ATC_P_BYTES;
+  const uint32_t bar_base = ring_smem + ATC_STAGES * ATC_BLK_BYTES;
   auto kv_full = [&](int s) { return bar_base + 8u * s; };
   auto kv_empty = [&](int s) { return bar_base + 8u * (ATC_STAGES + s); };
   const uint32_t q_full = bar_base + 8u * (2 * ATC_STAGES);
-  auto s_full = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + 1 + b); };
-  auto s_empty = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + 3 + b); };
-  auto p_full = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + 5 + b); };
-  auto p_empty = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + 7 + b); };
+  const uint32_t s_full = bar_base + 8u * (2 * ATC_STAGES + 1);
+  const uint32_t s_empty = bar_base + 8u * (2 * ATC_STAGES + 3);
+  const uint32_t p_full = bar_base + 8u * (2 * ATC_STAGES + 5);
+  const uint32_t p_empty = bar_base + 8u * (2 * ATC_STAGES + 7);
   const uint32_t o_full = bar_base + 8u * (2 * ATC_STAGES + 9);
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * ATC_STAGES + 10);
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
+  float* smax = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2][128] partial row maxima
 
   const AttnTileTC t = tiles[blockIdx.x];
   const int h = blockIdx.y;
@@ -93,11 +117,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     nblk_seg[s] = s < t.nseg ? (t.k_len[s] + ATC_KB - 1) / ATC_KB : 0;
     nb += nblk_seg[s];
   }
+  const int nsb = (nb + 1) >> 1;   // super-blocks of two 64-key boxes
+  // box `blk` of the flattened list; a missing second box of the last super-block repeats the first one with len 0
+  // (its scores are masked out), so that every super-block is exactly two ring stages
   auto locate = [&](int blk, int& row0, int& len, int& buf) {
+    const bool ghost = blk >= nb;
+    if (ghost) blk = nb - 1;
     int s = 0;
     if (blk >= nblk_seg[0]) { blk -= nblk_seg[0]; s = 1; if (blk >= nblk_seg[1]) { blk -= nblk_seg[1]; s = 2; } }
     row0 = t.k_row0[s] + blk * ATC_KB;
-    len = min(ATC_KB, t.k_len[s] - blk * ATC_KB);
+    len = ghost ? 0 : min(ATC_KB, t.k_len[s] - blk * ATC_KB);
     buf = t.k_buf[s];
   };
 
@@ -106,12 +135,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     prefetch_tmap(&tm1);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(q_full, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1);
-      mbar_init(s_empty(b), 4);   // one arrive per softmax warp
-      mbar_init(p_full(b), 4);
-      mbar_init(p_empty(b), 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);   // one arrive per softmax warp
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -123,8 +150,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  stamp(1);
   const uint32_t tmem_o = tmem_base;
-  auto tmem_s = [&](int b) { return tmem_base + 64u + 64u * b; };
+  const uint32_t tmem_p = tmem_base + 192u;
+  const uint32_t tmem_s = tmem_base + 64u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -142,158 +171,191 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         tma_load_2d(ring_smem + stage * ATC_BLK_BYTES, buf ? &tm1 : &tm0, kv_full(stage), col, row0);
         if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
       };
-      for (int kb = 0; kb < nb; ++kb) load_blk(kb, C + h * ATC_HD);          // pass 1: K only
-      for (int kb = 0; kb <= nb; ++kb) {                                     // pass 2: K_kb, then V_(kb-1)
-        if (kb < nb) load_blk(kb, C + h * ATC_HD);
-        if (kb >= 1) load_blk(kb - 1, 2 * C + h * ATC_HD);
+      for (int sb = 0; sb < nsb; ++sb) {                                      // pass 1: K only
+        load_blk(2 * sb, C + h * ATC_HD);
+        load_blk(2 * sb + 1, C + h * ATC_HD);
+      }
+      for (int sb = 0; sb <= nsb; ++sb) {                                     // pass 2: K_sb, then V_(sb-1)
+        if (sb < nsb) { load_blk(2 * sb, C + h * ATC_HD); load_blk(2 * sb + 1, C + h * ATC_HD); }
+        if (sb >= 1) { load_blk(2 * sb - 2, 2 * C + h * ATC_HD); load_blk(2 * sb - 1, 2 * C + h * ATC_HD); }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, ATC_KB);
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 2 * ATC_KB);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, ATC_HD);
       const uint64_t qdesc = make_kmajor_sw128_desc(q_smem);
-      int stage = 0;
+      int stage = 0;           // always even here: a super-block is the stage pair (stage, stage + 1)
       uint32_t phase = 0;
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_s = [&](int g) {   // g = running S-block counter over both passes
-        const int b = g & 1;
-        mbar_wait(s_empty(b), ((g >> 1) & 1u) ^ 1u);
+      auto wait_pair = [&]() {
         mbar_wait(kv_full(stage), phase);
+        mbar_wait(kv_full(stage + 1), phase);
         tc_fence_after();
-        const uint64_t kdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATC_HD / 16; ++k) mma_bf16_ss(tmem_s(b), qdesc + 2u * k, kdesc + 2u * k, idesc_s, k ? 1u : 0u);
-        mma_commit(kv_empty(stage));
-        mma_commit(s_full(b));
-        if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
       };
-      for (int kb = 0; kb < nb; ++kb) issue_s(kb);
-      for (int kb = 0; kb <= nb; ++kb) {
-        if (kb < nb) issue_s(nb + kb);
-        if (kb >= 1) {
-          const int j = kb - 1, b = j & 1;
-          mbar_wait(p_full(b), (j >> 1) & 1u);
-          mbar_wait(kv_full(stage), phase);
-          tc_fence_after();
-          const uint64_t pdesc = make_kmajor_sw128_desc(p_smem + b * ATC_P_BYTES);
+      auto release_pair = [&]() {
+        mma_commit(kv_empty(stage));
+        mma_commit(kv_empty(stage + 1));
+        stage += 2;
+        if (stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+      };
+      auto issue_s = [&](int g) {   // g = running S-block counter over both passes
+        mbar_wait(s_empty, (g & 1u) ^ 1u);
+        wait_pair();
+        const uint64_t kdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);   // 128 key rows
+#pragma unroll
+        for (int k = 0; k < ATC_HD / 16; ++k) mma_bf16_ss(tmem_s, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k ? 1u : 0u);
+        mma_commit(s_full);
+        release_pair();
+      };
+      for (int sb = 0; sb < nsb; ++sb) issue_s(sb);
+      for (int sb = 0; sb <= nsb; ++sb) {
+        if (sb < nsb) issue_s(nsb + sb);
+        if (sb >= 1) {
+          const int j = sb - 1;
+          mbar_wait(p_full, j & 1u);
+          wait_pair();
           const uint64_t vdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);
 #pragma unroll
-          for (int k = 0; k < ATC_KB / 16; ++k)   // 16 keys per MMA: P advances 32 B inside the atom, V 16 rows = 2 KB
-            mma_bf16_ss(tmem_o, pdesc + 2u * k, vdesc + 128u * k, idesc_o, (j | k) ? 1u : 0u);
-          mma_commit(kv_empty(stage));
-          mma_commit(p_empty(b));
-          if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+          for (int k = 0; k < 2 * ATC_KB / 16; ++k)   // 16 keys per MMA: P advances 8 TMEM columns, V 16 rows = 2 KB
+            mma_bf16_ts(tmem_o, tmem_p + 8u * k, vdesc + 128u * k, idesc_o, (j | k) ? 1u : 0u);
+          mma_commit(p_empty);
+          release_pair();
         }
       }
       mma_commit(o_full);
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps (thread == query row)
+    // ------------------------------------------------------------------ softmax warps (two threads per query row)
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;               // which 32 of a block's 64 keys this thread handles
     const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     float m_row = -INFINITY;
-    // pass 1: row maximum of the raw scores
-    for (int g = 0; g < nb; ++g) {
-      const int b = g & 1;
+    // pass 1: row maximum of the raw scores (this thread: box `half` of every super-block)
+    auto row_max = [&](const uint32_t (&v)[32], int lim0, float m) {
+      if (lim0 >= 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < lim0) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      return m;
+    };
+    const uint32_t s_addr = tmem_s + lane_off + 64u * half;
+    for (int g = 0; g < nsb; ++g) {
       int row0, len, buf;
-      locate(g, row0, len, buf);
-      mbar_wait(s_full(b), (g >> 1) & 1u);
+      locate(2 * g + half, row0, len, buf);
+      mbar_wait(s_full, g & 1u);
+      if (g == 0) stamp(2);
       tc_fence_after();
       uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_s(b) + lane_off, v0);
-      tmem_ld_32x32(tmem_s(b) + lane_off + 32, v1);
+      tmem_ld_32x32(s_addr, v0);
+      tmem_ld_32x32(s_addr + 32, v1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(b));
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < len) m_row = fmaxf(m_row, __uint_as_float(v0[j]));
-        if (j + 32 < len) m_row = fmaxf(m_row, __uint_as_float(v1[j]));
-      }
+      if (lane == 0) mbar_arrive(s_empty);
+      m_row = row_max(v0, len, m_row);
+      m_row = row_max(v1, len - 32, m_row);
     }
+    stamp(3);
+    smax[half * 128 + r] = m_row;
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
+    m_row = fmaxf(m_row, smax[(half ^ 1) * 128 + r]);
     const float mc = m_row * scale_log2e;
     float l_row = 0.f;
-    uint8_t* p_gen = smem_raw + (p_smem - smem_u32(smem_raw));
-    // pass 2: probabilities -> smem (A operand of the PV MMA), row sums
-    for (int j = 0; j < nb; ++j) {
-      const int g = nb + j, b = g & 1, pb = j & 1;
+    // in place: word i of v becomes the packed pair (p[2i], p[2i+1]) - keeps the live register set at 64
+    auto probs = [&](uint32_t (&v)[32], int lim0) {
+      uint32_t* pk = v;
+      if (lim0 >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
+          const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
+          const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
+          l_row += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      } else if (lim0 <= 0) {      // nothing valid in this 32-key chunk (segment tail / ghost box): no exponentials
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc));
+          if (2 * i >= lim0) p0 = 0.f;
+          if (2 * i + 1 >= lim0) p1 = 0.f;
+          l_row += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      }
+    };
+    // a warp whose 32 query rows all lie beyond the tile's q_rows computes nothing (it still takes part in the
+    // barrier protocol and writes zero probabilities)
+    const bool warp_live = quad * 32 < t.q_rows;
+    // pass 2: probabilities -> TMEM (A operand of the PV MMAs); thread `half` fills columns [32 half, 32 half + 32)
+    for (int j = 0; j < nsb; ++j) {
+      const int g = nsb + j;
       int row0, len, buf;
-      locate(j, row0, len, buf);
-      mbar_wait(s_full(b), (g >> 1) & 1u);
+      locate(2 * j + half, row0, len, buf);
+      mbar_wait(s_full, g & 1u);
       tc_fence_after();
       uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_s(b) + lane_off, v0);
-      tmem_ld_32x32(tmem_s(b) + lane_off + 32, v1);
+      tmem_ld_32x32(s_addr, v0);
+      tmem_ld_32x32(s_addr + 32, v1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(b));
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float p0 = ex2_approx(fmaf(__uint_as_float(v0[2 * i]), scale_log2e, -mc));
-        float p1 = ex2_approx(fmaf(__uint_as_float(v0[2 * i + 1]), scale_log2e, -mc));
-        float p2 = ex2_approx(fmaf(__uint_as_float(v1[2 * i]), scale_log2e, -mc));
-        float p3 = ex2_approx(fmaf(__uint_as_float(v1[2 * i + 1]), scale_log2e, -mc));
-        if (2 * i >= len) p0 = 0.f;
-        if (2 * i + 1 >= len) p1 = 0.f;
-        if (2 * i + 32 >= len) p2 = 0.f;
-        if (2 * i + 33 >= len) p3 = 0.f;
-        // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA multiplies
-        const __nv_bfloat162 q01 = __floats2bfloat162_rn(p0, p1), q23 = __floats2bfloat162_rn(p2, p3);
-        const float2 f01 = __bfloat1622float2(q01), f23 = __bfloat1622float2(q23);
-        l_row += (f01.x + f01.y) + (f23.x + f23.y);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&q01);
-        pk[16 + i] = *reinterpret_cast<const uint32_t*>(&q23);
-      }
-      mbar_wait(p_empty(pb), ((j >> 1) & 1u) ^ 1u);
-      uint4* prow = reinterpret_cast<uint4*>(p_gen + pb * ATC_P_BYTES + r * 128);
-#pragma unroll
-      for (int c = 0; c < 8; ++c)   // 16-byte chunk c (keys 8c..8c+7) at slot c ^ (row & 7): the TMA/UMMA 128B swizzle
-        prow[c ^ (r & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      fence_proxy_async_smem();
+      if (lane == 0) mbar_arrive(s_empty);
+      // this thread's 64 keys: key 2c (low half) and 2c+1 (high half) in packed word c
+      probs(v0, warp_live ? len : 0);
+      mbar_wait(p_empty, (j & 1u) ^ 1u);          // the PV MMAs of the previous super-block have read P
+      tc_fence_after();
+      tmem_st_32x16(tmem_p + lane_off + 32u * half, v0);
+      probs(v1, warp_live ? len - 32 : 0);
+      tmem_st_32x16(tmem_p + lane_off + 32u * half + 16u, v1);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(pb));
+      if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l -> bf16 -> out
+    // epilogue: O / L -> bf16 -> out (this thread: 32 of the 64 head channels)
+    stamp(4);
     mbar_wait(o_full, 0);
+    stamp(5);
     tc_fence_after();
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(tmem_o + lane_off, o0);
-    tmem_ld_32x32(tmem_o + lane_off + 32, o1);
+    uint32_t o[32];
+    tmem_ld_32x32(tmem_o + lane_off + 32u * half, o);
+    smax[half * 128 + r] = l_row;                    // (the maxima were consumed before the previous bar.sync)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_row += smax[(half ^ 1) * 128 + r];
     tmem_ld_wait();
     if (r < t.q_rows) {
       const float inv = 1.f / l_row;
-      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD);
+      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD + 32 * half);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
+        w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
         dst[c] = w;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
-        dst[4 + c] = w;
       }
     }
   }
 
+  stamp(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, ATC_TMEM_COLS);
+  stamp(7);
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
@@ -332,16 +394,38 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid(n_tiles, heads);
-  attn_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tm0, tm1, C, reinterpret_cast<const AttnTileTC*>(tiles_dev),
-                                                          reinterpret_cast<bf16*>(out), ldo,
-                                                          scale * 1.4426950408889634f);
+  attn_tc_kernel<false><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
+      tm0, tm1, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), reinterpret_cast<bf16*>(out), ldo,
+      scale * 1.4426950408889634f, nullptr);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MMT_OK : (int)e;
 }
 
+// Developer hook (not part of the declared ABI): same launch with phase time stamps, dbg = [heads * n_tiles * 8] int64.
+int launch_attn_tc_dbg(const void* qkv0, int rows0, int ld, int C, int heads, const int* tiles_dev, int n_tiles, void* out,
+                       int ldo, float scale, long long* dbg, cudaStream_t stream) {
+  CUtensorMap tm0;
+  int rc = make_qkv_tmap(&tm0, qkv0, rows0, 3 * C, ld);
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(n_tiles, heads);
+  attn_tc_kernel<true><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
+      tm0, tm0, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), reinterpret_cast<bf16*>(out), ldo,
+      scale * 1.4426950408889634f, dbg);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? MMT_OK : (int)e;
+}
+
 }  // namespace mmt
+
+extern "C" int mmt_dev_attn_timing(const void* qkv0, int rows0, int ld, int C, int heads, const int* tiles_dev,
+                                   int n_tiles, void* out, int ldo, float scale, long long* dbg, void* stream) {
+  return mmt::launch_attn_tc_dbg(qkv0, rows0, ld, C, heads, tiles_dev, n_tiles, out, ldo, scale, dbg,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
