@@ -121,6 +121,21 @@ int mmt_im2col3x3(const void* src1, int ld1, int s1, const void* src2, int ld2, 
                   void* out, int is_bf16, void* stream);
 
 /*
+ * Conv2d(C -> N, k=3, pad=1) + bias + activation on a bf16 NHWC map in [B*H*W, ld_in] as an IMPLICIT GEMM on the
+ * tensor cores: the K loop walks 9 taps x channel chunks and every A slice is one 4-D TMA box of the map shifted by
+ * the tap offset (out-of-image pixels arrive as zeros = the zero padding); no im2col matrix exists.  Wt [N, 9*C]
+ * holds the filter as (ky, kx, c) with eval-BatchNorm folded in.  out [B*H*W, ldo] bf16 or fp32.
+ * Reference: conv() lib/models/mixformer_cvt/head.py:7-20 as used in get_score_map :159-198.
+ */
+int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, int C, const void* Wt, int ldw, int N,
+                     const float* bias, int act, void* out, int ldo, int out_fp32, void* stream);
+
+/* out(b,y,x,:) = src1[b, y/s1, x/s1, :] (+ src2[b, y/s2, x/s2, :]), bf16 NHWC, dense out [B*H*W, C]:
+ * F.interpolate(scale_factor=2|4) + add of the pyramid head (head.py:166-178), the input of the next 3x3 conv. */
+int mmt_upsample_add(const void* src1, int ld1, int s1, const void* src2, int ld2, int s2, int B, int H, int W, int C,
+                     void* out, void* stream);
+
+/*
  * Corner decode for both corners: score = conv5_1x1(x4) + up4(a3) + up2(a4), softmax over S*S, soft-argmax,
  * xyxy / img_sz and box_xyxy_to_cxcywh.  score_maps (fp32 [B,2,S*S], raw logits) may be NULL.
  * Reference: head.py:181,198-212 (coords :138-145), lib/utils/box_ops.py:27-31, forward_box_head mixformer.py:325-338.

@@ -50,6 +50,17 @@ struct GemmEpi {
   int vec_ok;             // all vector-store alignment preconditions hold
 };
 
+// Implicit-GEMM geometry of a Conv2d(k=3, pad=1) on an NHWC map [B, H, W, C]: an M tile is a BW x BH pixel box
+// (BW * BH <= 128) of one image; the K loop walks 9 taps x ceil(C / 64) channel chunks, each A slice being ONE 4-D
+// TMA box shifted by the tap offset (out-of-image pixels and channels arrive as zeros).  enabled == 0: plain GEMM.
+struct GemmConv {
+  int enabled;
+  int H, W, C;
+  int BW, BH;
+  int tiles_x, tiles_y;    // boxes per image
+  int cchunks;             // ceil(C / 64)
+};
+
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -66,7 +77,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         int M, int N, int K, GemmEpi ep) {
+                         int M, int N, int K, GemmEpi ep, GemmConv cv) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,9 +95,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_per_img = cv.tiles_x * cv.tiles_y;
+  const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;
   const int num_tiles = n_tiles * m_tiles;
-  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int num_kb = cv.enabled ? 9 * cv.cchunks : (K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -116,15 +128,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int mt = tile / n_tiles;
+        const int m0 = mt * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, m0);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        if (!cv.enabled) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, n0);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        } else {
+          const int img = mt / tiles_per_img, bt = mt % tiles_per_img;
+          const int x0 = (bt % cv.tiles_x) * cv.BW, y0 = (bt / cv.tiles_x) * cv.BH;
+          const uint32_t a_bytes = static_cast<uint32_t>(cv.BW * cv.BH) * GEMM_BK * 2;
+          for (int tap = 0; tap < 9; ++tap) {
+            for (int cc = 0; cc < cv.cchunks; ++cc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), a_bytes + Cfg::B_BYTES);
+              const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+              tma_load_4d(a_dst, &tmA, full_bar(stage), cc * GEMM_BK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, img);
+              tma_load_2d(a_dst + Cfg::A_BYTES, &tmB, full_bar(stage), tap * cv.C + cc * GEMM_BK, n0);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
         }
       }
     }
@@ -186,9 +215,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int mt = tile / n_tiles;
       const int n0 = (tile % n_tiles) * BN;
-      const int row0 = m0 + quad * 32;
+      // global output row of tile-local row i (or -1): plain GEMM rows are contiguous; conv rows are the pixels
+      // of the tile's BW x BH box that fall inside the image
+      int cimg = 0, cx0 = 0, cy0 = 0;
+      if (cv.enabled) {
+        cimg = mt / tiles_per_img;
+        const int bt = mt % tiles_per_img;
+        cx0 = (bt % cv.tiles_x) * cv.BW;
+        cy0 = (bt / cv.tiles_x) * cv.BH;
+      }
+      auto grow_of = [&](int i) -> int {
+        if (!cv.enabled) {
+          const int g = mt * GEMM_BM + i;
+          return g < M ? g : -1;
+        }
+        const int by = i / cv.BW, bx = i - by * cv.BW;
+        const int y = cy0 + by, x = cx0 + bx;
+        return (by < cv.BH && y < cv.H && x < cv.W) ? (cimg * cv.H + y) * cv.W + x : -1;
+      };
+      const int lrow0 = quad * 32;
       const int rr_f = lane / VPR, cc_f = lane % VPR;          // fp32-out lane -> (row in group, vector)
       const int rr_h = lane / LPR_H, cc_h = lane % LPR_H;      // bf16-out lane -> (row in group, 8-column group)
       // per-chunk prefetch registers
@@ -211,8 +258,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (ep.resid) {
 #pragma unroll
           for (int it = 0; it < IT_F; ++it) {
-            const int grow = row0 + it * (32 / VPR) + rr_f;
-            if (grow < M)
+            const int grow = grow_of(lrow0 + it * (32 / VPR) + rr_f);
+            if (grow >= 0)
               rv[it] = __ldcs(reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(grow) * ep.ldr + nb) + cc_f);
           }
         }
@@ -246,7 +293,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int it = 0; it < IT_F; ++it) {
               const int r = it * (32 / VPR) + rr_f;
-              const int grow = row0 + r;
+              const int grow = grow_of(lrow0 + r);
               const uint4 w = stg4[r * VPR + (cc_f ^ key_of(r))];
               float x[4] = {__uint_as_float(w.x) + b0.x, __uint_as_float(w.y) + b0.y, __uint_as_float(w.z) + b0.z,
                             __uint_as_float(w.w) + b0.w};
@@ -257,7 +304,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
               }
-              if (grow < M) {
+              if (grow >= 0) {
                 if (ep.rowadd) {
                   const float4 p = __ldg(reinterpret_cast<const float4*>(
                                              ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb) + cc_f);
@@ -273,7 +320,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int it = 0; it < IT_H; ++it) {
               const int r = it * (32 / LPR_H) + rr_h;
-              const int grow = row0 + r;
+              const int grow = grow_of(lrow0 + r);
               const uint4 w0 = stg4[r * VPR + ((2 * cc_h) ^ key_of(r))];
               const uint4 w1 = stg4[r * VPR + ((2 * cc_h + 1) ^ key_of(r))];
               float x[8] = {__uint_as_float(w0.x) + b0.x, __uint_as_float(w0.y) + b0.y, __uint_as_float(w0.z) + b0.z,
@@ -286,7 +333,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k], 0.f);
               }
-              if (grow < M) {
+              if (grow >= 0) {
                 if (ep.rowadd) {
                   const float4* pr = reinterpret_cast<const float4*>(
                       ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb) + 2 * cc_h;
@@ -302,9 +349,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
           __syncwarp();
-        } else if (row0 + lane < M) {
+        } else if (grow_of(lrow0 + lane) >= 0) {
           // ragged / unaligned tail: scalar, bounds-checked, thread == row
-          const int row = row0 + lane;
+          const int row = grow_of(lrow0 + lane);
           const float* resid_row = ep.resid ? ep.resid + static_cast<size_t>(row) * ep.ldr : nullptr;
           const float* rowadd_row =
               ep.rowadd ? ep.rowadd + static_cast<size_t>(row % ep.rowadd_period) * N : nullptr;
@@ -375,7 +422,7 @@ static int num_sms() {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
-                       int max_ctas, cudaStream_t stream) {
+                       const GemmConv& cv, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tmB;
   int rc = make_tmap_2d(&tmB, W, N, K, ldw, BN);
@@ -387,10 +434,11 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, in
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int tiles = cdiv(M, GEMM_BM) * cdiv(N, BN);
+  const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * cv.tiles_x * cv.tiles_y : cdiv(M, GEMM_BM);
+  const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, cv);
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -407,6 +455,47 @@ static int pick_bn(int N) {
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
+                         const GemmConv& cv, int max_ctas, cudaStream_t s) {
+  switch (pick_bn(N)) {
+    case 256: return launch_gemm<256>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 192: return launch_gemm<192>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 128: return launch_gemm<128>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 96: return launch_gemm<96>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 64: return launch_gemm<64>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 48: return launch_gemm<48>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 32: return launch_gemm<32>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    default: return launch_gemm<16>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+  }
+}
+
+// NHWC map [B, H, W, C] (row stride ld elements) as a 4-D tensor; box = 64 channels x BW x BH pixels of one image.
+static int make_tmap_nhwc(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int ld, int BW, int BH) {
+  auto fn = get_encode_fn();
+  if (!fn) return MMT_ERR_UNSUPPORTED;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(W) * ld * 2,
+                        static_cast<cuuint64_t>(H) * W * ld * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(BW), static_cast<cuuint32_t>(BH), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
+}
+
+// pixel box of <= 128 pixels that wastes the fewest MMA rows on an H x W map
+static void pick_conv_box(int H, int W, int* BW, int* BH) {
+  double best = -1.0;
+  for (int bw = 1; bw <= W && bw <= 128; ++bw) {
+    const int bh = 128 / bw < H ? 128 / bw : H;
+    if (bh < 1) continue;
+    const double eff = static_cast<double>(H) * W / (static_cast<double>(cdiv(W, bw)) * cdiv(H, bh) * 128.0);
+    if (eff > best + 1e-9) { best = eff; *BW = bw; *BH = bh; }
+  }
 }
 
 }  // namespace mmt
@@ -431,15 +520,27 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
   CUtensorMap tmA;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
   if (rc) return rc;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (pick_bn(N)) {
-    case 256: return launch_gemm<256>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 192: return launch_gemm<192>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 128: return launch_gemm<128>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 96: return launch_gemm<96>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 64: return launch_gemm<64>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 48: return launch_gemm<48>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    case 32: return launch_gemm<32>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-    default: return launch_gemm<16>(tmA, W, ldw, M, N, K, ep, max_ctas, s);
-  }
+  GemmConv cv = {};
+  return dispatch_gemm(tmA, W, ldw, M, N, K, ep, cv, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, int C, const void* Wt, int ldw, int N,
+                                const float* bias, int act, void* out, int ldo, int out_fp32, void* stream) {
+  using namespace mmt;
+  MMT_CHECK_ARG(in && Wt && out && B > 0 && H > 0 && W > 0 && C > 0 && N > 0);
+  MMT_CHECK_ARG(ld_in >= C && (ld_in % 8) == 0 && ldw >= 9 * C && (ldw % 8) == 0 && ldo >= N);
+  MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
+  GemmConv cv = {};
+  cv.enabled = 1; cv.H = H; cv.W = W; cv.C = C;
+  pick_conv_box(H, W, &cv.BW, &cv.BH);
+  cv.tiles_x = cdiv(W, cv.BW); cv.tiles_y = cdiv(H, cv.BH); cv.cchunks = cdiv(C, GEMM_BK);
+  GemmEpi ep;
+  ep.bias = bias; ep.resid = nullptr; ep.rowadd = nullptr; ep.out = out;
+  ep.ldr = 0; ep.rowadd_period = 0; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  ep.vec_ok = al16(out) && (out_fp32 ? (ldo % 4 == 0) : (ldo % 8 == 0)) && (!bias || al16(bias));
+  CUtensorMap tmA;
+  int rc = make_tmap_nhwc(&tmA, in, B, H, W, C, ld_in, cv.BW, cv.BH);
+  if (rc) return rc;
+  return dispatch_gemm(tmA, Wt, ldw, B * H * W, N, 9 * C, ep, cv, 0, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -290,6 +290,39 @@ __global__ void im2col3x3_kernel(const T* __restrict__ src1, int ld1, int s1, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// upsample_add: out(b, y, x, :) = src1[b, y / s1, x / s1, :] (+ src2[b, y / s2, x / s2, :]) on NHWC maps, bf16, the
+// add in fp32 with one rounding (F.interpolate(scale_factor=2|4) + add, lib/models/mixformer_cvt/head.py:166-178).
+// Materialises the input of the implicit-GEMM 3x3 convolutions of the pyramid head once (instead of 9 im2col copies).
+__global__ void upsample_add_kernel(const bf16* __restrict__ src1, int ld1, int s1, const bf16* __restrict__ src2,
+                                    int ld2, int s2, int B, int H, int W, int C, bf16* __restrict__ out) {
+  const int cvn = C / 8;
+  const size_t total = static_cast<size_t>(B) * H * W * cvn;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = i % cvn;
+    size_t r = i / cvn;
+    const int x = r % W;
+    r /= W;
+    const int y = r % H;
+    const int b = r / H;
+    const int H1 = H / s1, W1 = W / s1;
+    uint4 v = *reinterpret_cast<const uint4*>(src1 + (static_cast<size_t>(b) * H1 * W1 + (y / s1) * W1 + x / s1) * ld1 + cv * 8);
+    if (src2) {
+      const int H2 = H / s2, W2 = W / s2;
+      const uint4 w = *reinterpret_cast<const uint4*>(src2 + (static_cast<size_t>(b) * H2 * W2 + (y / s2) * W2 + x / s2) * ld2 + cv * 8);
+      __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
+      const __nv_bfloat162* c = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __bfloat1622float2(a[k]), fc = __bfloat1622float2(c[k]);
+        a[k] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Corner decode: score = conv5_1x1(x4) + up4(a3) + up2(a4); softmax over S*S; soft-argmax expectation
 // with coord = stride * index; output (x, y) / img_sz  (lib/models/mixformer_cvt/head.py:181,198-212,
 // coordinate tables :138-145).  grid = (B, 2 corners); corner c uses the c-th pointer set.
@@ -467,6 +500,20 @@ extern "C" int mmt_im2col3x3(const void* src1, int ld1, int s1, const void* src2
     im2col3x3_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(src1), ld1, s1, reinterpret_cast<const bf16*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<bf16*>(out));
   else
     im2col3x3_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src1), ld1, s1, reinterpret_cast<const float*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<float*>(out));
+  MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_upsample_add(const void* src1, int ld1, int s1, const void* src2, int ld2, int s2, int B, int H, int W,
+                                int C, void* out, void* stream) {
+  MMT_CHECK_ARG(src1 && out && B > 0 && H > 0 && W > 0 && s1 > 0 && H % s1 == 0 && W % s1 == 0);
+  MMT_CHECK_ARG(!src2 || (s2 > 0 && H % s2 == 0 && W % s2 == 0));
+  MMT_CHECK_ARG(C % 8 == 0 && ld1 % 8 == 0 && (!src2 || ld2 % 8 == 0));
+  MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(src1) & 15) == 0 && (reinterpret_cast<uintptr_t>(src2) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
+  upsample_add_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src1), ld1, s1, reinterpret_cast<const bf16*>(src2), ld2, s2, B, H, W, C,
+      reinterpret_cast<bf16*>(out));
   MMT_RETURN_LAST_ERROR();
 }
 

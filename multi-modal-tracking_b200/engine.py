@@ -366,6 +366,23 @@ class ForwardEngine:
         return fused
 
     # ------------------------------------------------------------------------------------------ head
+    def _conv3x3(self, src, B, H, W, C, w, b, out, tag, up=None):
+        """Conv2d(k=3, pad=1) + folded BN + ReLU on NHWC rows.  `up` = (src1, s1, src2, s2): the conv input is
+        up_s1(src1) + up_s2(src2) (nearest), head.py:166-178.  bf16: implicit GEMM over 4-D TMA boxes (the upsampled
+        sum is materialised once); fp32 parity mode: im2col (upsampling folded into the gather) + SIMT GEMM."""
+        if self.bf16:
+            if up is not None:
+                src1, s1, src2, s2 = up
+                src = ops.upsample_add(src1, s1, B, H, W, C, self._buf(tag, f"up{H}", (B * H * W, C), self.act), src2, s2)
+            return ops.conv3x3(src, B, H, W, C, w, b, ops.ACT_RELU, out)
+        col = self._buf(tag, "col", (self._colmax,), self.act)[: B * H * W * 9 * C].view(B * H * W, 9 * C)
+        if up is not None:
+            src1, s1, src2, s2 = up
+            ops.im2col3x3(src1, s1, B, H, W, C, col, src2, s2)
+        else:
+            ops.im2col3x3(src, 1, B, H, W, C, col)
+        return ops.gemm(col, w, b, ops.ACT_RELU, out=out)
+
     def _run_head(self, feat, B, want_maps=True):
         """Pyramid corner head on NHWC rows feat [B*gs*gs, C] -> boxes cxcywh [B,4] (+ raw score maps)."""
         H = self.head
@@ -374,38 +391,33 @@ class ForwardEngine:
         C = feat.shape[1]
         tag = ("head", B)
         n18, n36, n72 = B * gs * gs, B * 4 * gs * gs, B * 16 * gs * gs
-        colmax = max(n18 * 9 * C, n36 * 9 * (ch // 2), n72 * 9 * (ch // 4))
-        col = self._buf(tag, "col", (colmax,), self.act)
-        view = lambda rows, k: col[: rows * k].view(rows, k)
+        self._colmax = max(n18 * 9 * C, n36 * 9 * (ch // 2), n72 * 9 * (ch // 4))
         s1 = self._buf(tag, "s1", (n18, self.s1_width), self.act)
-        ops.gemm(ops.im2col3x3(feat, 1, B, gs, gs, C, view(n18, 9 * C)), H["s1_w"], H["s1_b"], ops.ACT_RELU, out=s1)
+        self._conv3x3(feat, B, gs, gs, C, H["s1_w"], H["s1_b"], s1, tag)
         sl = lambda n: s1[:, self.s1_cols[n][0]: self.s1_cols[n][1]]
         x4s, a3s, a4s = [], [], []
         for c in ("tl", "br"):
             x2 = self._buf(tag, "x2" + c, (n18, ch // 2), self.act)
-            ops.gemm(ops.im2col3x3(sl(f"conv1_{c}"), 1, B, gs, gs, ch, view(n18, 9 * ch)), H[f"conv2_{c}_w"],
-                     H[f"conv2_{c}_b"], ops.ACT_RELU, out=x2)
+            self._conv3x3(sl(f"conv1_{c}"), B, gs, gs, ch, H[f"conv2_{c}_w"], H[f"conv2_{c}_b"], x2, tag)
             # up-1: conv3(up2(adjust1(x)) + up2(x2)) at 2gs x 2gs
             x3 = self._buf(tag, "x3" + c, (n36, ch // 4), self.act)
-            ops.gemm(ops.im2col3x3(sl(f"adjust1_{c}"), 2, B, 2 * gs, 2 * gs, ch // 2, view(n36, 9 * (ch // 2)), x2, 2),
-                     H[f"conv3_{c}_w"], H[f"conv3_{c}_b"], ops.ACT_RELU, out=x3)
+            self._conv3x3(None, B, 2 * gs, 2 * gs, ch // 2, H[f"conv3_{c}_w"], H[f"conv3_{c}_b"], x3, tag,
+                          up=(sl(f"adjust1_{c}"), 2, x2, 2))
             # up-2: conv4(up4(adjust2(x)) + up2(x3)) at 4gs x 4gs
             x4 = self._buf(tag, "x4" + c, (n72, ch // 8), self.act)
-            ops.gemm(ops.im2col3x3(sl(f"adjust2_{c}"), 4, B, 4 * gs, 4 * gs, ch // 4, view(n72, 9 * (ch // 4)), x3, 2),
-                     H[f"conv4_{c}_w"], H[f"conv4_{c}_b"], ops.ACT_RELU, out=x4)
+            self._conv3x3(None, B, 4 * gs, 4 * gs, ch // 4, H[f"conv4_{c}_w"], H[f"conv4_{c}_b"], x4, tag,
+                          up=(sl(f"adjust2_{c}"), 4, x3, 2))
             # side branches: adjust3 on x2 (gs), adjust4 on x3 (2gs)
             a = x2
             for j, co in enumerate((ch // 4, ch // 8, 1)):
                 o = self._buf(tag, f"a3{c}{j}", (n18, co), self.act)
-                ops.gemm(ops.im2col3x3(a, 1, B, gs, gs, a.shape[1], view(n18, 9 * a.shape[1])), H[f"adjust3_{c}.{j}_w"],
-                         H[f"adjust3_{c}.{j}_b"], ops.ACT_RELU, out=o)
+                self._conv3x3(a, B, gs, gs, a.shape[1], H[f"adjust3_{c}.{j}_w"], H[f"adjust3_{c}.{j}_b"], o, tag)
                 a = o
             a3s.append(a)
             a = x3
             for j, co in enumerate((ch // 8, 1)):
                 o = self._buf(tag, f"a4{c}{j}", (n36, co), self.act)
-                ops.gemm(ops.im2col3x3(a, 1, B, 2 * gs, 2 * gs, a.shape[1], view(n36, 9 * a.shape[1])),
-                         H[f"adjust4_{c}.{j}_w"], H[f"adjust4_{c}.{j}_b"], ops.ACT_RELU, out=o)
+                self._conv3x3(a, B, 2 * gs, 2 * gs, a.shape[1], H[f"adjust4_{c}.{j}_w"], H[f"adjust4_{c}.{j}_b"], o, tag)
                 a = o
             a4s.append(a)
             x4s.append(x4)

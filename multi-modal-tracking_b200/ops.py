@@ -225,6 +225,40 @@ def im2col3x3(src1, s1, B, H, W, C, out, src2=None, s2=1):
     return out
 
 
+_conv3x3 = _lib.fn("mmt_conv3x3_bf16")
+_upsample_add = _lib.fn("mmt_upsample_add")
+
+
+def conv3x3(src, B, H, W, C, w, bias, act, out):
+    """Implicit-GEMM Conv2d(k=3, pad=1)+bias+act: src bf16 rows [B*H*W, ld] (channel-slice views allowed, C channels
+    used), w bf16 [N, 9*C] packed (ky, kx, c), out [B*H*W, N] bf16/fp32 (column-slice views allowed)."""
+    _need_cuda(src, w, out)
+    assert src.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and src.stride(1) == 1 and out.stride(1) == 1
+    assert src.shape[0] == B * H * W and w.shape[1] == 9 * C and out.shape == (B * H * W, w.shape[0])
+    N = w.shape[0]
+    prof = PROFILER
+    ev = prof.begin() if prof is not None else None
+    _lib.check(_conv3x3(_ptr(src), c_int(src.stride(0)), c_int(B), c_int(H), c_int(W), c_int(C), _ptr(w),
+                        c_int(w.stride(0)), c_int(N), _ptr(bias), c_int(act), _ptr(out), c_int(out.stride(0)),
+                        c_int(1 if out.dtype == torch.float32 else 0), _stream()), "mmt_conv3x3_bf16")
+    _count()
+    if ev is not None:
+        prof.end(ev, 2.0 * B * H * W * N * 9 * C)
+    return out
+
+
+def upsample_add(src1, s1, B, H, W, C, out, src2=None, s2=1):
+    _need_cuda(src1, out)
+    assert src1.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert out.shape == (B * H * W, C) and src1.stride(1) == 1 and (src2 is None or src2.stride(1) == 1)
+    _ev = _begin()
+    _lib.check(_upsample_add(_ptr(src1), c_int(src1.stride(0)), c_int(s1), _ptr(src2),
+                             c_int(src2.stride(0) if src2 is not None else 0), c_int(s2), c_int(B), c_int(H), c_int(W),
+                             c_int(C), _ptr(out), _stream()), "mmt_upsample_add")
+    _count(1, "upsample_add", _ev)
+    return out
+
+
 def corner_decode(x4, w5, b5, a3, a4, B, S, stride_px, img_sz, xyxy, cxcywh, score_maps=None):
     """x4/a3/a4: (tl, br) pairs of row views; w5: (tl, br) fp32 [C4]; b5: (tl, br) floats."""
     _need_cuda(x4[0], xyxy, cxcywh)
