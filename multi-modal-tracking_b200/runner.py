@@ -27,9 +27,10 @@ def gather_boxes(boxes: torch.Tensor, group=None) -> torch.Tensor | None:
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return boxes.unsqueeze(0)
-    out = torch.empty((dist.get_world_size(group),) + tuple(boxes.shape), dtype=boxes.dtype, device=boxes.device)
-    dist.all_gather_into_tensor(out, boxes.contiguous(), group=group)
-    return out
+    world = dist.get_world_size(group)
+    out = torch.empty((world * boxes.shape[0],) + tuple(boxes.shape[1:]), dtype=boxes.dtype, device=boxes.device)
+    dist.all_gather_into_tensor(out, boxes.contiguous(), group=group)      # rank-major concatenation
+    return out.view((world,) + tuple(boxes.shape))
 
 
 def unshard_boxes(gathered: torch.Tensor, n_sequences: int) -> torch.Tensor:
