@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work (rank 0, N=1)")
     ap.add_argument("--no-profile", action="store_true", help="skip per-GEMM CUDA-event bracketing")
+    ap.add_argument("--no-latency", action="store_true", help="skip the bs=1 per-frame latency measurement")
     ap.add_argument("--breakdown", action="store_true",
                     help="developer aid: after the timed regions, run 3 more steps with EVERY op bracketed by CUDA "
                          "events and print the per-class table to stderr")
@@ -267,6 +268,37 @@ def main():
     e2e_value = n_seq_total * args.steps / (float(t2.item()) * 1e-3)
     assert bool(torch.isfinite(hb).all())
 
+    # ---- bs=1 per-frame latency (second half of BASELINE.json's metric), whole forward replayed as one CUDA graph
+    lat = None
+    if world == 1 and not args.no_latency:
+        host1 = synthetic.make_inputs(variant, cfg, 1, 99, pin=True)
+        dev1 = [to_dev(a) for a in host1]
+        model.enable_cuda_graph(True)
+        for _ in range(10):
+            model(*dev1)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+        for a, b in evs:
+            a.record()
+            model(*dev1)
+            b.record()
+            torch.cuda.synchronize()
+        dev_ms = sorted(a.elapsed_time(b) for a, b in evs)
+        fs1 = runner.FrameStep(model, dev)
+        for _ in range(10):
+            fs1.step(*host1)
+        wall = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            fs1.step(*host1)
+            wall.append((time.perf_counter() - t0) * 1e3)
+        wall.sort()
+        model.enable_cuda_graph(False)
+        lat = {"batch": 1, "mode": "one CUDA graph replay per frame", "device_p50_ms": dev_ms[100], "device_p99_ms": dev_ms[197],
+               "e2e_host_p50_ms": wall[100], "e2e_host_p99_ms": wall[197],
+               "note": "device = CUDA events around model(crops on device); e2e_host = wall clock of FrameStep.step "
+                       "(pinned host crops -> H2D -> graph replay -> D2H box -> sync)"}
+
     if args.breakdown and rank == 0:
         bp = ops.LaunchProfiler(all_ops=True)
         ops.PROFILER = bp
@@ -313,6 +345,7 @@ def main():
         "step_tensor_tflops_per_gpu": step_tflops,
         "step_tensor_frac_of_measured_peak": step_tflops / peaks["bf16_tflops"],
         "clocks": clocks.summary(),
+        "latency_bs1": lat,
     }
     if world == 1 and args.cpu_budget > 0:
         v, cores, sample = cpu_port_frames_per_s(variant, args.cpu_budget)

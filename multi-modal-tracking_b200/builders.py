@@ -249,6 +249,48 @@ class _EngineModule(nn.Module):
         self._engine = None
         self._packed_version = -1
         self._version = 0
+        self._use_graph = False
+        self._graphs = {}
+
+    def enable_cuda_graph(self, on: bool = True):
+        """Replay the whole forward (~240 kernel launches) as ONE CUDA graph per batch size: inputs are copied into
+        static device buffers, the graph is replayed on the current stream and fresh copies of the boxes are returned.
+        Removes the per-launch host cost, which is what bounds the bs=1 per-frame latency."""
+        self._use_graph = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
+
+    def _graphed_forward(self, template, online_template, search):
+        eng = self.engine()
+        flat = lambda a: list(a) if isinstance(a, (list, tuple)) else [a]
+        ins = flat(template) + flat(online_template) + flat(search)
+        key = (id(eng), tuple(tuple(t.shape) for t in ins))
+        g = self._graphs.get(key)
+        if g is None:
+            for t in ins:
+                if not t.is_cuda:
+                    raise NotImplementedError("mmt_b200 forward is CUDA-only (no CPU fallback)")
+            static = [torch.empty_like(t, dtype=torch.float32).contiguous() for t in ins]
+            for d, t in zip(static, ins):
+                d.copy_(t)
+            n = len(flat(template))
+            regroup = (lambda xs: xs) if isinstance(template, (list, tuple)) else (lambda xs: xs[0])
+            args = (regroup(static[:n]), regroup(static[n:2 * n]), regroup(static[2 * n:]))
+            eng.forward(*args, want_maps=False)          # warm-up: workspaces, function attributes, tile tables
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = eng.forward(*args, want_maps=False)
+            g = (graph, static, res)
+            self._graphs[key] = g
+        graph, static, res = g
+        for d, t in zip(static, ins):
+            d.copy_(t, non_blocking=True)
+        graph.replay()
+        out = dict(res)
+        out["pred_boxes"] = res["pred_boxes"].clone()
+        return out
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -275,6 +317,7 @@ class _EngineModule(nn.Module):
             # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
             raise NotImplementedError("mmt_b200 models run on CUDA only: call .cuda() first (no CPU fallback)")
         if self._engine is None or self._packed_version != self._version:
+            self._graphs = {}
             self._engine = ForwardEngine(self.variant, self._cfg, self.state_dict(), dev, self.precision)
             self._packed_version = self._version
         return self._engine
@@ -306,6 +349,8 @@ class MixFormer(_EngineModule):
     @torch.no_grad()
     def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None):
         sq = lambda t: t.squeeze(0) if t.dim() == 5 else t
+        if self._use_graph:
+            return self._finish(self._graphed_forward(sq(template), sq(online_template), sq(search)))
         return self._finish(self.engine().forward(sq(template), sq(online_template), sq(search)))
 
     def forward_box_head(self, search):
@@ -335,6 +380,8 @@ class MixFormer_RGBT(_EngineModule):
             # training-time CE schedule / template mask (lib/utils/ce_utils.py); the test-time trackers never
             # pass them (lib/test/tracker/asymmetric_shared_ce.py:96-98)
             raise NotImplementedError("ce_template_mask / ce_keep_rate are training-only arguments")
+        if self._use_graph and not return_features:
+            return self._finish(self._graphed_forward(list(template), list(online_template), list(search)))
         res = self.engine().forward(list(template), list(online_template), list(search))
         return self._finish(res, return_features)
 

@@ -294,7 +294,11 @@ class ForwardEngine:
         per_ln = stacked and self.variant in PER_MODALITY_LN
         gidx = None
         if self.ce_loc:
-            gidx = torch.arange(Ls, device=self.dev, dtype=torch.float32).repeat(nseq, 1).contiguous()
+            key = ("gidx0", nseq, Ls)
+            gidx = self._ws.get(key)        # global search-token indices 0..Ls-1 per sequence (float32 like the
+            if gidx is None:                # reference, asymmetric_shared_ce.py:397-399); built once per batch size
+                gidx = torch.arange(Ls, device=self.dev, dtype=torch.float32).repeat(nseq, 1).contiguous()
+                self._ws[key] = gidx
             self.aux.update(ce_scores=[], ce_keep=[], ce_removed=[])
         ce_i = 0
         for i, blk in enumerate(bb["blocks"]):

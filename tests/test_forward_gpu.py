@@ -139,3 +139,20 @@ def test_cpu_inputs_rejected(built_lib):
     model = model.cuda()
     with pytest.raises(NotImplementedError):
         model(*inputs)                      # CPU tensors into a CUDA model
+
+
+def test_cuda_graph_replay_matches_eager(built_lib):
+    """enable_cuda_graph: same boxes as the eager launch sequence, for changing inputs and two batch sizes."""
+    from mmt_b200 import synthetic
+    for variant in ("mixformer_vit_rgbt_shared", "asymmetric_shared_ce"):
+        model, cfg = synthetic.make_model(variant, 0)
+        model = model.cuda()
+        for batch, seed in ((1, 3), (2, 4), (1, 5)):
+            inputs = synthetic.make_inputs(variant, cfg, batch, seed, device="cuda")
+            model.enable_cuda_graph(False)
+            _, eager = model(*inputs)
+            model.enable_cuda_graph(True)
+            _, graphed = model(*inputs)
+            _, graphed2 = model(*inputs)
+            torch.cuda.synchronize()
+            assert torch.equal(eager, graphed) and torch.equal(graphed, graphed2), (variant, batch)
