@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace mmt {
 using namespace ptx;
@@ -48,6 +49,8 @@ struct GemmEpi {
   int act;                // MMT_ACT_*
   int out_fp32;
   int vec_ok;             // all vector-store alignment preconditions hold
+  int prefetch;           // L2-prefetch the next tile's A rows (off unless MMT_GEMM_PREFETCH=1; A/B measurements)
+  long long* dbg;         // developer aid (nullptr in production): per-CTA cycle counters, see mmt_dev_gemm_timing
 };
 
 // Implicit-GEMM geometry of a Conv2d(k=3, pad=1) on an NHWC map [B, H, W, C]: an M tile is a BW x BH pixel box
@@ -61,10 +64,13 @@ struct GemmConv {
   int cchunks;             // ceil(C / 64)
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster compute one 256 x BN tile with cta_group::2 MMAs - each loads its own 128 A rows and
+// HALF of the W rows, so a k-slice costs 32 KB of L2->SM traffic and smem per SM instead of 48 KB (BN = 256):
+// 6 pipeline stages instead of 4 and 1/3 less operand traffic for the same MMA work.
+template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_WORDS * 4 +
@@ -74,11 +80,14 @@ struct GemmCfg {
                                         : (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          int M, int N, int K, GemmEpi ep, GemmConv cv) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;     // tile-scheduler slot (a pair is one worker)
+  const int n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -96,7 +105,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
   const int tiles_per_img = cv.tiles_x * cv.tiles_y;
-  const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;
+  constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;
+  const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * tiles_per_img : (M + TILE_M - 1) / TILE_M;
   const int num_tiles = n_tiles * m_tiles;
   const int num_kb = cv.enabled ? 9 * cv.cchunks : (K + GEMM_BK - 1) / GEMM_BK;
 
@@ -109,16 +119,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), GEMM_EPI_WARPS);
+      mbar_init(tempty_bar(s), PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);   // PAIR: both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();    // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -127,12 +138,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
         const int mt = tile / n_tiles;
-        const int m0 = mt * GEMM_BM;
+        const int m0 = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
-        if (!cv.enabled) {
+        if (PAIR) {
+          // each CTA: its 128 A rows and its half of the W rows; all four boxes are counted on the leader's barrier
+          const int nb0 = n0 + static_cast<int>(cta_rank) * (BN / 2);
+          const int next_tile = tile + n_workers;
+          const int pm0 = (next_tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * GEMM_BM;
+          const bool pf = ep.prefetch && next_tile < num_tiles && pm0 != m0;
           for (int kb = 0; kb < num_kb; ++kb) {
+            if (pf) tma_prefetch_2d(&tmA, kb * GEMM_BK, pm0);     // next tile's A rows -> L2 (first touch is DRAM)
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d_pair(a_dst + Cfg::A_BYTES, &tmB, full_bar(stage), kb * GEMM_BK, nb0);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        } else if (!cv.enabled) {
+          const int next_tile = tile + n_workers;
+          const int pm0 = (next_tile / n_tiles) * TILE_M;
+          const bool pf = ep.prefetch && next_tile < num_tiles && pm0 != m0;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            if (pf) tma_prefetch_2d(&tmA, kb * GEMM_BK, pm0);     // next tile's A rows -> L2 (first touch is DRAM)
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
@@ -159,19 +189,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(GEMM_BM, BN);
+    if (lane == 0 && cta_rank == 0) {     // PAIR: only the leader CTA issues (for both SMs)
+      constexpr uint32_t idesc = make_idesc_bf16_f32(TILE_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      long long t_wait_acc = 0, t_wait_full = 0, t_total = ep.dbg ? clock64() : 0;
+      for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1u;
+        long long t0 = ep.dbg ? clock64() : 0;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
+        if (ep.dbg) t_wait_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
+          t0 = ep.dbg ? clock64() : 0;
           mbar_wait(full_bar(stage), phase);
+          if (ep.dbg) t_wait_full += clock64() - t0;
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
@@ -179,12 +214,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in 16-byte units
-            mma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) mma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else mma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          mma_commit(empty_bar(stage));
+          if (PAIR) mma_commit_pair(empty_bar(stage));      // frees the slot in both CTAs
+          else mma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(tfull_bar(as));
+        if (PAIR) mma_commit_pair(tfull_bar(as));           // both CTAs' epilogues read their own 128 TMEM lanes
+        else mma_commit(tfull_bar(as));
+      }
+      if (ep.dbg) {
+        ep.dbg[blockIdx.x * 4 + 0] = clock64() - t_total;
+        ep.dbg[blockIdx.x * 4 + 1] = t_wait_acc;     // MMA thread stalled on the epilogue (accumulator not drained)
+        ep.dbg[blockIdx.x * 4 + 2] = t_wait_full;    // MMA thread stalled on TMA data
+        ep.dbg[blockIdx.x * 4 + 3] = local;
       }
     }
   } else {
@@ -212,7 +256,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int IT_H = LPR_H;
     auto key_of = [](int r) { return (r / KEYDIV) & (VPR - 1); };
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
       const int mt = tile / n_tiles;
@@ -228,7 +272,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       auto grow_of = [&](int i) -> int {
         if (!cv.enabled) {
-          const int g = mt * GEMM_BM + i;
+          const int g = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + i;
           return g < M ? g : -1;
         }
         const int by = i / cv.BW, bx = i - by * cv.BW;
@@ -373,13 +417,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tempty_bar(as) & kPeerBitMask);   // the leader's barrier counts both CTAs
+        else mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (PAIR) {
+    cluster_sync_all();            // no CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -420,6 +472,42 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles
+static int launch_gemm_pair(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
+                            cudaStream_t stream) {
+  constexpr int BN = 256;
+  using Cfg = GemmCfg<BN, true>;
+  CUtensorMap tmB;
+  int rc = make_tmap_2d(&tmB, W, N, K, ldw, BN / 2);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = cdiv(M, 2 * GEMM_BM) * cdiv(N, BN);
+  int pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GemmConv cv = {};
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, M, N, K, ep, cv);
+  if (e != cudaSuccess) return (int)e;
+  MMT_RETURN_LAST_ERROR();
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
                        const GemmConv& cv, int max_ctas, cudaStream_t stream) {
@@ -429,7 +517,7 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, in
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -438,7 +526,7 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, in
   const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, cv);
+  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, cv);
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -457,8 +545,29 @@ static int pick_bn(int N) {
   return best;
 }
 
+static int g_prefetch_mode = -1;
+static bool prefetch_enabled() {
+  if (g_prefetch_mode < 0) {
+    const char* e = getenv("MMT_GEMM_PREFETCH");      // measured: -4% on the backbone GEMMs (profiles/r1_gemm_bound.md)
+    g_prefetch_mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_prefetch_mode == 1;
+}
+long long* g_gemm_dbg = nullptr;   // developer hook, see mmt_dev_gemm_timing
+static int g_pair_mode = -1;   // MMT_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
+static bool pair_enabled() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("MMT_GEMM_PAIR");
+    g_pair_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pair_mode == 1;
+}
+
 static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
                          const GemmConv& cv, int max_ctas, cudaStream_t s) {
+  if (!cv.enabled && max_ctas <= 0 && (N % 256) == 0 && cdiv(M, 2 * GEMM_BM) * (N / 256) >= num_sms() / 2 &&
+      pair_enabled())
+    return launch_gemm_pair(tmA, W, ldw, M, N, K, ep, s);
   switch (pick_bn(N)) {
     case 256: return launch_gemm<256>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
     case 192: return launch_gemm<192>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
@@ -513,6 +622,8 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
   GemmEpi ep;
   ep.bias = bias; ep.resid = resid; ep.rowadd = rowadd; ep.out = out;
   ep.ldr = ldr; ep.rowadd_period = rowadd_period; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
+  ep.dbg = mmt::g_gemm_dbg;
+  ep.prefetch = mmt::prefetch_enabled() ? 1 : 0;
   // fast path preconditions: 16-byte vector loads of bias / rowadd / resid and 16-byte vector stores
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = al16(out) && (out_fp32 ? (ldo % 4 == 0) : (ldo % 8 == 0)) && (!bias || al16(bias)) &&
@@ -522,6 +633,13 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
   if (rc) return rc;
   GemmConv cv = {};
   return dispatch_gemm(tmA, W, ldw, M, N, K, ep, cv, max_ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Developer hook (not part of the declared ABI): point the next mmt_gemm_bf16 launches at a device buffer of
+// 4 int64 per CTA {total cycles of the MMA thread, cycles stalled on the epilogue, cycles stalled on TMA data, tiles}.
+extern "C" int mmt_dev_gemm_timing(long long* dbg) {
+  mmt::g_gemm_dbg = dbg;
+  return 0;
 }
 
 extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, int C, const void* Wt, int ldw, int N,
@@ -537,6 +655,8 @@ extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, 
   GemmEpi ep;
   ep.bias = bias; ep.resid = nullptr; ep.rowadd = nullptr; ep.out = out;
   ep.ldr = 0; ep.rowadd_period = 0; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
+  ep.dbg = nullptr;
+  ep.prefetch = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = al16(out) && (out_fp32 ? (ldo % 4 == 0) : (ldo % 8 == 0)) && (!bias || al16(bias));
   CUtensorMap tmA;

@@ -36,6 +36,10 @@ CASES = [
     (2592, 96, 1728, True, 2, False, 0, False),      # head conv3
     (5184, 48, 864, True, 2, False, 0, False),       # head conv4 (K tail: 864 = 13.5 * 64)
     (324, 1, 432, True, 2, False, 0, True),          # 1-channel adjust conv (scalar tail path)
+    (19000, 2304, 768, True, 0, False, 0, False),    # CTA-pair kernel (cta_group::2): qkv, ragged M (74.2 pair tiles)
+    (18945, 768, 768, True, 0, True, 0, True),       # CTA-pair: proj + in-place residual, odd M
+    (6400, 3072, 768, True, 1, False, 0, False),     # CTA-pair: fc1 + GELU
+    (19200, 768, 3072, True, 0, True, 0, True),      # CTA-pair: fc2 + residual, K = 48 slices
     (130, 40, 72, False, 0, False, 0, False),        # ragged everything
     (100, 300, 200, True, 1, True, 7, True),
 ]
