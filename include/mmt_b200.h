@@ -184,6 +184,9 @@ int mmt_ce_gather_tokens(const float* x, int nseq, int n_tok, int Lt, const int*
 int mmt_ce_recover(const float* x, int nseq, int n_tok, int Lt, const float* gidx, int Lk, int Ls0, void* out, int C,
                    int out_bf16, void* stream);
 
+/* rois[b] = (b, xyxy[b] * scale), fp32 [B,5]: the SPM's target_roi (score_decoder.py:37-44). */
+int mmt_spm_rois(const float* xyxy, int B, float scale, float* rois, void* stream);
+
 /*
  * Precise RoI pooling forward: rois fp32 [R,5] = (batch_idx, x0, y0, x1, y1).  channels_last = 0: feat NCHW,
  * out [R,C,PH,PW] (the reference op's layout, prroi_pooling_gpu.c:22-44); channels_last = 1: feat NHWC, out

@@ -7,6 +7,8 @@
     build_mixformer_vit_rgbt_uni(cfg, train=False)       lib/models/mixformer_vit_rgbt/mixformer_unibackbone.py
     build_asymmetric_shared(cfg, train=False)            lib/models/mixformer_vit_rgbt/asymmetric_shared.py
     build_asymmetric_shared_ce(cfg, train=False)         lib/models/mixformer_vit_rgbt/asymmetric_shared_ce.py:590-640
+    build_mixformer_vit_online_score(cfg, train=False)   lib/models/mixformer_vit/mixformer_online.py:363-385
+        (SPM score head + cached-template set_online / forward_test)
 
 The returned nn.Module owns nn.Parameters / buffers under EXACTLY the reference's state_dict keys and shapes, so
 `load_state_dict(torch.load(ckpt)["net"], strict=True)` works on reference checkpoints.  The torch sub-modules
@@ -312,6 +314,8 @@ class _EngineModule(nn.Module):
 
     def engine(self):
         from .engine import ForwardEngine
+        if self.variant == "mixformer_vit_online":
+            from .engine_online import OnlineEngine as ForwardEngine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
@@ -386,6 +390,70 @@ class MixFormer_RGBT(_EngineModule):
         return self._finish(res, return_features)
 
 
+class _MLP(nn.Module):
+    """Parameter layout of MLP (lib/models/mixformer_cvt/head.py:215-232, BN=False)."""
+
+    def __init__(self, inp, hidden, out, num_layers):
+        super().__init__()
+        h = [hidden] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([inp] + h, h + [out]))
+
+
+class _ScoreDecoder(nn.Module):
+    """Parameter layout of ScoreDecoder, the SPM (lib/models/mixformer_cvt/score_decoder.py:12-30)."""
+
+    def __init__(self, num_heads, hidden_dim, nlayer_head=3, pool_size=4):
+        super().__init__()
+        self.num_heads, self.pool_size = num_heads, pool_size
+        self.score_head = _MLP(hidden_dim, hidden_dim, 1, nlayer_head)
+        lin = lambda: nn.ModuleList(nn.Linear(hidden_dim, hidden_dim, bias=True) for _ in range(2))
+        self.proj_q, self.proj_k, self.proj_v, self.proj = lin(), lin(), lin(), lin()
+        self.norm1 = nn.LayerNorm(hidden_dim)
+        self.norm2 = nn.ModuleList(nn.LayerNorm(hidden_dim) for _ in range(2))
+        self.score_token = nn.Parameter(torch.zeros(1, 1, hidden_dim))
+        nn.init.trunc_normal_(self.score_token, std=.02)
+
+
+class MixFormerOnlineScore(_EngineModule):
+    """MixViT tracker with the SPM score head and the cached-template test path
+    (lib/models/mixformer_vit/mixformer_online.py:286-360).  forward() is the full forward (+ pred_scores);
+    set_online(template, online_template) caches the templates' per-layer K/V and the template feature;
+    forward_test(search) runs the search tokens only against that cache.  Like the reference, the cached path is
+    per sequence: set_online takes ONE template and n online templates, forward_test ONE search crop."""
+    variant = "mixformer_vit_online"
+
+    def __init__(self, backbone, box_head, score_branch, cfg):
+        super().__init__()
+        self.backbone, self.box_head, self.score_branch = backbone, box_head, score_branch
+        self._init_engine_state(cfg)
+
+    @staticmethod
+    def _sq(t):
+        return t.squeeze(0) if t.dim() == 5 else t
+
+    def _finish_online(self, res, run_score_head):
+        coords = res["pred_boxes"]
+        out = {"pred_boxes": coords}
+        if run_score_head:
+            out["pred_scores"] = res["pred_scores"].view(-1)
+        return out, coords
+
+    @torch.no_grad()
+    def forward(self, template, online_template, search, run_score_head=True, gt_bboxes=None):
+        res = self.engine().forward(self._sq(template), self._sq(online_template), self._sq(search),
+                                    run_score_head=run_score_head, gt_bboxes=gt_bboxes)
+        return self._finish_online(res, run_score_head)
+
+    @torch.no_grad()
+    def set_online(self, template, online_template):
+        self.engine().set_online(self._sq(template), self._sq(online_template))
+
+    @torch.no_grad()
+    def forward_test(self, search, run_score_head=True, gt_bboxes=None):
+        res = self.engine().forward_test(self._sq(search), run_score_head=run_score_head, gt_bboxes=gt_bboxes)
+        return self._finish_online(res, run_score_head)
+
+
 def _require_inference(train):
     if train:
         raise NotImplementedError("mmt_b200 builders construct inference models only: call build_*(cfg, train=False)")
@@ -429,7 +497,15 @@ def build_asymmetric_shared_ce(cfg, train=False) -> MixFormer_RGBT:
     return _build_stacked("asymmetric_shared_ce", cfg, train, True)
 
 
+def build_mixformer_vit_online_score(cfg, settings=None, train=False) -> MixFormerOnlineScore:
+    _require_inference(train)
+    backbone = _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE, timm_leftovers=True)
+    score_branch = _ScoreDecoder(num_heads=cfg.MODEL.HIDDEN_DIM // 64, hidden_dim=cfg.MODEL.HIDDEN_DIM, pool_size=4)
+    return MixFormerOnlineScore(backbone, build_box_head(cfg), score_branch, cfg).eval()
+
+
 BUILDERS = {
+    "mixformer_vit_online": build_mixformer_vit_online_score,
     "mixformer_vit": build_mixformer_vit,
     "mixformer_vit_rgbt": build_mixformer_vit_rgbt,
     "mixformer_vit_rgbt_shared": build_mixformer_vit_rgbt_shared,

@@ -411,6 +411,16 @@ __global__ void xyxy_to_cxcywh_kernel(const float* __restrict__ xyxy, float* __r
   out[b * 4 + 3] = y1 - y0;
 }
 
+// rois[b] = (b, xyxy[b] * scale): the target_roi tensor of the SPM (lib/models/mixformer_cvt/score_decoder.py:37-44:
+// normalised box * feature width, batch index = arange(B)).
+__global__ void spm_rois_kernel(const float* __restrict__ xyxy, int B, float scale, float* __restrict__ rois) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  rois[b * 5 + 0] = static_cast<float>(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rois[b * 5 + 1 + k] = xyxy[b * 4 + k] * scale;
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -500,6 +510,12 @@ extern "C" int mmt_im2col3x3(const void* src1, int ld1, int s1, const void* src2
     im2col3x3_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(src1), ld1, s1, reinterpret_cast<const bf16*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<bf16*>(out));
   else
     im2col3x3_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src1), ld1, s1, reinterpret_cast<const float*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<float*>(out));
+  MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_spm_rois(const float* xyxy, int B, float scale, float* rois, void* stream) {
+  MMT_CHECK_ARG(xyxy && rois && B > 0);
+  spm_rois_kernel<<<cdiv(B, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xyxy, B, scale, rois);
   MMT_RETURN_LAST_ERROR();
 }
 

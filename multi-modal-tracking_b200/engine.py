@@ -51,7 +51,7 @@ class ForwardEngine:
         if self.head_type != "CORNER_UP":
             raise NotImplementedError("only the CORNER_UP (pyramid) head - used by every shipped YAML - is on the "
                                       "accelerated path")
-        self.rgbt = variant != "mixformer_vit"
+        self.rgbt = variant not in ("mixformer_vit", "mixformer_vit_online")
         self.fusion_class = m.get("FUSION_CLASS") if self.rgbt else None
         bb = m.get("BACKBONE", {})
         self.ce_loc = list(bb["CE_LOC"]) if (variant == "asymmetric_shared_ce" and "CE_LOC" in bb) else []
@@ -171,7 +171,7 @@ class ForwardEngine:
         return F
 
     def _pack(self, sd):
-        if self.variant == "mixformer_vit":
+        if self.variant in ("mixformer_vit", "mixformer_vit_online"):
             self.bbs = [self._pack_backbone(sd, "backbone.", False)]
         elif self.variant == "mixformer_vit_rgbt":
             self.bbs = [self._pack_backbone(sd, "backbone_v.", False), self._pack_backbone(sd, "backbone_i.", False)]
@@ -235,18 +235,21 @@ class ForwardEngine:
         ops.patchify(imgs_s, patches, 2 * n_t, self.N0)
         ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos"], out=x)
 
-    def _block(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep=None, gidx=None):
-        """One pre-LN block on x [nseq*N, dim] fp32 (in place).  Returns (x, N, Ls, gidx) - changed by CE."""
+    def _block(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep=None, gidx=None, tiles=None, qkv1=None,
+               qkv_out=None):
+        """One pre-LN block on x [nseq*N, dim] fp32 (in place).  Returns (x, N, Ls, gidx) - changed by CE.
+        tiles / qkv1 / qkv_out: explicit attention tile table, second (cached) qkv buffer and the buffer that receives
+        this block's qkv (the cached-template paths of engine_online.py)."""
         M = nseq * N
         dim = self.dim
         h = self._buf(tag, "h", (M, dim), self.act)
-        qkv = self._buf(tag, "qkv", (M, 3 * dim), self.act)
+        qkv = qkv_out if qkv_out is not None else self._buf(tag, "qkv", (M, 3 * dim), self.act)
         att = self._buf(tag, "att", (M, dim), self.act)
         g0, b0, g1, b1 = blk["ln1"]
         self._ln(x, g0, b0, g1, b1, ln_period, 1e-6, h)
         ops.gemm(h, blk["qkv_w"], blk["qkv_b"], out=qkv)
-        tiles, max_keys = self._attn_tiles("cross" if cross else "sym", nseq, N, Ls)
-        ops.mixattn(qkv, None, dim, self.heads, tiles, max_keys, att, self.scale)
+        tiles, max_keys = tiles if tiles is not None else self._attn_tiles("cross" if cross else "sym", nseq, N, Ls)
+        ops.mixattn(qkv, qkv1, dim, self.heads, tiles, max_keys, att, self.scale)
         ops.gemm(att, blk["proj_w"], blk["proj_b"], ops.ACT_NONE, x, None, out=x)
         if ce_keep is not None:
             x, N, Ls, gidx = self._candidate_elimination(qkv, x, nseq, N, Ls, ce_keep, gidx, tag)
@@ -309,6 +312,7 @@ class ForwardEngine:
                 if not ce_keep < 1:
                     ce_keep = None
             x, N, Ls, gidx = self._block(blk, x, nseq, N, Ls, (nseq * N // 2) if per_ln else 0, cross, tag, ce_keep, gidx)
+        self._last_x = (x, N)            # residual stream after the last block (template rows: engine_online.py)
         feat = self._buf(tag, "search_rows", (nseq * self.Ls0, self.dim), self.act)
         if Ls != self.Ls0:
             ops.ce_recover(x, nseq, N, self.Lt, gidx, Ls, self.Ls0, feat)
@@ -431,6 +435,7 @@ class ForwardEngine:
         boxes = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
         ops.corner_decode(x4s, (H["w5_tl"], H["w5_br"]), (H["b5_tl"], H["b5_br"]), a3s, a4s, B, S, 4.0,
                           float(self.search_size), xyxy, boxes, maps)
+        self._last_xyxy = xyxy
         return boxes, maps
 
     # ------------------------------------------------------------------------------------------ forward

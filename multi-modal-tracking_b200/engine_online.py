@@ -1,0 +1,179 @@
+"""Engine of the online (SPM) MixViT tracker: the full forward with the score head, and the cached-template test
+path `set_online` / `forward_test` (lib/models/mixformer_vit/mixformer_online.py:80-113, 229-262, 286-360;
+lib/models/mixformer_cvt/score_decoder.py:32-66).  Same kernels as engine.py; the cache is one packed qkv buffer
+per layer that the attention kernels read as a second key/value source (tile records with k_buf = 1)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import ForwardEngine, _f32
+
+
+class OnlineEngine(ForwardEngine):
+    def _pack(self, sd):
+        super()._pack(sd)
+        dev = self.dev
+        g = lambda k: sd["score_branch." + k]
+        S = {"token": _f32(g("score_token").reshape(1, -1), dev),
+             "norm1": (_f32(g("norm1.weight"), dev), _f32(g("norm1.bias"), dev)), "layers": [], "mlp": []}
+        for i in range(2):
+            S["layers"].append(dict(
+                q_w=self._w(g(f"proj_q.{i}.weight")), q_b=_f32(g(f"proj_q.{i}.bias"), dev),
+                kv_w=self._w(torch.cat([g(f"proj_k.{i}.weight"), g(f"proj_v.{i}.weight")], 0)),
+                kv_b=_f32(torch.cat([g(f"proj_k.{i}.bias"), g(f"proj_v.{i}.bias")], 0), dev),
+                o_w=self._w(g(f"proj.{i}.weight")), o_b=_f32(g(f"proj.{i}.bias"), dev),
+                ln=(_f32(g(f"norm2.{i}.weight"), dev), _f32(g(f"norm2.{i}.bias"), dev))))
+        i = 0
+        while f"score_branch.score_head.layers.{i}.weight" in sd:
+            S["mlp"].append((self._w(g(f"score_head.layers.{i}.weight")), _f32(g(f"score_head.layers.{i}.bias"), dev)))
+            i += 1
+        self.spm = S
+        self.spm_heads = self.dim // 64
+        self.spm_scale = self.dim ** -0.5            # hidden_dim ** -0.5 (score_decoder.py:18), not head_dim
+        self.qkv_mem = None                          # per-layer cached template qkv [Tm, 3C]
+        self.templ_rows = None                       # cached feature rows of the first template [T, C]
+
+    # ------------------------------------------------------------------------------------------ SPM
+    def _spm_tiles(self, B, T):
+        key = ("spm", B, T)
+        hit = self._tiles.get(key)
+        if hit is None:
+            recs = [[b, 1, b, 1, b * T, 0, 0, T, 0, 0, 1, 0, 0, 0, 0, 0] for b in range(B)]
+            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), T)
+            self._tiles[key] = hit
+        return hit
+
+    def _run_spm(self, feat32, templ_rows, xyxy, B):
+        """ScoreDecoder.forward: feat32 fp32 NHWC rows [B*gs*gs, C]; templ_rows `act` [B*T, C]; xyxy fp32 [B,4]
+        normalised -> logits fp32 [B]."""
+        C, gs, S = self.dim, self.gs, self.spm
+        tag = ("spm", B)
+        rois = ops.spm_rois(xyxy, float(gs), self._buf(tag, "rois", (B, 5), torch.float32))
+        pooled = self._buf(tag, "pooled", (B, 16, C), torch.float32)
+        ops.prroi_pool(feat32.view(B, gs, gs, C), rois, 4, 4, 1.0, channels_last=True, out=pooled)
+        pooled_a = ops.copy_rows(pooled.view(B * 16, C), B * 16, 0, B * 16, 1, self._buf(tag, "pooled_a", (B * 16, C), self.act))
+        tok = self._ws.get(("spm_tok", B))
+        if tok is None:
+            tok = S["token"].expand(B, -1).contiguous()
+            self._ws[("spm_tok", B)] = tok
+        x = self._buf(tag, "x", (B, C), self.act)
+        self._ln(tok, S["norm1"][0], S["norm1"][1], None, None, 0, 1e-5, x)
+        qkv0 = self._buf(tag, "qkv0", (B, 3 * C), self.act)
+        att = self._buf(tag, "att", (B, C), self.act)
+        y = self._buf(tag, "y", (B, C), torch.float32)
+        for i, (mem, T) in enumerate(((pooled_a, 16), (templ_rows, templ_rows.shape[0] // B))):
+            L = S["layers"][i]
+            qkv1 = self._buf(tag, f"qkv1_{i}", (B * T, 3 * C), self.act)
+            ops.gemm(x, L["q_w"], L["q_b"], out=qkv0[:, :C])
+            ops.gemm(mem, L["kv_w"], L["kv_b"], out=qkv1[:, C:])
+            tiles, mk = self._spm_tiles(B, T)
+            ops.mixattn(qkv0, qkv1, C, self.spm_heads, tiles, mk, att, self.spm_scale)
+            ops.gemm(att, L["o_w"], L["o_b"], out=y)
+            self._ln(y, L["ln"][0], L["ln"][1], None, None, 0, 1e-5, x)
+        h = x
+        n = len(S["mlp"])
+        for i, (w, b) in enumerate(S["mlp"]):
+            last = i == n - 1
+            if last:
+                o = torch.empty((B, w.shape[0]), device=self.dev, dtype=torch.float32)
+            else:
+                o = self._buf(tag, f"mlp{i}", (B, w.shape[0]), self.act)
+            ops.gemm(h, w, b, ops.ACT_NONE if last else ops.ACT_RELU, out=o)
+            h = o
+        return h.view(B)
+
+    def _scores(self, x, N, row_off_s, B, templ_rows, gt_bboxes):
+        """fp32 search rows out of the residual stream -> SPM."""
+        feat32 = ops.copy_rows(x, N, row_off_s, self.Ls0, B, self._buf(("spm", B), "feat32", (B * self.Ls0, self.dim), torch.float32))
+        if gt_bboxes is not None:
+            xyxy = gt_bboxes.detach().to(device=self.dev, dtype=torch.float32).reshape(B, 4).contiguous()
+        else:
+            xyxy = self._last_xyxy
+        return self._run_spm(feat32, templ_rows, xyxy, B)
+
+    # ------------------------------------------------------------------------------------------ full forward
+    def forward(self, template, online_template, search, want_maps=True, run_score_head=True, gt_bboxes=None):
+        self.aux = {}
+        t, ot, s = (self._check_img(template, self.template_size), self._check_img(online_template, self.template_size),
+                    self._check_img(search, self.search_size))
+        B = s.shape[0]
+        x = self._buf(B, "x", (B * self.N0, self.dim), torch.float32)
+        self._embed(self.bbs[0], B, t, ot, s, x)
+        feat = self._run_backbone(self.bbs[0], x, B, ("bb", B), False)
+        boxes, maps = self._run_head(feat, B, want_maps)
+        res = dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feat)
+        if run_score_head:
+            T = self.gt * self.gt
+            templ = ops.copy_rows(x, self.N0, 0, T, B, self._buf(("spm", B), "templ", (B * T, self.dim), self.act))
+            res["pred_scores"] = self._scores(x, self.N0, self.Lt, B, templ, gt_bboxes)
+        return res
+
+    # ------------------------------------------------------------------------------------------ cached-template path
+    def _full_tiles(self, rows, key_segs, tag):
+        """Query rows [0, rows) in 128-row tiles, every tile reading the same key segments [(buf, row0, len), ...]."""
+        key = (tag, rows, tuple(key_segs))
+        hit = self._tiles.get(key)
+        if hit is None:
+            recs = []
+            for o in range(0, rows, 128):
+                segs = list(key_segs) + [(0, 0, 0)] * (3 - len(key_segs))
+                recs.append([o, min(128, rows - o), o, len(key_segs)] + [sg[1] for sg in segs] + [sg[2] for sg in segs] +
+                            [sg[0] for sg in segs] + [0, 0, 0])
+            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), sum(sg[2] for sg in key_segs))
+            self._tiles[key] = hit
+        return hit
+
+    def set_online(self, template, online_template):
+        """VisionTransformer.set_online / Attention.set_online (mixformer_online.py:243-262, 96-113): ONE template and
+        n online templates form one token sequence with full self-attention; every layer's qkv is kept."""
+        t = self._check_img(template, self.template_size)
+        ot = self._check_img(online_template, self.template_size)
+        if t.shape[0] != 1:
+            raise RuntimeError("set_online caches ONE sequence (template batch must be 1), like the reference "
+                               "(x_ot.reshape(1, -1, C), mixformer_online.py:252)")
+        T = self.gt * self.gt
+        Tm = (1 + ot.shape[0]) * T
+        bb = self.bbs[0]
+        tag = ("online_t", Tm)
+        x = self._buf(tag, "x", (Tm, self.dim), torch.float32)
+        patches = self._buf(tag, "patches", (Tm, 3 * 256), self.act)
+        ops.patchify(t, patches, 0, Tm)
+        ops.patchify(ot, patches, T, T)
+        pos_t = self._ws.get("pos_t")
+        if pos_t is None:
+            pos_t = bb["pos"][:T].contiguous()
+            self._ws["pos_t"] = pos_t
+            self._ws["pos_s"] = bb["pos"][2 * T:].contiguous()
+        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, pos_t, out=x)
+        self.qkv_mem = [self._buf(tag, f"qkv_mem{i}", (Tm, 3 * self.dim), self.act) for i in range(self.depth)]
+        tiles = self._full_tiles(Tm, [(0, 0, Tm)], "set_online")
+        for i, blk in enumerate(bb["blocks"]):
+            self._block(blk, x, 1, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=self.qkv_mem[i])
+        self.templ_rows = ops.copy_rows(x, Tm, 0, T, 1, self._buf(tag, "templ_rows", (T, self.dim), self.act))
+        self.mem_rows = Tm
+
+    def forward_test(self, search, want_maps=True, run_score_head=True, gt_bboxes=None):
+        """VisionTransformer.forward_test / Attention.forward_test (mixformer_online.py:229-241, 80-94): search tokens
+        only; keys/values = cached template rows + own rows."""
+        if self.qkv_mem is None:
+            raise RuntimeError("forward_test called before set_online")
+        s = self._check_img(search, self.search_size)
+        if s.shape[0] != 1:
+            raise RuntimeError("forward_test runs ONE search crop against the cached templates, like the reference")
+        Ls, Tm, bb = self.Ls0, self.mem_rows, self.bbs[0]
+        tag = ("online_s", Tm)
+        x = self._buf(tag, "x", (Ls, self.dim), torch.float32)
+        patches = self._buf(tag, "patches", (Ls, 3 * 256), self.act)
+        ops.patchify(s, patches, 0, Ls)
+        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_s"], out=x)
+        tiles = self._full_tiles(Ls, [(1, 0, Tm), (0, 0, Ls)], "forward_test")
+        for i, blk in enumerate(bb["blocks"]):
+            self._block(blk, x, 1, Ls, 0, 0, False, tag, tiles=tiles, qkv1=self.qkv_mem[i])
+        feat = ops.copy_rows(x, Ls, 0, Ls, 1, self._buf(tag, "search_rows", (Ls, self.dim), self.act))
+        boxes, maps = self._run_head(feat, 1, want_maps)
+        res = dict(pred_boxes=boxes.view(1, 1, 4), score_maps=maps, feat_rows=feat)
+        if run_score_head:
+            res["pred_scores"] = self._scores(x, Ls, 0, 1, self.templ_rows, gt_bboxes)
+        return res

@@ -351,6 +351,18 @@ def ce_recover(x, nseq, n_tok, Lt, gidx, Lk, Ls0, out):
     _count(1, "ce_recover", _ev)
 
 
+_spm_rois = _lib.fn("mmt_spm_rois")
+
+
+def spm_rois(xyxy, scale, rois):
+    _need_cuda(xyxy, rois)
+    assert xyxy.dtype == torch.float32 and rois.dtype == torch.float32 and xyxy.is_contiguous() and rois.is_contiguous()
+    _ev = _begin()
+    _lib.check(_spm_rois(_ptr(xyxy), c_int(xyxy.shape[0]), c_float(scale), _ptr(rois), _stream()), "mmt_spm_rois")
+    _count(1, "spm_rois", _ev)
+    return rois
+
+
 def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None):
     """feat fp32 [N,C,H,W] (or [N,H,W,C] with channels_last) ; rois fp32 [R,5] -> [R,C,ph,pw] (or [R,ph*pw,C])."""
     _need_cuda(feat, rois)

@@ -62,9 +62,74 @@ def run_reference(variant, sd, inputs):
     return res
 
 
+def _cpu_prroi_module():
+    """PrRoIPool2D is GPU-only in the reference (prroi_pool/functional.py:62-63); on CPU the reference's ScoreDecoder
+    is run with the oracle restatement of the pooling plugged in (itself pinned by the reference's known-answer test)."""
+    from oracle import native_ops_oracle as NO
+
+    class P(torch.nn.Module):
+        def forward(self, features, rois):
+            return torch.from_numpy(NO.prroi_pool_forward(features.numpy(), rois.numpy(), 4, 4, 1.0))
+    return P()
+
+
+def main_online(sharpen):
+    """mixformer_vit_online: full forward with the SPM score head, and set_online + forward_test (cached templates)."""
+    variant = "mixformer_vit_online"
+    model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen)
+    sd = model.state_dict()
+    ref, rcfg = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant])
+    missing, unexpected = ref.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    ref.score_branch.search_prroipool = _cpu_prroi_module()
+    cap = {}
+    orig = ref.box_head.get_score_map
+
+    def hooked(x):
+        tl, br = orig(x)
+        cap["maps"] = torch.stack([tl.flatten(1), br.flatten(1)], dim=1)
+        return tl, br
+    ref.box_head.get_score_map = hooked
+    save = {}
+    t, ot, s = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+    with torch.no_grad():
+        out, _ = ref(t, ot, s, run_score_head=True)
+    ora = O.forward(variant, sd, cfg, t, ot, s)
+    d = [(out["pred_boxes"] - ora["pred_boxes"]).abs().max().item(), (cap["maps"] - ora["score_maps"]).abs().max().item(),
+         (out["pred_scores"] - ora["pred_scores"]).abs().max().item()]
+    print(f"{variant} ({'sharpened' if sharpen else 'plain'}) full: oracle vs reference boxes {d[0]:.3e} maps {d[1]:.3e} scores {d[2]:.3e}")
+    assert d[0] <= 1e-5 and d[1] <= 2e-4 and d[2] <= 2e-4
+    save.update(pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy(), pred_scores=out["pred_scores"].numpy())
+    # cached-template path: one template, 3 online templates, one search crop
+    g = torch.Generator().manual_seed(INPUT_SEED + 10)
+    tt = torch.randn(1, 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.TEMPLATE.SIZE, generator=g)
+    oo = torch.randn(3, 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.TEMPLATE.SIZE, generator=g)
+    ss = torch.randn(1, 3, cfg.DATA.SEARCH.SIZE, cfg.DATA.SEARCH.SIZE, generator=g)
+    with torch.no_grad():
+        ref.set_online(tt, oo)
+        out2, _ = ref.forward_test(ss, run_score_head=True)
+    st = O.online_set(sd, cfg, tt, oo)
+    ora2 = O.online_forward_test(sd, cfg, st, ss)
+    d = [(out2["pred_boxes"] - ora2["pred_boxes"]).abs().max().item(), (cap["maps"] - ora2["score_maps"]).abs().max().item(),
+         (out2["pred_scores"] - ora2["pred_scores"]).abs().max().item()]
+    print(f"   cached-template path: oracle vs reference boxes {d[0]:.3e} maps {d[1]:.3e} scores {d[2]:.3e}")
+    assert d[0] <= 1e-5 and d[1] <= 2e-4 and d[2] <= 2e-4
+    save.update(online_template=tt.numpy(), online_online_template=oo.numpy(), online_search=ss.numpy(),
+                online_pred_boxes=out2["pred_boxes"].numpy(), online_score_maps=cap["maps"].numpy(),
+                online_pred_scores=out2["pred_scores"].numpy())
+    print("   scores (logits):", out["pred_scores"].tolist(), out2["pred_scores"].tolist())
+    tag = "" if sharpen else "_plain"
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}{tag}_b{BATCH}.npz"), **save)
+
+
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
+    if "mixformer_vit_online" in variants:
+        torch.set_num_threads(8)
+        for sharpen in (True, False):
+            main_online(sharpen)
+        variants = [v for v in variants if v != "mixformer_vit_online"]
     for variant, sharpen in [(v, s) for v in variants for s in (True, False)]:
         # two seeded weight sets: "sharpened" (peaky corner maps, see synthetic.py) and "plain" = the builders'
         # default random init, the weight set BASELINE.json's north_star names for the bf16 tolerances

@@ -425,6 +425,114 @@ def box_head(sd, feat, cfg):
     return box_xyxy_to_cxcywh(xyxy).view(-1, 1, 4), maps
 
 
+# ------------------------------------------------------------------------------------------------- a10 SPM
+def box_cxcywh_to_xyxy(x):
+    """lib/utils/box_ops.py:8-12."""
+    cx, cy, w, h = x.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+
+
+def score_decoder(sd, search_feat, template_feat, search_box, num_heads):
+    """ScoreDecoder.forward lib/models/mixformer_cvt/score_decoder.py:32-66.  search_feat [B,C,H,W], template_feat
+    [B,C,Ht,Wt], search_box [B,4] normalised xyxy.  PrRoIPool (GPU-only in the reference) is the restatement in
+    oracle/native_ops_oracle.py.  Returns raw logits [B]."""
+    from oracle import native_ops_oracle as NO
+    b, c, h, w = search_feat.shape
+    scale = c ** -0.5                                         # hidden_dim ** -0.5, NOT head_dim (score_decoder.py:18)
+    bb = search_box.clone().view(-1, 4) * w
+    rois = torch.cat([torch.arange(b, dtype=torch.float32).view(-1, 1), bb], dim=1)
+    pooled = torch.from_numpy(NO.prroi_pool_forward(search_feat.numpy(), rois.numpy(), 4, 4, 1.0))   # [B,C,4,4]
+    x = sd["score_token"].expand(b, -1, -1)
+    x = F.layer_norm(x, (c,), sd["norm1.weight"], sd["norm1.bias"], 1e-5)
+    mem = [pooled.flatten(2).transpose(1, 2), template_feat.flatten(2).transpose(1, 2)]
+    hd = c // num_heads
+    for i in range(2):
+        q = F.linear(x, sd[f"proj_q.{i}.weight"], sd[f"proj_q.{i}.bias"]).view(b, -1, num_heads, hd).transpose(1, 2)
+        k = F.linear(mem[i], sd[f"proj_k.{i}.weight"], sd[f"proj_k.{i}.bias"]).view(b, -1, num_heads, hd).transpose(1, 2)
+        v = F.linear(mem[i], sd[f"proj_v.{i}.weight"], sd[f"proj_v.{i}.bias"]).view(b, -1, num_heads, hd).transpose(1, 2)
+        a = ((q @ k.transpose(-2, -1)) * scale).softmax(dim=-1)
+        x = (a @ v).transpose(1, 2).reshape(b, -1, c)
+        x = F.linear(x, sd[f"proj.{i}.weight"], sd[f"proj.{i}.bias"])
+        x = F.layer_norm(x, (c,), sd[f"norm2.{i}.weight"], sd[f"norm2.{i}.bias"], 1e-5)
+    n = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("score_head.layers."))
+    for i in range(n):                                         # MLP head.py:229-232
+        x = F.linear(x, sd[f"score_head.layers.{i}.weight"], sd[f"score_head.layers.{i}.bias"])
+        if i < n - 1:
+            x = F.relu(x)
+    return x.view(-1)
+
+
+def forward_head_online(sd, search_feat, template_feat, mc, heads, run_score_head=True, gt_bboxes=None):
+    """MixFormerOnlineScore.forward_head lib/models/mixformer_vit/mixformer_online.py:326-343."""
+    boxes, maps = box_head(_sub(sd, "box_head."), search_feat, mc)
+    out = dict(pred_boxes=boxes, score_maps=maps, feat=search_feat)
+    if run_score_head:
+        bb = gt_bboxes if gt_bboxes is not None else box_cxcywh_to_xyxy(boxes.clone().view(-1, 4))
+        out["pred_scores"] = score_decoder(_sub(sd, "score_branch."), search_feat, template_feat, bb, heads)
+    return out
+
+
+class OnlineState:
+    """Cached-template state of one sequence (Attention.set_online / VisionTransformer.set_online,
+    lib/models/mixformer_vit/mixformer_online.py:96-113,243-262): per-layer qkv of the template tokens and the
+    final feature of the first template."""
+
+    def __init__(self):
+        self.qkv_mem = []
+        self.template = None
+
+
+def online_set(sd, cfg, template, online_template):
+    """model.set_online(template [1,3,T,T], online_template [n,3,T,T])."""
+    mc = cfg if "variant" in cfg else model_cfg("mixformer_vit_online", cfg)
+    d = vit_dims(mc["vit_type"])
+    bsd = _sub(sd, "backbone.")
+    w, b = bsd["patch_embed.proj.weight"], bsd["patch_embed.proj.bias"]
+    x_t = patch_embed(template, w, b) + bsd["pos_embed_t"]
+    x_ot = patch_embed(online_template, w, b) + bsd["pos_embed_t"]
+    x = torch.cat([x_t, x_ot.reshape(1, -1, x_ot.shape[-1])], dim=1)
+    st = OnlineState()
+    H, C = d["heads"], x.shape[-1]
+    for i in range(d["depth"]):
+        p = _sub(bsd, f"blocks.{i}.")
+        a = _sub(p, "attn.")
+        h = _ln(x, p, "norm1", 1e-6)
+        B, N, _ = h.shape
+        qkv = F.linear(h, a["qkv.weight"], a["qkv.bias"]).reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+        st.qkv_mem.append(qkv)
+        q, k, v = qkv.unbind(0)
+        att = ((q @ k.transpose(-2, -1)) * (C // H) ** -0.5).softmax(dim=-1)
+        y = (att @ v).transpose(1, 2).reshape(B, N, C)
+        x = x + F.linear(y, a["proj.weight"], a["proj.bias"])
+        x = x + mlp(_ln(x, p, "norm2", 1e-6), _sub(p, "mlp."))
+    g = mc["template_size"] // 16
+    st.template = _tokens_to_map(x[:, :g * g], g)
+    return st
+
+
+def online_forward_test(sd, cfg, st, search, run_score_head=True):
+    """model.forward_test(search [1,3,S,S]) against the cache (Attention.forward_test :80-94, backbone :229-241)."""
+    mc = cfg if "variant" in cfg else model_cfg("mixformer_vit_online", cfg)
+    d = vit_dims(mc["vit_type"])
+    bsd = _sub(sd, "backbone.")
+    x = patch_embed(search, bsd["patch_embed.proj.weight"], bsd["patch_embed.proj.bias"]) + bsd["pos_embed_s"]
+    H, C = d["heads"], x.shape[-1]
+    for i in range(d["depth"]):
+        p = _sub(bsd, f"blocks.{i}.")
+        a = _sub(p, "attn.")
+        h = _ln(x, p, "norm1", 1e-6)
+        B, N, _ = h.shape
+        qkv_s = F.linear(h, a["qkv.weight"], a["qkv.bias"]).reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+        q_s = qkv_s[0]
+        _, k, v = torch.cat([st.qkv_mem[i], qkv_s], dim=3).unbind(0)
+        att = ((q_s @ k.transpose(-2, -1)) * (C // H) ** -0.5).softmax(dim=-1)
+        y = (att @ v).transpose(1, 2).reshape(B, N, C)
+        x = x + F.linear(y, a["proj.weight"], a["proj.bias"])
+        x = x + mlp(_ln(x, p, "norm2", 1e-6), _sub(p, "mlp."))
+    g = mc["search_size"] // 16
+    return forward_head_online(sd, _tokens_to_map(x, g), st.template, mc, d["heads"], run_score_head)
+
+
 # ------------------------------------------------------------------------------------------------- whole forward
 def model_cfg(variant, cfg):
     """The handful of config keys the forward depends on, from a reference-style cfg tree."""
@@ -451,6 +559,10 @@ def forward(variant, sd, cfg, template, online_template, search):
     d = vit_dims(mc["vit_type"])
     g = mc["search_size"] // 16
     aux = {}
+    if variant == "mixformer_vit_online":   # lib/models/mixformer_vit/mixformer_online.py:297-311 (+ SPM)
+        s, x = backbone_plain(_sub(sd, "backbone."), template, online_template, search, d["heads"], d["depth"])
+        gt = mc["template_size"] // 16
+        return forward_head_online(sd, _tokens_to_map(s, g), _tokens_to_map(x[:, :gt * gt], gt), mc, d["heads"])
     if variant == "mixformer_vit":          # lib/models/mixformer_vit/mixformer.py:294-306
         s, _ = backbone_plain(_sub(sd, "backbone."), template, online_template, search, d["heads"], d["depth"])
         feat = _tokens_to_map(s, g)

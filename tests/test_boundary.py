@@ -47,8 +47,23 @@ def test_state_dict_layout(variant):
     assert not missing and not unexpected
 
 
+def test_online_score_state_dict_layout():
+    """mixformer_vit_online: backbone with timm leftovers, FrozenBN head (HEAD_FREEZE_BN: no num_batches_tracked),
+    score_branch.* of the SPM."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    model, _ = synthetic.make_model("mixformer_vit_online", 0, sharpen=False)
+    sd = model.state_dict()
+    assert "score_branch.score_token" in sd and sd["score_branch.score_head.layers.2.weight"].shape == (1, 768)
+    assert sd["score_branch.proj_k.1.weight"].shape == (768, 768) and "score_branch.norm2.1.bias" in sd
+    assert "box_head.conv1_tl.1.running_var" in sd and "box_head.conv1_tl.1.num_batches_tracked" not in sd
+    assert "backbone.cls_token" in sd
+    for fn in ("set_online", "forward_test", "forward"):
+        assert callable(getattr(model, fn))
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
-@pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce"])
+@pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce", "mixformer_vit_online"])
 def test_reference_builder_accepts_our_state_dict(variant):
     """strict=True load of our state_dict INTO the unmodified reference module (and the reverse)."""
     import mmt_b200  # noqa: F401

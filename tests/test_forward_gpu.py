@@ -156,3 +156,59 @@ def test_cuda_graph_replay_matches_eager(built_lib):
             _, graphed2 = model(*inputs)
             torch.cuda.synchronize()
             assert torch.equal(eager, graphed) and torch.equal(graphed, graphed2), (variant, batch)
+
+
+ONLINE = "mixformer_vit_online"
+
+
+@pytest.mark.parametrize("sharpen", [True, False], ids=["sharpened", "plain"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_online_score_model(built_lib, precision, sharpen):
+    """SPM score head (PrRoIPool + score-token decoder) on the full forward, and the cached-template path
+    set_online + forward_test, against the reference's golden outputs (lib/models/mixformer_vit/mixformer_online.py)."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(ONLINE, 0, sharpen=sharpen)
+    model = model.cuda().set_precision(precision)
+    g = _golden(ONLINE, sharpen)
+    inputs = synthetic.make_inputs(ONLINE, cfg, 2, 1, device="cuda")
+    out, coords = model(*inputs, run_score_head=True)
+    res = model._engine.forward(*inputs)
+    torch.cuda.synchronize()
+    assert torch.equal(res["pred_boxes"], coords) and torch.equal(res["pred_scores"], out["pred_scores"])
+    model.set_online(torch.from_numpy(g["online_template"]).cuda(), torch.from_numpy(g["online_online_template"]).cuda())
+    out2, _ = model.forward_test(torch.from_numpy(g["online_search"]).cuda(), run_score_head=True)
+    res2 = model._engine.forward_test(torch.from_numpy(g["online_search"]).cuda())
+    torch.cuda.synchronize()
+    size = cfg.DATA.SEARCH.SIZE
+    d = dict(box=np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * size,
+             map=np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max(),
+             score=np.abs(out["pred_scores"].cpu().numpy() - g["pred_scores"]).max(),
+             obox=np.abs(out2["pred_boxes"].cpu().numpy() - g["online_pred_boxes"]).max() * size,
+             omap=np.abs(res2["score_maps"].cpu().numpy() - g["online_score_maps"]).max(),
+             oscore=np.abs(out2["pred_scores"].cpu().numpy() - g["online_pred_scores"]).max())
+    print(f"{ONLINE} {precision} {'sharpened' if sharpen else 'plain'}: " + "  ".join(f"{k} {v:.3e}" for k, v in d.items()))
+    assert out["pred_scores"].shape == (2,) and out2["pred_scores"].shape == (1,)
+    if precision == "fp32":
+        assert d["box"] <= 1e-4 * size and d["obox"] <= 1e-4 * size
+        assert max(d["map"], d["omap"], d["score"], d["oscore"]) <= 1e-4
+    elif not sharpen:        # north-star bf16 bound on the weight set it names; score logits to 1e-2 as well
+        assert d["box"] <= 0.5 and d["obox"] <= 0.5
+        assert max(d["map"], d["omap"], d["score"], d["oscore"]) <= 1e-2
+    else:
+        lim = 2e-2 * np.abs(g["score_maps"]).max()
+        assert d["box"] <= 2.0 and d["obox"] <= 2.0 and d["map"] <= lim and d["omap"] <= lim
+        assert max(d["score"], d["oscore"]) <= 5e-2
+
+
+def test_online_paths_reject_misuse(built_lib):
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(ONLINE, 0)
+    model = model.cuda()
+    t, ot, s = synthetic.make_inputs(ONLINE, cfg, 2, 1, device="cuda")
+    with pytest.raises(RuntimeError):
+        model.forward_test(s[:1])                 # no cache yet
+    with pytest.raises(RuntimeError):
+        model.set_online(t, ot)                   # template batch must be 1
+    model.set_online(t[:1], ot)
+    with pytest.raises(RuntimeError):
+        model.forward_test(s)                     # one search crop per cached sequence

@@ -29,6 +29,26 @@ def test_oracle_matches_reference_vectors(variant):
             assert out["ce_keep_v"][j].shape[1] == (227, 159, 112)[j]     # 324 -> 227 -> 159 -> 112
 
 
+def test_online_oracle_matches_reference_vectors():
+    """mixformer_vit_online: full forward with the SPM score, and set_online + forward_test on the stored crops."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    variant = "mixformer_vit_online"
+    model, cfg = synthetic.make_model(variant, 0, sharpen=False)
+    sd = model.state_dict()
+    g = np.load(os.path.join(GOLDEN, f"{variant}_plain_b2.npz"))
+    out = O.forward(variant, sd, cfg, *synthetic.make_inputs(variant, cfg, 2, 1))
+    assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
+    assert np.abs(out["pred_scores"].numpy() - g["pred_scores"]).max() <= 1e-4
+    st = O.online_set(sd, cfg, torch.from_numpy(g["online_template"]), torch.from_numpy(g["online_online_template"]))
+    out2 = O.online_forward_test(sd, cfg, st, torch.from_numpy(g["online_search"]))
+    assert np.abs(out2["pred_boxes"].numpy() - g["online_pred_boxes"]).max() <= 1e-5
+    assert np.abs(out2["pred_scores"].numpy() - g["online_pred_scores"]).max() <= 1e-4
+    assert np.abs(out2["score_maps"].numpy() - g["online_score_maps"]).max() <= 2e-4
+
+
 def test_golden_boxes_are_not_degenerate():
     """The sharpened seeded weights must give boxes away from the crop centre, otherwise the 0.5 px bound
     would hold for any implementation ('parity at random init')."""
