@@ -97,3 +97,14 @@ def make_inputs(variant: str, cfg, batch: int, seed: int = 1, device="cpu", pin:
         return one(ts), one(ts), one(ss)
     t, ot, s = [one(ts), one(ts)], [one(ts), one(ts)], [one(ss), one(ss)]
     return t, ot, s
+
+
+def make_online_inputs(cfg, n_online: int = 3, seed: int = 11, device="cpu"):
+    """(template [1,3,T,T], online_template [n,3,T,T], search [1,3,S,S]) for the cached-template path
+    (set_online / forward_test), seeded N(0,1) crops."""
+    g = torch.Generator().manual_seed(seed)
+    ts, ss = cfg.DATA.TEMPLATE.SIZE, cfg.DATA.SEARCH.SIZE
+    t = torch.randn(1, 3, ts, ts, generator=g)
+    ot = torch.randn(n_online, 3, ts, ts, generator=g)
+    s = torch.randn(1, 3, ss, ss, generator=g)
+    return tuple(x.to(device) if device != "cpu" else x for x in (t, ot, s))

@@ -73,12 +73,14 @@ def _cpu_prroi_module():
     return P()
 
 
-def main_online(sharpen):
-    """mixformer_vit_online: full forward with the SPM score head, and set_online + forward_test (cached templates)."""
+def main_online(sharpen, yaml_name=None, batch=BATCH):
+    """mixformer_vit_online: full forward with the SPM score head, and set_online + forward_test (cached templates).
+    yaml_name = "baseline_large": MixViT-L (1024 x 24 layers, 384 search / 192 template), batch 1."""
     variant = "mixformer_vit_online"
-    model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen)
+    yaml_name = yaml_name or synthetic.DEFAULT_YAML[variant]
+    model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen, yaml_name=yaml_name)
     sd = model.state_dict()
-    ref, rcfg = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant])
+    ref, rcfg = ref_shims.build_reference_model(variant, yaml_name)
     missing, unexpected = ref.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
     ref.score_branch.search_prroipool = _cpu_prroi_module()
@@ -91,7 +93,7 @@ def main_online(sharpen):
         return tl, br
     ref.box_head.get_score_map = hooked
     save = {}
-    t, ot, s = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+    t, ot, s = synthetic.make_inputs(variant, cfg, batch, INPUT_SEED)
     with torch.no_grad():
         out, _ = ref(t, ot, s, run_score_head=True)
     ora = O.forward(variant, sd, cfg, t, ot, s)
@@ -101,10 +103,7 @@ def main_online(sharpen):
     assert d[0] <= 1e-5 and d[1] <= 2e-4 and d[2] <= 2e-4
     save.update(pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy(), pred_scores=out["pred_scores"].numpy())
     # cached-template path: one template, 3 online templates, one search crop
-    g = torch.Generator().manual_seed(INPUT_SEED + 10)
-    tt = torch.randn(1, 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.TEMPLATE.SIZE, generator=g)
-    oo = torch.randn(3, 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.TEMPLATE.SIZE, generator=g)
-    ss = torch.randn(1, 3, cfg.DATA.SEARCH.SIZE, cfg.DATA.SEARCH.SIZE, generator=g)
+    tt, oo, ss = synthetic.make_online_inputs(cfg, 3, INPUT_SEED + 10)
     with torch.no_grad():
         ref.set_online(tt, oo)
         out2, _ = ref.forward_test(ss, run_score_head=True)
@@ -114,12 +113,11 @@ def main_online(sharpen):
          (out2["pred_scores"] - ora2["pred_scores"]).abs().max().item()]
     print(f"   cached-template path: oracle vs reference boxes {d[0]:.3e} maps {d[1]:.3e} scores {d[2]:.3e}")
     assert d[0] <= 1e-5 and d[1] <= 2e-4 and d[2] <= 2e-4
-    save.update(online_template=tt.numpy(), online_online_template=oo.numpy(), online_search=ss.numpy(),
-                online_pred_boxes=out2["pred_boxes"].numpy(), online_score_maps=cap["maps"].numpy(),
+    save.update(online_pred_boxes=out2["pred_boxes"].numpy(), online_score_maps=cap["maps"].numpy(),
                 online_pred_scores=out2["pred_scores"].numpy())
     print("   scores (logits):", out["pred_scores"].tolist(), out2["pred_scores"].tolist())
-    tag = "" if sharpen else "_plain"
-    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}{tag}_b{BATCH}.npz"), **save)
+    tag = ("" if sharpen else "_plain") + ("" if yaml_name == synthetic.DEFAULT_YAML[variant] else "_" + yaml_name)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}{tag}_b{batch}.npz"), **save)
 
 
 def main(variants):
@@ -129,6 +127,7 @@ def main(variants):
         torch.set_num_threads(8)
         for sharpen in (True, False):
             main_online(sharpen)
+        main_online(False, "baseline_large", 1)
         variants = [v for v in variants if v != "mixformer_vit_online"]
     for variant, sharpen in [(v, s) for v in variants for s in (True, False)]:
         # two seeded weight sets: "sharpened" (peaky corner maps, see synthetic.py) and "plain" = the builders'

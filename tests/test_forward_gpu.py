@@ -175,9 +175,10 @@ def test_online_score_model(built_lib, precision, sharpen):
     res = model._engine.forward(*inputs)
     torch.cuda.synchronize()
     assert torch.equal(res["pred_boxes"], coords) and torch.equal(res["pred_scores"], out["pred_scores"])
-    model.set_online(torch.from_numpy(g["online_template"]).cuda(), torch.from_numpy(g["online_online_template"]).cuda())
-    out2, _ = model.forward_test(torch.from_numpy(g["online_search"]).cuda(), run_score_head=True)
-    res2 = model._engine.forward_test(torch.from_numpy(g["online_search"]).cuda())
+    tt, oo, ss = synthetic.make_online_inputs(cfg, 3, 11, device="cuda")
+    model.set_online(tt, oo)
+    out2, _ = model.forward_test(ss, run_score_head=True)
+    res2 = model._engine.forward_test(ss)
     torch.cuda.synchronize()
     size = cfg.DATA.SEARCH.SIZE
     d = dict(box=np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * size,
@@ -212,3 +213,29 @@ def test_online_paths_reject_misuse(built_lib):
     model.set_online(t[:1], ot)
     with pytest.raises(RuntimeError):
         model.forward_test(s)                     # one search crop per cached sequence
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_online_score_model_vit_large(built_lib, precision):
+    """MixViT-L online (experiments/mixformer_vit_online/baseline_large.yaml: 1024 x 24 layers x 16 heads, 384 search /
+    192 template -> 864 tokens, 96 x 96 corner maps): full forward + SPM and the cached-template path."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(ONLINE, 0, sharpen=False, yaml_name="baseline_large")
+    model = model.cuda().set_precision(precision)
+    g = np.load(os.path.join(GOLDEN, f"{ONLINE}_plain_baseline_large_b1.npz"))
+    inputs = synthetic.make_inputs(ONLINE, cfg, 1, 1, device="cuda")
+    out, _ = model(*inputs, run_score_head=True)
+    tt, oo, ss = synthetic.make_online_inputs(cfg, 3, 11, device="cuda")
+    model.set_online(tt, oo)
+    out2, _ = model.forward_test(ss, run_score_head=True)
+    torch.cuda.synchronize()
+    size = cfg.DATA.SEARCH.SIZE
+    d = dict(box=np.abs(out["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * size,
+             score=np.abs(out["pred_scores"].cpu().numpy() - g["pred_scores"]).max(),
+             obox=np.abs(out2["pred_boxes"].cpu().numpy() - g["online_pred_boxes"]).max() * size,
+             oscore=np.abs(out2["pred_scores"].cpu().numpy() - g["online_pred_scores"]).max())
+    print(f"{ONLINE} large {precision}: " + "  ".join(f"{k} {v:.3e}" for k, v in d.items()))
+    if precision == "fp32":
+        assert max(d["box"], d["obox"]) <= 1e-4 * size and max(d["score"], d["oscore"]) <= 1e-4
+    else:
+        assert max(d["box"], d["obox"]) <= 0.5 and max(d["score"], d["oscore"]) <= 1e-2

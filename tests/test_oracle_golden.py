@@ -42,8 +42,9 @@ def test_online_oracle_matches_reference_vectors():
     out = O.forward(variant, sd, cfg, *synthetic.make_inputs(variant, cfg, 2, 1))
     assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
     assert np.abs(out["pred_scores"].numpy() - g["pred_scores"]).max() <= 1e-4
-    st = O.online_set(sd, cfg, torch.from_numpy(g["online_template"]), torch.from_numpy(g["online_online_template"]))
-    out2 = O.online_forward_test(sd, cfg, st, torch.from_numpy(g["online_search"]))
+    tt, oo, ss = synthetic.make_online_inputs(cfg, 3, 11)
+    st = O.online_set(sd, cfg, tt, oo)
+    out2 = O.online_forward_test(sd, cfg, st, ss)
     assert np.abs(out2["pred_boxes"].numpy() - g["online_pred_boxes"]).max() <= 1e-5
     assert np.abs(out2["pred_scores"].numpy() - g["online_pred_scores"]).max() <= 1e-4
     assert np.abs(out2["score_maps"].numpy() - g["online_score_maps"]).max() <= 2e-4
