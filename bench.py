@@ -42,7 +42,7 @@ UNIT = "frames/s"
 # 2*MAC of matmul + conv of one sequence-frame, reference modules under FlopCounterMode
 GFLOP_PER_FRAME = {"mixformer_vit": 92.40, "mixformer_vit_rgbt": 183.79, "mixformer_vit_rgbt_shared": 183.79,
                    "mixformer_vit_rgbt_unibackbone": 183.79, "asymmetric_shared": 186.85,
-                   "asymmetric_shared_ce": 143.65}
+                   "asymmetric_shared_ce": 143.65, "mixformer_vit_online": 92.45, "mixformer_convmae_online": 118.05}
 
 
 def _peaks():

@@ -81,6 +81,19 @@ int mmt_layernorm(const float* x, int rows, int C, float eps, const float* g0, c
 int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
                   float* out_f32, void* out_bf16, int out_seq_rows, int out_row_off, void* stream);
 
+/*
+ * ConvMAE stem (lib/models/mixformer_convmae/mixformer_online.py).  mmt_layernorm_act: channel LayerNorm of fp32 NHWC
+ * rows + optional exact GELU (PatchEmbed.forward :45-50; CBlock norms :172-189 with gelu = 0); seg_rows > 0 re-maps
+ * output row r to (r / seg_rows) * out_seq_rows + out_row_off + r % seg_rows (token order [t | ot | s]).
+ * mmt_patchify2x2: rows of a Conv2d(C, E, 2, stride 2) patch matrix, k = (ky*2 + kx)*C + c.  mmt_dwconv5x5: depthwise
+ * Conv2d(E, E, 5, padding 2, groups E) + bias (CBlock.attn :172), weights fp32 [25, E] tap-major.
+ */
+int mmt_layernorm_act(const float* x, int rows, int C, float eps, const float* gamma, const float* beta, int gelu,
+                      float* out_f32, void* out_bf16, int seg_rows, int out_seq_rows, int out_row_off, void* stream);
+int mmt_patchify2x2(const float* x, int B, int H, int W, int C, void* out, int out_bf16, void* stream);
+int mmt_dwconv5x5(const void* in, const float* w, const float* bias, int B, int H, int W, int E, void* out, int is_bf16,
+                  void* stream);
+
 /* dst[s*rows_per_seq + r, :] = T(src[s*seq_stride + row_off + r, :]): e.g. the search tokens of every sequence
  * out of the [template, online template, search] token layout (torch.split, mixformer.py:208). */
 int mmt_copy_rows(const float* src, int seq_stride, int row_off, int rows_per_seq, int nseq, int C, void* dst,

@@ -9,6 +9,7 @@
     build_asymmetric_shared_ce(cfg, train=False)         lib/models/mixformer_vit_rgbt/asymmetric_shared_ce.py:590-640
     build_mixformer_vit_online_score(cfg, train=False)   lib/models/mixformer_vit/mixformer_online.py:363-385
         (SPM score head + cached-template set_online / forward_test)
+    build_mixformer_convmae_online_score(cfg, train=False)  lib/models/mixformer_convmae/mixformer_online.py:506-526
 
 The returned nn.Module owns nn.Parameters / buffers under EXACTLY the reference's state_dict keys and shapes, so
 `load_state_dict(torch.load(ckpt)["net"], strict=True)` works on reference checkpoints.  The torch sub-modules
@@ -96,6 +97,62 @@ class _Backbone(nn.Module):
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=0.02)
                 nn.init.zeros_(m.bias)
+
+
+class _CMlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Conv2d(dim, hidden, 1)
+        self.fc2 = nn.Conv2d(hidden, dim, 1)
+
+
+class _CBlock(nn.Module):
+    """Parameter layout of CBlock (lib/models/mixformer_convmae/mixformer_online.py:167-180)."""
+
+    def __init__(self, dim, mlp_ratio=4):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.conv1 = nn.Conv2d(dim, dim, 1)
+        self.conv2 = nn.Conv2d(dim, dim, 1)
+        self.attn = nn.Conv2d(dim, dim, 5, padding=2, groups=dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _CMlp(dim, int(dim * mlp_ratio))
+
+
+class _ConvPatchEmbed(nn.Module):
+    def __init__(self, patch, inp, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(inp, dim, kernel_size=patch, stride=patch)
+        self.norm = nn.LayerNorm(dim)
+
+
+class _ConvViT(nn.Module):
+    """Parameter layout of ConvViT (lib/models/mixformer_convmae/mixformer_online.py:192-262)."""
+    DIMS = {"convmae_base": ((256, 384, 768), (2, 2, 11), 12), "convmae_large": ((384, 768, 1024), (2, 2, 20), 16)}
+
+    def __init__(self, vit_type, img_size_s, img_size_t):
+        super().__init__()
+        if vit_type not in self.DIMS:
+            raise KeyError("VIT_TYPE shoule set to 'convmae_base' or 'convmae_large'")
+        (e0, e1, e2), depth, heads = self.DIMS[vit_type]
+        self.embed_dim, self.num_heads = e2, heads
+        self.patch_embed1 = _ConvPatchEmbed(4, 3, e0)
+        self.patch_embed2 = _ConvPatchEmbed(2, e0, e1)
+        self.patch_embed3 = _ConvPatchEmbed(2, e1, e2)
+        self.patch_embed4 = nn.Linear(e2, e2)
+        self.blocks1 = nn.ModuleList([_CBlock(e0) for _ in range(depth[0])])
+        self.blocks2 = nn.ModuleList([_CBlock(e1) for _ in range(depth[1])])
+        self.blocks3 = nn.ModuleList([_Block(e2, False) for _ in range(depth[2])])
+        self.norm = nn.LayerNorm(e2, eps=1e-6)
+        for m in self.modules():      # ConvViT._init_weights :236-244
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+        self.grid_size_s, self.grid_size_t = img_size_s // 16, img_size_t // 16
+        self.pos_embed_s = nn.Parameter(torch.zeros(1, self.grid_size_s ** 2, e2), requires_grad=False)
+        self.pos_embed_t = nn.Parameter(torch.zeros(1, self.grid_size_t ** 2, e2), requires_grad=False)
+        self.pos_embed_s.data.copy_(sincos_pos_embed_2d(e2, self.grid_size_s).unsqueeze(0))
+        self.pos_embed_t.data.copy_(sincos_pos_embed_2d(e2, self.grid_size_t).unsqueeze(0))
 
 
 class FrozenBatchNorm2d(nn.Module):
@@ -316,6 +373,8 @@ class _EngineModule(nn.Module):
         from .engine import ForwardEngine
         if self.variant == "mixformer_vit_online":
             from .engine_online import OnlineEngine as ForwardEngine
+        elif self.variant == "mixformer_convmae_online":
+            from .engine_online import ConvMAEOnlineEngine as ForwardEngine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
@@ -504,7 +563,21 @@ def build_mixformer_vit_online_score(cfg, settings=None, train=False) -> MixForm
     return MixFormerOnlineScore(backbone, build_box_head(cfg), score_branch, cfg).eval()
 
 
+class MixFormerConvMAEOnlineScore(MixFormerOnlineScore):
+    """ConvMAE-backbone online tracker (lib/models/mixformer_convmae/mixformer_online.py:427-504)."""
+    variant = "mixformer_convmae_online"
+
+
+def build_mixformer_convmae_online_score(cfg, settings=None, train=False) -> MixFormerConvMAEOnlineScore:
+    """lib/models/mixformer_convmae/mixformer_online.py:506-526."""
+    _require_inference(train)
+    backbone = _ConvViT(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE)
+    score_branch = _ScoreDecoder(num_heads=cfg.MODEL.HIDDEN_DIM // 64, hidden_dim=cfg.MODEL.HIDDEN_DIM, pool_size=4)
+    return MixFormerConvMAEOnlineScore(backbone, build_box_head(cfg), score_branch, cfg).eval()
+
+
 BUILDERS = {
+    "mixformer_convmae_online": build_mixformer_convmae_online_score,
     "mixformer_vit_online": build_mixformer_vit_online_score,
     "mixformer_vit": build_mixformer_vit,
     "mixformer_vit_rgbt": build_mixformer_vit_rgbt,

@@ -23,7 +23,10 @@ import torch
 from . import ops
 from .pos_embed import fusion_pos_table
 
-VIT_DIMS = {"base_patch16": dict(dim=768, depth=12, heads=12), "large_patch16": dict(dim=1024, depth=24, heads=16)}
+VIT_DIMS = {"base_patch16": dict(dim=768, depth=12, heads=12), "large_patch16": dict(dim=1024, depth=24, heads=16),
+            # ConvMAE (lib/models/mixformer_convmae/mixformer_online.py:395-410): conv stem (4,2,2) then MixViT blocks
+            "convmae_base": dict(dim=768, depth=11, heads=12, stem=(256, 384)),
+            "convmae_large": dict(dim=1024, depth=20, heads=16, stem=(384, 768))}
 STACKED = ("mixformer_vit_rgbt_shared", "mixformer_vit_rgbt_unibackbone", "asymmetric_shared", "asymmetric_shared_ce")
 CROSS_MODAL = ("asymmetric_shared", "asymmetric_shared_ce")
 PER_MODALITY_LN = ("mixformer_vit_rgbt_shared", "asymmetric_shared", "asymmetric_shared_ce")
@@ -41,7 +44,10 @@ class ForwardEngine:
         self.act = torch.bfloat16 if self.bf16 else torch.float32
         m = cfg["MODEL"]
         d = VIT_DIMS[m["VIT_TYPE"]]
+        self.vit_type = m["VIT_TYPE"]
         self.dim, self.depth, self.heads = d["dim"], d["depth"], d["heads"]
+        self.stem_dims = d.get("stem")           # ConvMAE: channel widths of the two conv stages
+        self.block_prefix = "blocks3." if self.stem_dims else "blocks."
         self.search_size = int(cfg["DATA"]["SEARCH"]["SIZE"])
         self.template_size = int(cfg["DATA"]["TEMPLATE"]["SIZE"])
         self.gs, self.gt = self.search_size // 16, self.template_size // 16
@@ -51,7 +57,7 @@ class ForwardEngine:
         if self.head_type != "CORNER_UP":
             raise NotImplementedError("only the CORNER_UP (pyramid) head - used by every shipped YAML - is on the "
                                       "accelerated path")
-        self.rgbt = variant not in ("mixformer_vit", "mixformer_vit_online")
+        self.rgbt = variant not in ("mixformer_vit", "mixformer_vit_online", "mixformer_convmae_online")
         self.fusion_class = m.get("FUSION_CLASS") if self.rgbt else None
         bb = m.get("BACKBONE", {})
         self.ce_loc = list(bb["CE_LOC"]) if (variant == "asymmetric_shared_ce" and "CE_LOC" in bb) else []
@@ -70,13 +76,17 @@ class ForwardEngine:
         dev = self.dev
         g = lambda k: sd[prefix + k]
         bb = {}
-        bb["pe_w"] = self._w(g("patch_embed.proj.weight").reshape(self.dim, -1))
-        bb["pe_b"] = _f32(g("patch_embed.proj.bias"), dev)
+        if self.stem_dims:      # the token-embedding GEMM is patch_embed4 (Linear) on the conv stem's output
+            bb["pe_w"] = self._w(g("patch_embed4.weight"))
+            bb["pe_b"] = _f32(g("patch_embed4.bias"), dev)
+        else:
+            bb["pe_w"] = self._w(g("patch_embed.proj.weight").reshape(self.dim, -1))
+            bb["pe_b"] = _f32(g("patch_embed.proj.bias"), dev)
         pt, ps = g("pos_embed_t")[0], g("pos_embed_s")[0]
         bb["pos"] = _f32(torch.cat([pt, pt, ps], dim=0), dev)          # [N0, dim]
         blocks = []
         for i in range(self.depth):
-            p = f"blocks.{i}."
+            p = f"{self.block_prefix}{i}."
             b = {}
             for j in (1, 2):
                 if per_modality_ln:
@@ -171,7 +181,7 @@ class ForwardEngine:
         return F
 
     def _pack(self, sd):
-        if self.variant in ("mixformer_vit", "mixformer_vit_online"):
+        if self.variant in ("mixformer_vit", "mixformer_vit_online", "mixformer_convmae_online"):
             self.bbs = [self._pack_backbone(sd, "backbone.", False)]
         elif self.variant == "mixformer_vit_rgbt":
             self.bbs = [self._pack_backbone(sd, "backbone_v.", False), self._pack_backbone(sd, "backbone_i.", False)]
@@ -226,14 +236,24 @@ class ForwardEngine:
         return self._tiles[key]
 
     # ------------------------------------------------------------------------------------------ backbone
+    def _embed_buf(self, rows):
+        """A-operand buffer of the token-embedding GEMM: one row per token, in final token order."""
+        return self._buf(rows, "patches", (rows, 3 * 256), self.act)
+
+    def _stage_tokens(self, bb, img, buf, tok_off, tok_per_seq):
+        """Write the embedding-GEMM input rows of the crops `img` [n,3,S,S] at rows b*tok_per_seq + tok_off + patch.
+        MixViT: the 16x16 patch matrix.  (ConvMAE: the conv stem's output, engine_online.ConvMAEOnlineEngine.)"""
+        ops.patchify(img, buf, tok_off, tok_per_seq)
+
     def _embed(self, bb, B, imgs_t, imgs_ot, imgs_s, x):
-        """Patch-embed the three crops of `B` sequences into x [B*N0, dim] (rows b*N0 + [t | ot | s])."""
-        patches = self._buf(B, "patches", (x.shape[0], 3 * 256), self.act)
+        """Embed the three crops of `B` sequences into x [B*N0, dim] (rows b*N0 + [t | ot | s]): staging of the GEMM
+        input in token order, then ONE GEMM with bias and the positional table in the epilogue."""
+        buf = self._embed_buf(x.shape[0])
         n_t = self.gt * self.gt
-        ops.patchify(imgs_t, patches, 0, self.N0)
-        ops.patchify(imgs_ot, patches, n_t, self.N0)
-        ops.patchify(imgs_s, patches, 2 * n_t, self.N0)
-        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos"], out=x)
+        self._stage_tokens(bb, imgs_t, buf, 0, self.N0)
+        self._stage_tokens(bb, imgs_ot, buf, n_t, self.N0)
+        self._stage_tokens(bb, imgs_s, buf, 2 * n_t, self.N0)
+        ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos"], out=x)
 
     def _block(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep=None, gidx=None, tiles=None, qkv1=None,
                qkv_out=None):

@@ -138,9 +138,9 @@ class OnlineEngine(ForwardEngine):
         bb = self.bbs[0]
         tag = ("online_t", Tm)
         x = self._buf(tag, "x", (Tm, self.dim), torch.float32)
-        patches = self._buf(tag, "patches", (Tm, 3 * 256), self.act)
-        ops.patchify(t, patches, 0, Tm)
-        ops.patchify(ot, patches, T, T)
+        patches = self._embed_buf(Tm)
+        self._stage_tokens(bb, t, patches, 0, Tm)
+        self._stage_tokens(bb, ot, patches, T, T)
         pos_t = self._ws.get("pos_t")
         if pos_t is None:
             pos_t = bb["pos"][:T].contiguous()
@@ -165,8 +165,8 @@ class OnlineEngine(ForwardEngine):
         Ls, Tm, bb = self.Ls0, self.mem_rows, self.bbs[0]
         tag = ("online_s", Tm)
         x = self._buf(tag, "x", (Ls, self.dim), torch.float32)
-        patches = self._buf(tag, "patches", (Ls, 3 * 256), self.act)
-        ops.patchify(s, patches, 0, Ls)
+        patches = self._embed_buf(Ls)
+        self._stage_tokens(bb, s, patches, 0, Ls)
         ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_s"], out=x)
         tiles = self._full_tiles(Ls, [(1, 0, Tm), (0, 0, Ls)], "forward_test")
         for i, blk in enumerate(bb["blocks"]):
@@ -177,3 +177,88 @@ class OnlineEngine(ForwardEngine):
         if run_score_head:
             res["pred_scores"] = self._scores(x, Ls, 0, 1, self.templ_rows, gt_bboxes)
         return res
+
+
+class ConvMAEOnlineEngine(OnlineEngine):
+    """mixformer_convmae_online: the same online engine behind the ConvMAE conv stem
+    (lib/models/mixformer_convmae/mixformer_online.py:266-392): per crop, Conv 4x4/4 + LN + GELU, 2 CBlocks,
+    Conv 2x2/2 + LN + GELU, 2 CBlocks, Conv 2x2/2 + LN + GELU, then patch_embed4 (Linear) + pos-embed as the
+    token-embedding GEMM.  Stem residual streams are fp32 NHWC rows; every conv except the depthwise 5x5 is a GEMM."""
+
+    def _pack(self, sd):
+        super()._pack(sd)
+        dev = self.dev
+        g = lambda k: sd["backbone." + k]
+        E0, E1 = self.stem_dims
+        st = {}
+        st["pe1_w"] = self._w(g("patch_embed1.proj.weight").reshape(E0, -1))                       # (c, ky, kx)
+        st["pe2_w"] = self._w(g("patch_embed2.proj.weight").permute(0, 2, 3, 1).reshape(E1, -1))   # (ky, kx, c)
+        st["pe3_w"] = self._w(g("patch_embed3.proj.weight").permute(0, 2, 3, 1).reshape(self.dim, -1))
+        for j in (1, 2, 3):
+            st[f"pe{j}_b"] = _f32(g(f"patch_embed{j}.proj.bias"), dev)
+            st[f"pe{j}_ln"] = (_f32(g(f"patch_embed{j}.norm.weight"), dev), _f32(g(f"patch_embed{j}.norm.bias"), dev))
+        for stage, E in ((1, E0), (2, E1)):
+            blocks = []
+            i = 0
+            while f"backbone.blocks{stage}.{i}.conv1.weight" in sd:
+                p = f"blocks{stage}.{i}."
+                blocks.append(dict(
+                    ln1=(_f32(g(p + "norm1.weight"), dev), _f32(g(p + "norm1.bias"), dev)),
+                    ln2=(_f32(g(p + "norm2.weight"), dev), _f32(g(p + "norm2.bias"), dev)),
+                    c1_w=self._w(g(p + "conv1.weight").reshape(E, E)), c1_b=_f32(g(p + "conv1.bias"), dev),
+                    c2_w=self._w(g(p + "conv2.weight").reshape(E, E)), c2_b=_f32(g(p + "conv2.bias"), dev),
+                    dw_w=_f32(g(p + "attn.weight").reshape(E, 25).t(), dev), dw_b=_f32(g(p + "attn.bias"), dev),
+                    f1_w=self._w(g(p + "mlp.fc1.weight").reshape(-1, E)), f1_b=_f32(g(p + "mlp.fc1.bias"), dev),
+                    f2_w=self._w(g(p + "mlp.fc2.weight").reshape(E, -1)), f2_b=_f32(g(p + "mlp.fc2.bias"), dev)))
+                i += 1
+            st[f"blocks{stage}"] = blocks
+        self.stem = st
+
+    def _embed_buf(self, rows):
+        return self._buf(rows, "pe4_in", (rows, self.dim), self.act)
+
+    def _ln_act(self, x, ln, gelu, out, **remap):
+        if out.dtype == torch.float32:
+            ops.layernorm_act(x, ln[0], ln[1], 1e-5, gelu, out_f32=out, **remap)
+        else:
+            ops.layernorm_act(x, ln[0], ln[1], 1e-5, gelu, out_bf16=out, **remap)
+
+    def _cblock(self, blk, x, n, H, W, E, tag):
+        """CBlock.forward (:181-189, mask=None): x += conv2(dw5x5(conv1(LN(x)))); x += fc2(GELU(fc1(LN(x))))."""
+        rows = n * H * W
+        h = self._buf(tag, f"h{E}", (rows, E), self.act)
+        c1 = self._buf(tag, f"c1{E}", (rows, E), self.act)
+        dw = self._buf(tag, f"dw{E}", (rows, E), self.act)
+        self._ln_act(x, blk["ln1"], False, h)
+        ops.gemm(h, blk["c1_w"], blk["c1_b"], out=c1)
+        ops.dwconv5x5(c1, blk["dw_w"], blk["dw_b"], n, H, W, dw)
+        ops.gemm(dw, blk["c2_w"], blk["c2_b"], ops.ACT_NONE, x, None, out=x)
+        self._ln_act(x, blk["ln2"], False, h)
+        hid = self._buf(tag, f"hid{E}", (rows, blk["f1_w"].shape[0]), self.act)
+        ops.gemm(h, blk["f1_w"], blk["f1_b"], ops.ACT_GELU, out=hid)
+        ops.gemm(hid, blk["f2_w"], blk["f2_b"], ops.ACT_NONE, x, None, out=x)
+
+    def _stage_tokens(self, bb, img, buf, tok_off, tok_per_seq):
+        st = self.stem
+        E0, E1 = self.stem_dims
+        n, S = img.shape[0], img.shape[2]
+        H1, H2, H3 = S // 4, S // 8, S // 16
+        tag = ("stem", n, S)
+        p1 = self._buf(tag, "p1", (n * H1 * H1, 48), self.act)
+        ops.patchify(img, p1, 0, H1 * H1, patch=4)
+        y1 = self._buf(tag, "y1", (n * H1 * H1, E0), torch.float32)
+        ops.gemm(p1, st["pe1_w"], st["pe1_b"], out=y1)
+        self._ln_act(y1, st["pe1_ln"], True, y1)
+        for blk in st["blocks1"]:
+            self._cblock(blk, y1, n, H1, H1, E0, tag)
+        p2 = ops.patchify2x2(y1, n, H1, H1, self._buf(tag, "p2", (n * H2 * H2, 4 * E0), self.act))
+        y2 = self._buf(tag, "y2", (n * H2 * H2, E1), torch.float32)
+        ops.gemm(p2, st["pe2_w"], st["pe2_b"], out=y2)
+        self._ln_act(y2, st["pe2_ln"], True, y2)
+        for blk in st["blocks2"]:
+            self._cblock(blk, y2, n, H2, H2, E1, tag)
+        p3 = ops.patchify2x2(y2, n, H2, H2, self._buf(tag, "p3", (n * H3 * H3, 4 * E1), self.act))
+        y3 = self._buf(tag, "y3", (n * H3 * H3, self.dim), torch.float32)
+        ops.gemm(p3, st["pe3_w"], st["pe3_b"], out=y3)
+        # LN + GELU of patch_embed3, written straight into the token order of the embedding GEMM (patch_embed4)
+        self._ln_act(y3, st["pe3_ln"], True, buf, seg_rows=H3 * H3, out_seq_rows=tok_per_seq, out_row_off=tok_off)

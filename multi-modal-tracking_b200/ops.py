@@ -351,6 +351,47 @@ def ce_recover(x, nseq, n_tok, Lt, gidx, Lk, Ls0, out):
     _count(1, "ce_recover", _ev)
 
 
+_layernorm_act = _lib.fn("mmt_layernorm_act")
+_patchify2x2 = _lib.fn("mmt_patchify2x2")
+_dwconv5x5 = _lib.fn("mmt_dwconv5x5")
+
+
+def layernorm_act(x, g, b, eps, gelu, out_f32=None, out_bf16=None, seg_rows=0, out_seq_rows=0, out_row_off=0):
+    """Channel LayerNorm (+ exact GELU) of fp32 rows; optional re-mapping of the output rows (see mmt_b200.h)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    assert out_f32 is None or (out_f32.dtype == torch.float32 and out_f32.is_contiguous())
+    assert out_bf16 is None or (out_bf16.dtype == torch.bfloat16 and out_bf16.is_contiguous())
+    _ev = _begin()
+    _lib.check(_layernorm_act(_ptr(x), c_int(x.shape[0]), c_int(x.shape[1]), c_float(eps), _ptr(g), _ptr(b),
+                              c_int(1 if gelu else 0), _ptr(out_f32), _ptr(out_bf16), c_int(seg_rows),
+                              c_int(out_seq_rows), c_int(out_row_off), _stream()), "mmt_layernorm_act")
+    _count(1, "layernorm_act", _ev)
+
+
+def patchify2x2(x, B, H, W, out):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    C = x.shape[1]
+    assert x.shape[0] == B * H * W and out.shape == (B * (H // 2) * (W // 2), 4 * C)
+    _ev = _begin()
+    _lib.check(_patchify2x2(_ptr(x), c_int(B), c_int(H), c_int(W), c_int(C), _ptr(out), c_int(_is_bf16(out)),
+                            _stream()), "mmt_patchify2x2")
+    _count(1, "patchify2x2", _ev)
+    return out
+
+
+def dwconv5x5(x, w, bias, B, H, W, out):
+    _need_cuda(x, w, bias, out)
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and x.shape == out.shape
+    assert w.dtype == torch.float32 and w.shape == (25, x.shape[1]) and x.shape[0] == B * H * W
+    _ev = _begin()
+    _lib.check(_dwconv5x5(_ptr(x), _ptr(w), _ptr(bias), c_int(B), c_int(H), c_int(W), c_int(x.shape[1]), _ptr(out),
+                          c_int(_is_bf16(x)), _stream()), "mmt_dwconv5x5")
+    _count(1, "dwconv5x5", _ev)
+    return out
+
+
 _spm_rois = _lib.fn("mmt_spm_rois")
 
 

@@ -27,6 +27,7 @@ DEFAULT_YAML = {
     "asymmetric_shared": "attention_lasher_newfusion_2layer",
     "asymmetric_shared_ce": "attention_lasher_newfusion_2layer",
     "mixformer_vit_online": "baseline",
+    "mixformer_convmae_online": "baseline",
 }
 
 
@@ -93,7 +94,7 @@ def make_inputs(variant: str, cfg, batch: int, seed: int = 1, device="cpu", pin:
             t = t.pin_memory()
         return t.to(device) if device != "cpu" else t
 
-    if variant in ("mixformer_vit", "mixformer_vit_online"):
+    if variant in ("mixformer_vit", "mixformer_vit_online", "mixformer_convmae_online"):
         return one(ts), one(ts), one(ss)
     t, ot, s = [one(ts), one(ts)], [one(ts), one(ts)], [one(ss), one(ss)]
     return t, ot, s

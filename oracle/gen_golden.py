@@ -73,10 +73,9 @@ def _cpu_prroi_module():
     return P()
 
 
-def main_online(sharpen, yaml_name=None, batch=BATCH):
-    """mixformer_vit_online: full forward with the SPM score head, and set_online + forward_test (cached templates).
-    yaml_name = "baseline_large": MixViT-L (1024 x 24 layers, 384 search / 192 template), batch 1."""
-    variant = "mixformer_vit_online"
+def main_online(sharpen, yaml_name=None, batch=BATCH, variant="mixformer_vit_online"):
+    """mixformer_vit_online / mixformer_convmae_online: full forward with the SPM score head, and set_online +
+    forward_test (cached templates).  yaml_name = "baseline_large": the -L models (384 search / 192 template), batch 1."""
     yaml_name = yaml_name or synthetic.DEFAULT_YAML[variant]
     model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen, yaml_name=yaml_name)
     sd = model.state_dict()
@@ -123,12 +122,13 @@ def main_online(sharpen, yaml_name=None, batch=BATCH):
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
-    if "mixformer_vit_online" in variants:
-        torch.set_num_threads(8)
-        for sharpen in (True, False):
-            main_online(sharpen)
-        main_online(False, "baseline_large", 1)
-        variants = [v for v in variants if v != "mixformer_vit_online"]
+    torch.set_num_threads(8)
+    for ov in ("mixformer_vit_online", "mixformer_convmae_online"):
+        if ov in variants:
+            for sharpen in (True, False):
+                main_online(sharpen, variant=ov)
+            main_online(False, "baseline_large", 1, variant=ov)
+            variants = [v for v in variants if v != ov]
     for variant, sharpen in [(v, s) for v in variants for s in (True, False)]:
         # two seeded weight sets: "sharpened" (peaky corner maps, see synthetic.py) and "plain" = the builders'
         # default random init, the weight set BASELINE.json's north_star names for the bf16 tolerances

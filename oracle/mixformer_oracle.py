@@ -118,15 +118,68 @@ def vit_dims(vit_type):
         return dict(dim=1024, depth=24, heads=16)
     if vit_type == "base_patch16":
         return dict(dim=768, depth=12, heads=12)
+    if vit_type == "convmae_base":       # lib/models/mixformer_convmae/mixformer_online.py:395-410
+        return dict(dim=768, depth=11, heads=12, convmae=True)
+    if vit_type == "convmae_large":
+        return dict(dim=1024, depth=20, heads=16, convmae=True)
     raise KeyError("VIT_TYPE shoule set to 'large_patch16' or 'base_patch16'")
 
 
+def _chan_ln(x, w, b, eps=1e-5):
+    """nn.LayerNorm over channels of an NCHW map: norm(x.permute(0,2,3,1)).permute(0,3,1,2)."""
+    return F.layer_norm(x.permute(0, 2, 3, 1), (x.shape[1],), w, b, eps).permute(0, 3, 1, 2)
+
+
+def _conv_patch_embed(sd, name, x, stride):
+    """PatchEmbed.forward lib/models/mixformer_convmae/mixformer_online.py:48-51: proj -> channel LN -> GELU."""
+    x = F.conv2d(x, sd[name + ".proj.weight"], sd[name + ".proj.bias"], stride=stride)
+    return F.gelu(_chan_ln(x, sd[name + ".norm.weight"], sd[name + ".norm.bias"]))
+
+
+def _cblock(p, x):
+    """CBlock.forward (mask=None) lib/models/mixformer_convmae/mixformer_online.py:181-189."""
+    h = _chan_ln(x, p["norm1.weight"], p["norm1.bias"])
+    h = F.conv2d(h, p["conv1.weight"], p["conv1.bias"])
+    h = F.conv2d(h, p["attn.weight"], p["attn.bias"], padding=2, groups=h.shape[1])
+    x = x + F.conv2d(h, p["conv2.weight"], p["conv2.bias"])
+    h = _chan_ln(x, p["norm2.weight"], p["norm2.bias"])
+    h = F.conv2d(F.gelu(F.conv2d(h, p["mlp.fc1.weight"], p["mlp.fc1.bias"])), p["mlp.fc2.weight"], p["mlp.fc2.bias"])
+    return x + h
+
+
+def convmae_stem(sd, img):
+    """ConvViT.forward, one crop: lib/models/mixformer_convmae/mixformer_online.py:266-276 -> tokens [B, n, C]."""
+    x = _conv_patch_embed(sd, "patch_embed1", img, 4)
+    i = 0
+    while f"blocks1.{i}.conv1.weight" in sd:
+        x = _cblock(_sub(sd, f"blocks1.{i}."), x)
+        i += 1
+    x = _conv_patch_embed(sd, "patch_embed2", x, 2)
+    i = 0
+    while f"blocks2.{i}.conv1.weight" in sd:
+        x = _cblock(_sub(sd, f"blocks2.{i}."), x)
+        i += 1
+    x = _conv_patch_embed(sd, "patch_embed3", x, 2)
+    x = x.flatten(2).permute(0, 2, 1)
+    return F.linear(x, sd["patch_embed4.weight"], sd["patch_embed4.bias"])
+
+
+def _tokens_of(sd, img):
+    """Token embedding of one crop WITHOUT the positional table: 16x16 patch conv (MixViT) or the ConvMAE stem."""
+    if "patch_embed4.weight" in sd:
+        return convmae_stem(sd, img)
+    return patch_embed(img, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"])
+
+
+def _block_prefix(sd):
+    return "blocks3." if "patch_embed4.weight" in sd else "blocks."
+
+
 def _embed_tokens(sd, x_t, x_ot, x_s):
-    """VisionTransformer.forward lib/models/mixformer_vit/mixformer.py:192-203."""
-    w, b = sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"]
-    t = patch_embed(x_t, w, b) + sd["pos_embed_t"]
-    ot = patch_embed(x_ot, w, b) + sd["pos_embed_t"]
-    s = patch_embed(x_s, w, b) + sd["pos_embed_s"]
+    """VisionTransformer.forward lib/models/mixformer_vit/mixformer.py:192-203 (ConvViT.forward :266-311)."""
+    t = _tokens_of(sd, x_t) + sd["pos_embed_t"]
+    ot = _tokens_of(sd, x_ot) + sd["pos_embed_t"]
+    s = _tokens_of(sd, x_s) + sd["pos_embed_s"]
     return torch.cat([t, ot, s], dim=1), t.shape[1] * 2, s.shape[1]
 
 
@@ -137,8 +190,9 @@ def backbone_plain(sd, x_t, x_ot, x_s, heads, depth, per_modality_ln=False):
     batch = RGB uses norm*_v, second half norm*_i).  Returns the search tokens [B, n_s, C] (no final norm)."""
     x, n_t, n_s = _embed_tokens(sd, x_t, x_ot, x_s)
     eps = 1e-6
+    bp = _block_prefix(sd)
     for i in range(depth):
-        p = _sub(sd, f"blocks.{i}.")
+        p = _sub(sd, f"{bp}{i}.")
         a = _sub(p, "attn.")
         m = _sub(p, "mlp.")
         if per_modality_ln:
@@ -487,14 +541,14 @@ def online_set(sd, cfg, template, online_template):
     mc = cfg if "variant" in cfg else model_cfg("mixformer_vit_online", cfg)
     d = vit_dims(mc["vit_type"])
     bsd = _sub(sd, "backbone.")
-    w, b = bsd["patch_embed.proj.weight"], bsd["patch_embed.proj.bias"]
-    x_t = patch_embed(template, w, b) + bsd["pos_embed_t"]
-    x_ot = patch_embed(online_template, w, b) + bsd["pos_embed_t"]
+    x_t = _tokens_of(bsd, template) + bsd["pos_embed_t"]
+    x_ot = _tokens_of(bsd, online_template) + bsd["pos_embed_t"]
     x = torch.cat([x_t, x_ot.reshape(1, -1, x_ot.shape[-1])], dim=1)
     st = OnlineState()
     H, C = d["heads"], x.shape[-1]
+    bp = _block_prefix(bsd)
     for i in range(d["depth"]):
-        p = _sub(bsd, f"blocks.{i}.")
+        p = _sub(bsd, f"{bp}{i}.")
         a = _sub(p, "attn.")
         h = _ln(x, p, "norm1", 1e-6)
         B, N, _ = h.shape
@@ -515,10 +569,11 @@ def online_forward_test(sd, cfg, st, search, run_score_head=True):
     mc = cfg if "variant" in cfg else model_cfg("mixformer_vit_online", cfg)
     d = vit_dims(mc["vit_type"])
     bsd = _sub(sd, "backbone.")
-    x = patch_embed(search, bsd["patch_embed.proj.weight"], bsd["patch_embed.proj.bias"]) + bsd["pos_embed_s"]
+    x = _tokens_of(bsd, search) + bsd["pos_embed_s"]
     H, C = d["heads"], x.shape[-1]
+    bp = _block_prefix(bsd)
     for i in range(d["depth"]):
-        p = _sub(bsd, f"blocks.{i}.")
+        p = _sub(bsd, f"{bp}{i}.")
         a = _sub(p, "attn.")
         h = _ln(x, p, "norm1", 1e-6)
         B, N, _ = h.shape
@@ -559,7 +614,7 @@ def forward(variant, sd, cfg, template, online_template, search):
     d = vit_dims(mc["vit_type"])
     g = mc["search_size"] // 16
     aux = {}
-    if variant == "mixformer_vit_online":   # lib/models/mixformer_vit/mixformer_online.py:297-311 (+ SPM)
+    if variant in ("mixformer_vit_online", "mixformer_convmae_online"):   # mixformer_online.py:297-311 (+ SPM)
         s, x = backbone_plain(_sub(sd, "backbone."), template, online_template, search, d["heads"], d["depth"])
         gt = mc["template_size"] // 16
         return forward_head_online(sd, _tokens_to_map(s, g), _tokens_to_map(x[:, :gt * gt], gt), mc, d["heads"])

@@ -47,6 +47,17 @@ def test_state_dict_layout(variant):
     assert not missing and not unexpected
 
 
+def test_convmae_state_dict_layout():
+    """ConvMAE online: 371 keys / 102.2 M (base), 479 keys / 298.0 M (large) - SURVEY.md appendix B."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    for yaml_name, keys, params in (("baseline", 371, 102.2), ("baseline_large", 479, 298.0)):
+        model, _ = synthetic.make_model("mixformer_convmae_online", 0, sharpen=False, yaml_name=yaml_name)
+        sd = model.state_dict()
+        assert len(sd) == keys and abs(sum(p.numel() for p in model.parameters()) / 1e6 - params) < 0.06
+        assert sd["backbone.blocks1.0.attn.weight"].shape[1:] == (1, 5, 5) and "backbone.patch_embed4.weight" in sd
+
+
 def test_online_score_state_dict_layout():
     """mixformer_vit_online: backbone with timm leftovers, FrozenBN head (HEAD_FREEZE_BN: no num_batches_tracked),
     score_branch.* of the SPM."""
@@ -63,7 +74,8 @@ def test_online_score_state_dict_layout():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
-@pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce", "mixformer_vit_online"])
+@pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce", "mixformer_vit_online",
+                                     "mixformer_convmae_online"])
 def test_reference_builder_accepts_our_state_dict(variant):
     """strict=True load of our state_dict INTO the unmodified reference module (and the reverse)."""
     import mmt_b200  # noqa: F401

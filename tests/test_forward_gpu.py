@@ -161,9 +161,13 @@ def test_cuda_graph_replay_matches_eager(built_lib):
 ONLINE = "mixformer_vit_online"
 
 
+ONLINE_VARIANTS = ["mixformer_vit_online", "mixformer_convmae_online"]
+
+
 @pytest.mark.parametrize("sharpen", [True, False], ids=["sharpened", "plain"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_online_score_model(built_lib, precision, sharpen):
+@pytest.mark.parametrize("ONLINE", ONLINE_VARIANTS)
+def test_online_score_model(built_lib, ONLINE, precision, sharpen):
     """SPM score head (PrRoIPool + score-token decoder) on the full forward, and the cached-template path
     set_online + forward_test, against the reference's golden outputs (lib/models/mixformer_vit/mixformer_online.py)."""
     from mmt_b200 import synthetic
@@ -216,9 +220,11 @@ def test_online_paths_reject_misuse(built_lib):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_online_score_model_vit_large(built_lib, precision):
-    """MixViT-L online (experiments/mixformer_vit_online/baseline_large.yaml: 1024 x 24 layers x 16 heads, 384 search /
-    192 template -> 864 tokens, 96 x 96 corner maps): full forward + SPM and the cached-template path."""
+@pytest.mark.parametrize("ONLINE", ONLINE_VARIANTS)
+def test_online_score_model_large(built_lib, ONLINE, precision):
+    """The -L online models of BASELINE.json configs[4] (experiments/mixformer_{vit,convmae}_online/baseline_large.yaml:
+    MixViT-L 1024 x 24 layers / ConvMAE-L 384-768-1024 stem + 20 layers, 16 heads, 384 search / 192 template -> 864
+    tokens, 96 x 96 corner maps): full forward + SPM and the cached-template path."""
     from mmt_b200 import synthetic
     model, cfg = synthetic.make_model(ONLINE, 0, sharpen=False, yaml_name="baseline_large")
     model = model.cuda().set_precision(precision)

@@ -29,13 +29,13 @@ def test_oracle_matches_reference_vectors(variant):
             assert out["ce_keep_v"][j].shape[1] == (227, 159, 112)[j]     # 324 -> 227 -> 159 -> 112
 
 
-def test_online_oracle_matches_reference_vectors():
-    """mixformer_vit_online: full forward with the SPM score, and set_online + forward_test on the stored crops."""
+@pytest.mark.parametrize("variant", ["mixformer_vit_online", "mixformer_convmae_online"])
+def test_online_oracle_matches_reference_vectors(variant):
+    """Online trackers: full forward with the SPM score, and set_online + forward_test on seeded crops."""
     import mmt_b200  # noqa: F401
     from mmt_b200 import synthetic
     from oracle import mixformer_oracle as O
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    variant = "mixformer_vit_online"
     model, cfg = synthetic.make_model(variant, 0, sharpen=False)
     sd = model.state_dict()
     g = np.load(os.path.join(GOLDEN, f"{variant}_plain_b2.npz"))
