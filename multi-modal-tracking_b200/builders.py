@@ -438,14 +438,16 @@ class MixFormer_RGBT(_EngineModule):
 
     @torch.no_grad()
     def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None,
-                ce_template_mask=None, ce_keep_rate=None, return_features=False):
+                ce_template_mask=None, ce_keep_rate=None, return_features=False, ready_events=None):
         if ce_template_mask is not None or ce_keep_rate is not None:
             # training-time CE schedule / template mask (lib/utils/ce_utils.py); the test-time trackers never
             # pass them (lib/test/tracker/asymmetric_shared_ce.py:96-98)
             raise NotImplementedError("ce_template_mask / ce_keep_rate are training-only arguments")
         if self._use_graph and not return_features:
+            for e in (ready_events or ()):
+                torch.cuda.current_stream().wait_event(e)
             return self._finish(self._graphed_forward(list(template), list(online_template), list(search)))
-        res = self.engine().forward(list(template), list(online_template), list(search))
+        res = self.engine().forward(list(template), list(online_template), list(search), ready_events=ready_events)
         return self._finish(res, return_features)
 
 

@@ -466,13 +466,18 @@ class ForwardEngine:
             raise RuntimeError(f"expected a [B,3,{size},{size}] crop, got {tuple(t.shape)}")
         return t.float().contiguous() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
 
-    def forward(self, template, online_template, search, want_maps=True):
+    def forward(self, template, online_template, search, want_maps=True, ready_events=None):
+        """ready_events: optional [event_v, event_i] recorded on a copy stream after that modality's crops arrived
+        (runner.FrameStep): the compute stream waits for a modality only right before its patch embedding, so the
+        second modality's host->device copy overlaps the first one's work."""
         self.aux = {}
+        wait = (lambda m: torch.cuda.current_stream().wait_event(ready_events[m])) if ready_events else (lambda m: None)
         if not self.rgbt:
             t, ot, s = (self._check_img(template, self.template_size), self._check_img(online_template, self.template_size),
                         self._check_img(search, self.search_size))
             B = s.shape[0]
             x = self._buf(B, "x", (B * self.N0, self.dim), torch.float32)
+            wait(0)
             self._embed(self.bbs[0], B, t, ot, s, x)
             feat = self._run_backbone(self.bbs[0], x, B, ("bb", B), False)
             boxes, maps = self._run_head(feat, B, want_maps)
@@ -487,11 +492,13 @@ class ForwardEngine:
             feats = []
             for m in range(2):
                 xm = x[m * M1:(m + 1) * M1]
+                wait(m)
                 self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm)
                 feats.append(self._run_backbone(self.bbs[m], xm, B, ("bb", B, m), False))
             sv, si = feats
         else:                                          # batch-stacked modalities, shared weights
             for m in range(2):
+                wait(m)
                 self._embed(self.bbs[0], B, t[m], ot[m], s[m], x[m * M1:(m + 1) * M1])
             f = self._run_backbone(self.bbs[0], x, 2 * B, ("bb", B), True)
             sv, si = f[: B * self.Ls0], f[B * self.Ls0:]

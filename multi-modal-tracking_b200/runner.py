@@ -45,8 +45,9 @@ class FrameStep:
 
     step(template, online_template, search) takes CPU tensors (RGB-only) or [v, i] lists of CPU tensors (RGB-T)
     shaped like the model's forward arguments, stages them through pinned memory when they are not already
-    pinned, copies them to the device on the current stream, runs the model and returns the [B, 4] cxcywh boxes
-    as a pinned CPU tensor after synchronising.  Nothing is cached between steps.
+    pinned, copies them to the device, runs the model and returns the [B, 4] cxcywh boxes as a pinned CPU tensor
+    after synchronising.  Nothing is cached between steps.  For RGB-T models the copies run on a side stream, one
+    event per modality, so that the thermal crops travel while the RGB stream is already being embedded.
     """
 
     def __init__(self, model, device=None):
@@ -59,6 +60,8 @@ class FrameStep:
         self._out = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._events = [torch.cuda.Event(), torch.cuda.Event()]
 
     def _to_device(self, key, t: torch.Tensor) -> torch.Tensor:
         if t.is_cuda:
@@ -80,14 +83,22 @@ class FrameStep:
 
     def step(self, template, online_template, search) -> torch.Tensor:
         self.h2d_bytes = self.d2h_bytes = 0
-        args = []
-        for name, a in (("t", template), ("ot", online_template), ("s", search)):
-            if isinstance(a, (list, tuple)):
-                args.append([self._to_device((name, m), x) for m, x in enumerate(a)])
-            else:
-                args.append(self._to_device((name, 0), a))
+        rgbt = isinstance(search, (list, tuple))
         with torch.cuda.device(self.device):
-            out, coords = self.model(*args)
+            if rgbt:
+                cur = torch.cuda.current_stream()
+                self._copy_stream.wait_stream(cur)         # the device buffers are free again (previous step is done)
+                args = ([None, None], [None, None], [None, None])
+                with torch.cuda.stream(self._copy_stream):
+                    for m in range(2):
+                        for k, (name, a) in enumerate((("t", template), ("ot", online_template), ("s", search))):
+                            args[k][m] = self._to_device((name, m), a[m])
+                        self._events[m].record(self._copy_stream)
+                out, coords = self.model(*args, ready_events=self._events)
+            else:
+                args = [self._to_device((name, 0), a) for name, a in
+                        (("t", template), ("ot", online_template), ("s", search))]
+                out, coords = self.model(*args)
             boxes = coords.view(-1, 4)
             if self._out is None or self._out.shape != boxes.shape:
                 self._out = torch.empty(boxes.shape, dtype=torch.float32).pin_memory()
