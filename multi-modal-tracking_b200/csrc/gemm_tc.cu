@@ -294,10 +294,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (!full) return;
         if (ep.bias) {
           if (ep.out_fp32) bv[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + cc_f);
-          else {
-            bv[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + 2 * cc_h);
-            bv[1] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + 2 * cc_h + 1);
-          }
         }
         if (ep.resid) {
 #pragma unroll
@@ -309,6 +305,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       };
       prefetch(half);
+      // bf16 outputs: bias/activation happen BEFORE the transpose (thread == row) so that the staging tile holds
+      // packed bf16 - half the shared-memory traffic of an fp32 tile, and shared-memory wavefronts (epilogue staging
+      // + TMA fills) are what bounds this kernel (profiles/r1_gemm_bound.md).  thread == row needs every bias value
+      // of a chunk, so the warp's bias slices (<= 4 chunks x CH floats) are parked in the upper part of its staging
+      // area once per tile and read back as broadcast vectors.
+      constexpr int MAXC = (NCH + 1) / 2;           // chunks per warp
+      float* bias_s = reinterpret_cast<float*>(stg4) + 32 * 16;   // after the 32 x 64 B bf16 staging rows
+      const bool bias_smem = !ep.out_fp32 && ep.vec_ok && ep.bias != nullptr;
+      if (bias_smem) {
+        __syncwarp();
+        if (lane < MAXC * (CH / 4)) {
+          const int k = lane / (CH / 4), vq = lane % (CH / 4);
+          const int nbk = n0 + (half + 2 * k) * CH;
+          float4 bvv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (half + 2 * k < NCH && nbk + CH <= N) bvv = __ldg(reinterpret_cast<const float4*>(ep.bias + nbk) + vq);
+          reinterpret_cast<float4*>(bias_s)[lane] = bvv;
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -326,13 +341,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int nb = n0 + c * CH;
         if (nb >= N) continue;
         const bool full = ep.vec_ok && (nb + CH <= N);
-        if (full) {
-          // ---- 1. stage raw accumulators: row `lane`, vector j at slot j ^ key(lane)
+        if (full && ep.out_fp32) {
+          // ---- fp32 output: stage raw accumulators (row `lane`, vector j at slot j ^ key(lane)), finish transposed
 #pragma unroll
           for (int j = 0; j < VPR; ++j)
             stg4[lane * VPR + (j ^ key_of(lane))] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
-          if (ep.out_fp32) {
+          {
             float* obase = reinterpret_cast<float*>(ep.out) + nb;
 #pragma unroll
             for (int it = 0; it < IT_F; ++it) {
@@ -359,38 +374,57 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 reinterpret_cast<float4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_f] = o;
               }
             }
-          } else {
-            bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb;
+          }
+          __syncwarp();
+        } else if (full) {
+          // ---- bf16 output: bias + activation (+ positional add) with thread == row, pack, stage bf16, store transposed
+          const int kc = (c - half) >> 1;                      // this warp's chunk slot -> its bias slice
+          float f[CH];
 #pragma unroll
-            for (int it = 0; it < IT_H; ++it) {
-              const int r = it * (32 / LPR_H) + rr_h;
-              const int grow = grow_of(lrow0 + r);
-              const uint4 w0 = stg4[r * VPR + ((2 * cc_h) ^ key_of(r))];
-              const uint4 w1 = stg4[r * VPR + ((2 * cc_h + 1) ^ key_of(r))];
-              float x[8] = {__uint_as_float(w0.x) + b0.x, __uint_as_float(w0.y) + b0.y, __uint_as_float(w0.z) + b0.z,
-                            __uint_as_float(w0.w) + b0.w, __uint_as_float(w1.x) + b1.x, __uint_as_float(w1.y) + b1.y,
-                            __uint_as_float(w1.z) + b1.z, __uint_as_float(w1.w) + b1.w};
-              if (ep.act == MMT_ACT_GELU) {
+          for (int j = 0; j < CH; ++j) f[j] = __uint_as_float(v[j]);
+          if (ep.bias) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = gelu_fast(x[k]);
-              } else if (ep.act == MMT_ACT_RELU) {
+            for (int j = 0; j < CH; j += 4) {
+              const float4 b = reinterpret_cast<const float4*>(bias_s + kc * CH)[j >> 2];   // broadcast read
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+          if (ep.act == MMT_ACT_GELU) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = fmaxf(x[k], 0.f);
-              }
-              if (grow >= 0) {
-                if (ep.rowadd) {
-                  const float4* pr = reinterpret_cast<const float4*>(
-                      ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb) + 2 * cc_h;
-                  const float4 p0 = __ldg(pr), p1 = __ldg(pr + 1);
-                  x[0] += p0.x; x[1] += p0.y; x[2] += p0.z; x[3] += p0.w;
-                  x[4] += p1.x; x[5] += p1.y; x[6] += p1.z; x[7] += p1.w;
-                }
-                uint4 o;
-                o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-                o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-                reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_h] = o;
+            for (int j = 0; j < CH; ++j) f[j] = gelu_fast(f[j]);
+          } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (ep.rowadd) {
+            const int grow = grow_of(lrow0 + lane);
+            if (grow >= 0) {
+              const float4* pr = reinterpret_cast<const float4*>(
+                  ep.rowadd + static_cast<size_t>(grow % ep.rowadd_period) * N + nb);
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 p = __ldg(pr + (j >> 2));
+                f[j] += p.x; f[j + 1] += p.y; f[j + 2] += p.z; f[j + 3] += p.w;
               }
             }
+          }
+          // staging rows are CH * 2 bytes = LPR_H 16-byte vectors; vector j of row `lane` at slot j ^ key
+          constexpr int KD_H = 8 / LPR_H;
+#pragma unroll
+          for (int j = 0; j < LPR_H; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            stg4[lane * LPR_H + (j ^ ((lane / KD_H) & (LPR_H - 1)))] = w;
+          }
+          __syncwarp();
+          bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb;
+#pragma unroll
+          for (int it = 0; it < IT_H; ++it) {
+            const int r = it * (32 / LPR_H) + rr_h;
+            const int grow = grow_of(lrow0 + r);
+            const uint4 w = stg4[r * LPR_H + (cc_h ^ ((r / KD_H) & (LPR_H - 1)))];
+            if (grow >= 0) reinterpret_cast<uint4*>(obase + static_cast<size_t>(grow) * ep.ldo)[cc_h] = w;
           }
           __syncwarp();
         } else if (grow_of(lrow0 + lane) >= 0) {
