@@ -390,6 +390,20 @@ class _EngineModule(nn.Module):
             raise NotImplementedError("mmt_b200 provides the inference forward only (training is out of scope)")
         return super().train(False)
 
+    # Template-side reuse (an extension, not a reference API): the trackers re-send
+    # unchanged templates with every frame (lib/test/tracker/mixformer_vit.py:71); cache_templates() once per template
+    # update + forward_search() per frame give the same boxes as forward() for 72 % of the token rows.
+    @torch.no_grad()
+    def cache_templates(self, template, online_template):
+        sq = lambda t: t.squeeze(0) if (torch.is_tensor(t) and t.dim() == 5) else t
+        self.engine().cache_templates(sq(template), sq(online_template))
+
+    @torch.no_grad()
+    def forward_search(self, search):
+        sq = lambda t: t.squeeze(0) if (torch.is_tensor(t) and t.dim() == 5) else t
+        res = self.engine().forward_search(sq(search))
+        return {"pred_boxes": res["pred_boxes"]}, res["pred_boxes"]
+
     def _finish(self, res, return_features=False):
         coords = res["pred_boxes"]
         out_dict = {"pred_boxes": coords}

@@ -507,6 +507,114 @@ class ForwardEngine:
         res = dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=fused, search_rows=(sv, si), **self.aux)
         return res
 
+    # ------------------------------------------------------------------------------------------ template-side reuse
+    # in every variant template rows attend template keys only, so the templates'
+    # per-layer q/k/v do not depend on the search crop and are identical from one template update to the next.
+    # cache_templates() runs the template tokens once and keeps every layer's packed qkv; forward_search() then runs
+    # the search tokens only, reading the cached rows as a second key/value source (tile records with k_buf = 1).
+    # Symmetric variants (template/search interaction only through the search rows' keys): results are bit-identical
+    # to forward() - same GEMM K-order per row, same key-block boundaries in the attention kernels.
+    def _seq_tiles(self, kind, nseq, rows_per_seq, key_segs_fn):
+        key = (kind, nseq, rows_per_seq)
+        hit = self._tiles.get(key)
+        if hit is None:
+            recs, max_keys = [], 0
+            for sq in range(nseq):
+                segs = key_segs_fn(sq)
+                max_keys = max(max_keys, sum(sg[2] for sg in segs))
+                pad = segs + [(0, 0, 0)] * (3 - len(segs))
+                for o in range(0, rows_per_seq, 128):
+                    q0 = sq * rows_per_seq + o
+                    recs.append([q0, min(128, rows_per_seq - o), q0, len(segs)] + [sg[1] for sg in pad] +
+                                [sg[2] for sg in pad] + [sg[0] for sg in pad] + [0, 0, 0])
+            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), max_keys)
+            self._tiles[key] = hit
+        return hit
+
+    def _check_cacheable(self):
+        if self.variant in CROSS_MODAL or self.ce_loc:
+            raise NotImplementedError("template caching is implemented for the symmetric variants (mixformer_vit, "
+                                      "mixformer_vit_rgbt, _shared, _unibackbone)")
+
+    def cache_templates(self, template, online_template):
+        self._check_cacheable()
+        Lt, T = self.Lt, self.gt * self.gt
+        if not self.rgbt:
+            groups = [(self.bbs[0], [self._check_img(template, self.template_size)],
+                       [self._check_img(online_template, self.template_size)], False)]
+        else:
+            t = [self._check_img(v, self.template_size) for v in template]
+            ot = [self._check_img(v, self.template_size) for v in online_template]
+            if self.variant == "mixformer_vit_rgbt":
+                groups = [(self.bbs[m], [t[m]], [ot[m]], False) for m in range(2)]
+            else:
+                groups = [(self.bbs[0], t, ot, self.variant in PER_MODALITY_LN)]
+        self._tcache = []
+        for gi, (bb, ts, ots, per_ln) in enumerate(groups):
+            B = ts[0].shape[0]
+            nseq = B * len(ts)
+            tag = ("tcache", B, gi)
+            x = self._buf(tag, "x", (nseq * Lt, self.dim), torch.float32)
+            buf = self._embed_buf(nseq * Lt)
+            for m in range(len(ts)):
+                sub = buf[m * B * Lt:(m + 1) * B * Lt]
+                self._stage_tokens(bb, ts[m], sub, 0, Lt)
+                self._stage_tokens(bb, ots[m], sub, T, Lt)
+            pos_tt = self._ws.get("pos_tt")
+            if pos_tt is None:
+                pos_tt = bb["pos"][:Lt].contiguous()
+                self._ws["pos_tt"] = pos_tt
+                self._ws["pos_ss"] = bb["pos"][Lt:].contiguous()
+            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, pos_tt, out=x)
+            tiles = self._seq_tiles("tcache", nseq, Lt, lambda sq: [(0, sq * Lt, Lt)])
+            cache = [self._buf(tag, f"qkv{i}", (nseq * Lt, 3 * self.dim), self.act) for i in range(self.depth)]
+            for i, blk in enumerate(bb["blocks"]):
+                self._block(blk, x, nseq, Lt, 0, (nseq * Lt // 2) if per_ln else 0, False, tag, tiles=tiles,
+                            qkv_out=cache[i])
+            self._tcache.append((cache, nseq, B))
+
+    def forward_search(self, search, want_maps=True):
+        """The per-frame forward of forward() for the search crops alone, against cache_templates()' cache."""
+        self._check_cacheable()
+        if getattr(self, "_tcache", None) is None:
+            raise RuntimeError("forward_search called before cache_templates")
+        self.aux = {}
+        Lt, Ls = self.Lt, self.Ls0
+        ss = [self._check_img(search, self.search_size)] if not self.rgbt else \
+            [self._check_img(v, self.search_size) for v in search]
+        B = ss[0].shape[0]
+        if self.variant == "mixformer_vit_rgbt":
+            groups = [(self.bbs[m], [ss[m]], False) for m in range(2)]
+        else:
+            groups = [(self.bbs[0], ss, self.variant in PER_MODALITY_LN)]
+        feats = []
+        for gi, (bb, imgs, per_ln) in enumerate(groups):
+            cache, nseq_c, Bc = self._tcache[gi]
+            nseq = B * len(imgs)
+            if nseq != nseq_c:
+                raise RuntimeError(f"cached templates are for {Bc} sequences, got {B} search crops")
+            tag = ("scache", B, gi)
+            x = self._buf(tag, "x", (nseq * Ls, self.dim), torch.float32)
+            buf = self._embed_buf(nseq * Ls)
+            for m in range(len(imgs)):
+                self._stage_tokens(bb, imgs[m], buf[m * B * Ls:(m + 1) * B * Ls], 0, Ls)
+            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_ss"], out=x)
+            tiles = self._seq_tiles("scache", nseq, Ls, lambda sq: [(1, sq * Lt, Lt), (0, sq * Ls, Ls)])
+            for i, blk in enumerate(bb["blocks"]):
+                self._block(blk, x, nseq, Ls, 0, (nseq * Ls // 2) if per_ln else 0, False, tag, tiles=tiles,
+                            qkv1=cache[i])
+            feats.append(ops.copy_rows(x, Ls, 0, Ls, nseq, self._buf(tag, "search_rows", (nseq * Ls, self.dim), self.act)))
+        if not self.rgbt:
+            boxes, maps = self._run_head(feats[0], B, want_maps)
+            return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feats[0])
+        if len(feats) == 2:
+            sv, si = feats
+        else:
+            sv, si = feats[0][: B * Ls], feats[0][B * Ls:]
+        fused = self._run_fusion(sv, si, B)
+        boxes, maps = self._run_head(fused, B, want_maps)
+        return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=fused, search_rows=(sv, si))
+
     def forward_head_only(self, search_feat):
         """Corner head on an NCHW feature map (forward_box_head, mixformer.py:325-338)."""
         B, C, H, W = search_feat.shape

@@ -245,3 +245,34 @@ def test_online_score_model_large(built_lib, ONLINE, precision):
         assert max(d["box"], d["obox"]) <= 1e-4 * size and max(d["score"], d["oscore"]) <= 1e-4
     else:
         assert max(d["box"], d["obox"]) <= 0.5 and max(d["score"], d["oscore"]) <= 1e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("variant", ["mixformer_vit", "mixformer_vit_rgbt", "mixformer_vit_rgbt_shared",
+                                     "mixformer_vit_rgbt_unibackbone"])
+def test_template_cache_is_bit_identical(built_lib, variant, precision):
+    """cache_templates() + forward_search() (search tokens only, cached template q/k/v as a second key source) must
+    reproduce forward() bit for bit in the symmetric variants: idempotence of the template side."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(variant, 0)
+    model = model.cuda().set_precision(precision)
+    t, ot, s = synthetic.make_inputs(variant, cfg, 3, 5, device="cuda")
+    _, full = model(t, ot, s)
+    model.cache_templates(t, ot)
+    _, cached = model.forward_search(s)
+    t2, ot2, s2 = synthetic.make_inputs(variant, cfg, 3, 6, device="cuda")      # new frame, same templates
+    _, full2 = model(t, ot, s2)
+    _, cached2 = model.forward_search(s2)
+    torch.cuda.synchronize()
+    assert torch.equal(full, cached) and torch.equal(full2, cached2)
+    with pytest.raises(RuntimeError):
+        model.forward_search([x[:2] for x in s] if isinstance(s, list) else s[:2])      # batch differs from the cache
+
+
+def test_template_cache_refused_for_cross_modal(built_lib):
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model("asymmetric_shared_ce", 0)
+    model = model.cuda()
+    t, ot, s = synthetic.make_inputs("asymmetric_shared_ce", cfg, 1, 5, device="cuda")
+    with pytest.raises(NotImplementedError):
+        model.cache_templates(t, ot)
