@@ -40,13 +40,28 @@ class LaunchProfiler:
         self.spans.setdefault(name, []).append((start, e, flops))
 
     def summary(self, name="gemm_bf16"):
-        """(launches, total_ms, total_flops) of one class; call after a device synchronise."""
-        sp = self.spans.get(name, [])
+        """(launches, total_ms, total_flops) of one class (a prefix selects several, e.g. "gemm_bf16" = pair + single +
+        conv3x3 instantiations); call after a device synchronise."""
+        sp = [x for k, v in self.spans.items() if k.startswith(name) for x in v]
         ms = sum(a.elapsed_time(b) for a, b, _ in sp)
         return len(sp), ms, float(sum(f for _, _, f in sp))
 
     def table(self):
         return {k: dict(zip(("launches", "ms", "flops"), self.summary(k))) for k in self.spans}
+
+
+_PAIR_MIN = None
+
+
+def _pair_min_tiles():
+    global _PAIR_MIN
+    if _PAIR_MIN is None:
+        import os
+        if os.environ.get("MMT_GEMM_PAIR", "1") == "0":
+            _PAIR_MIN = 1 << 60
+        else:
+            _PAIR_MIN = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
+    return _PAIR_MIN
 
 
 def _begin():
@@ -115,7 +130,9 @@ def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_d
                         _stream())
         _lib.check(st, "mmt_gemm_bf16")
         if ev is not None:
-            prof.end(ev, 2.0 * M * N * K)
+            # same dispatch rule as gemm_tc.cu::dispatch_gemm: the CTA-pair kernel takes the big N % 256 == 0 GEMMs
+            pair = max_ctas <= 0 and N % 256 == 0 and ((M + 255) // 256) * (N // 256) >= _pair_min_tiles()
+            prof.end(ev, 2.0 * M * N * K, "gemm_bf16_pair" if pair else "gemm_bf16_single")
     else:
         assert a.dtype == torch.float32 and out.dtype == torch.float32
         st = _gemm_f32(_ptr(a), c_int(a.stride(0)), _ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
@@ -243,7 +260,7 @@ def conv3x3(src, B, H, W, C, w, bias, act, out):
                         c_int(1 if out.dtype == torch.float32 else 0), _stream()), "mmt_conv3x3_bf16")
     _count()
     if ev is not None:
-        prof.end(ev, 2.0 * B * H * W * N * 9 * C)
+        prof.end(ev, 2.0 * B * H * W * N * 9 * C, "gemm_bf16_conv3x3")
     return out
 
 
