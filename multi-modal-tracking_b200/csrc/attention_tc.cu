@@ -14,11 +14,13 @@
 //   warp 1     MMA issuer   : S = Q K^T  (tcgen05.mma M128 N128 K16 x4, both operands K-major smem) into TMEM;
 //              O += P V with A = P read from TENSOR MEMORY and B = the V boxes in smem, MN-major (the probabilities
 //              never touch shared memory: operand reads from smem, not the MMA rate, bound an SS-mode PV here).
-//   warps 2-9  softmax      : two threads per query row (one 64-key box of the super-block each).  EXACT two-pass
-//              softmax: pass 1 reads every S block for the row maximum; pass 2 recomputes S (tensor time is cheap
-//              here), forms p = exp2((s - max) * scale * log2 e), accumulates the row sum and writes P as packed
-//              bf16 into TMEM with tcgen05.st (the A operand of the PV MMA) - O never needs rescaling.
-//              Epilogue: O * (1 / row sum) -> bf16 -> out.
+//   warps 2-9  softmax      : two threads per query row (one 64-key box of the super-block each).  Online softmax
+//              in ONE pass over the keys with a LAZY running maximum: p = exp2((s - m) * scale * log2 e) is formed
+//              against the current m; m (and with it O and the row sum, by exp2((m_old - m_new) ...)) is only moved
+//              when a block's maximum exceeds it by more than 2^8 - p stays <= 256, exactly representable headroom
+//              for bf16 P and the fp32 accumulators, and the O / row-sum ratio is unchanged.  P is written as packed
+//              bf16 into TMEM with tcgen05.st (the A operand of the PV MMA); the rare O rescale is a TMEM
+//              load-scale-store by the same threads between two PV MMAs.  Epilogue: O * (1 / row sum) -> bf16 -> out.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "../../include/mmt_b200.h"
@@ -44,7 +46,7 @@ constexpr int ATC_STAGES = 4;
 constexpr int ATC_BLK_BYTES = ATC_KB * ATC_HD * 2;  // 8 KB
 constexpr int ATC_Q_BYTES = 128 * ATC_HD * 2;       // 16 KB
 constexpr int ATC_THREADS = 320;
-constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 1280;
+constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 256 + 2048;
 constexpr uint32_t ATC_TMEM_COLS = 256;             // O: [0,64)  S: [64,192)  P: [192,256) (128 keys, bf16x2 per column)
 
 // kind::f16 instruction descriptor with B taken MN-major (bit 16): V blocks are [key][d] with d contiguous.
@@ -103,7 +105,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * ATC_STAGES + 10);
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
-  float* smax = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2][128] partial row maxima
+  float* smax = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2 parities][2 halves][128]
 
   const AttnTileTC t = tiles[blockIdx.x];
   const int h = blockIdx.y;
@@ -171,11 +173,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         tma_load_2d(ring_smem + stage * ATC_BLK_BYTES, buf ? &tm1 : &tm0, kv_full(stage), col, row0);
         if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
       };
-      for (int sb = 0; sb < nsb; ++sb) {                                      // pass 1: K only
-        load_blk(2 * sb, C + h * ATC_HD);
-        load_blk(2 * sb + 1, C + h * ATC_HD);
-      }
-      for (int sb = 0; sb <= nsb; ++sb) {                                     // pass 2: K_sb, then V_(sb-1)
+      for (int sb = 0; sb <= nsb; ++sb) {                                     // K_sb, then V_(sb-1)
         if (sb < nsb) { load_blk(2 * sb, C + h * ATC_HD); load_blk(2 * sb + 1, C + h * ATC_HD); }
         if (sb >= 1) { load_blk(2 * sb - 2, 2 * C + h * ATC_HD); load_blk(2 * sb - 1, 2 * C + h * ATC_HD); }
       }
@@ -210,9 +208,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         mma_commit(s_full);
         release_pair();
       };
-      for (int sb = 0; sb < nsb; ++sb) issue_s(sb);
       for (int sb = 0; sb <= nsb; ++sb) {
-        if (sb < nsb) issue_s(nsb + sb);
+        if (sb < nsb) issue_s(sb);
         if (sb >= 1) {
           const int j = sb - 1;
           mbar_wait(p_full, j & 1u);
@@ -233,8 +230,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const int half = (warp - 2) >> 2;               // which 32 of a block's 64 keys this thread handles
     const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m_row = -INFINITY;
-    // pass 1: row maximum of the raw scores (this thread: box `half` of every super-block)
+    float m_row = -INFINITY;      // lazy running maximum (raw score units)
+    float mc = 0.f;               // m_row * scale_log2e
+    float l_row = 0.f;            // this thread's part of the row sum
     auto row_max = [&](const uint32_t (&v)[32], int lim0, float m) {
       if (lim0 >= 32) {
 #pragma unroll
@@ -246,29 +244,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       }
       return m;
     };
-    const uint32_t s_addr = tmem_s + lane_off + 64u * half;
-    for (int g = 0; g < nsb; ++g) {
-      int row0, len, buf;
-      locate(2 * g + half, row0, len, buf);
-      mbar_wait(s_full, g & 1u);
-      if (g == 0) stamp(2);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(s_addr, v0);
-      tmem_ld_32x32(s_addr + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      m_row = row_max(v0, len, m_row);
-      m_row = row_max(v1, len - 32, m_row);
-    }
-    stamp(3);
-    smax[half * 128 + r] = m_row;
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
-    m_row = fmaxf(m_row, smax[(half ^ 1) * 128 + r]);
-    const float mc = m_row * scale_log2e;
-    float l_row = 0.f;
     // in place: word i of v becomes the packed pair (p[2i], p[2i+1]) - keeps the live register set at 64
     auto probs = [&](uint32_t (&v)[32], int lim0) {
       uint32_t* pk = v;
@@ -299,12 +274,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     // a warp whose 32 query rows all lie beyond the tile's q_rows computes nothing (it still takes part in the
     // barrier protocol and writes zero probabilities)
     const bool warp_live = quad * 32 < t.q_rows;
-    // pass 2: probabilities -> TMEM (A operand of the PV MMAs); thread `half` fills columns [32 half, 32 half + 32)
+    const uint32_t s_addr = tmem_s + lane_off + 64u * half;
+    const uint32_t o_addr = tmem_o + lane_off + 32u * half;
     for (int j = 0; j < nsb; ++j) {
-      const int g = nsb + j;
       int row0, len, buf;
       locate(2 * j + half, row0, len, buf);
-      mbar_wait(s_full, g & 1u);
+      mbar_wait(s_full, j & 1u);
+      if (j == 0) stamp(2);
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(s_addr, v0);
@@ -313,10 +289,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
+      // block maximum of the row: this thread's 64 keys, then the partner thread's through shared memory
+      float bm = row_max(v0, len, -INFINITY);
+      bm = row_max(v1, len - 32, bm);
+      float* ex = smax + (j & 1) * 256;
+      ex[half * 128 + r] = bm;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
+      bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
+      // lazy maximum: move m only when the block exceeds it by more than 2^8 (always on the first block: m = -inf)
+      float factor = 1.f;
+      bool moved = false;
+      if ((bm - m_row) * scale_log2e > 8.f) {
+        factor = ex2_approx((m_row - bm) * scale_log2e);   // 0 on the first block
+        m_row = bm;
+        mc = m_row * scale_log2e;
+        l_row *= factor;
+        moved = warp_live;
+      }
       // this thread's 64 keys: key 2c (low half) and 2c+1 (high half) in packed word c
       probs(v0, warp_live ? len : 0);
-      mbar_wait(p_empty, (j & 1u) ^ 1u);          // the PV MMAs of the previous super-block have read P
+      mbar_wait(p_empty, (j & 1u) ^ 1u);          // the PV MMAs of the previous super-block have completed
       tc_fence_after();
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {
+        // rescale this thread's 32 columns of the O row by its own factor (1 for rows that did not move)
+        uint32_t o[32];
+        tmem_ld_32x32(o_addr, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+        tmem_st_32x32(o_addr, o);
+      }
       tmem_st_32x16(tmem_p + lane_off + 32u * half, v0);
       probs(v1, warp_live ? len - 32 : 0);
       tmem_st_32x16(tmem_p + lane_off + 32u * half + 16u, v1);
@@ -324,6 +326,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (j == 0) stamp(3);
     }
     // epilogue: O / L -> bf16 -> out (this thread: 32 of the 64 head channels)
     stamp(4);
@@ -332,9 +335,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     tc_fence_after();
     uint32_t o[32];
     tmem_ld_32x32(tmem_o + lane_off + 32u * half, o);
-    smax[half * 128 + r] = l_row;                    // (the maxima were consumed before the previous bar.sync)
+    float* exl = smax + (nsb & 1) * 256;             // the parity the last block did not use
+    exl[half * 128 + r] = l_row;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    l_row += smax[(half ^ 1) * 128 + r];
+    l_row += exl[(half ^ 1) * 128 + r];
     tmem_ld_wait();
     if (r < t.q_rows) {
       const float inv = 1.f / l_row;

@@ -95,3 +95,24 @@ def test_mixattn_peaked_rows(built_lib):
     ref = _reference(qkv, segs, HD ** -0.5)
     assert bool(torch.isfinite(out.float()).all())
     assert (out.float() - ref).abs().max().item() <= 4e-2
+
+
+def test_mixattn_growing_maxima(built_lib):
+    """Scores that keep growing along the key axis force the lazy running maximum of the single-pass softmax to move
+    (and the O accumulator in TMEM to be rescaled) in every key block."""
+    from mmt_b200 import ops
+    nseq, Lt, Ls = 2, 128, 324
+    N = Lt + Ls
+    g = torch.Generator(device="cuda").manual_seed(21)
+    qkv = torch.randn(nseq * N, 3 * C, device="cuda", generator=g)
+    ramp = (torch.arange(nseq * N, device="cuda") % N).float() / N            # 0..1 along each sequence's tokens
+    qkv[:, :C] = qkv[:, :C].abs() * 1.5                                       # positive queries
+    qkv[:, C:2 * C] = qkv[:, C:2 * C].abs() * (0.2 + 4.0 * ramp[:, None])     # keys grow with the position
+    qkv = qkv.to(torch.bfloat16)
+    tiles, segs = _tiles(nseq, N, Lt, Ls, False)
+    out = torch.empty((nseq * N, C), device="cuda", dtype=torch.bfloat16)
+    ops.mixattn(qkv, None, C, HEADS, tiles.cuda(), N, out, HD ** -0.5)
+    torch.cuda.synchronize()
+    ref = _reference(qkv, segs, HD ** -0.5)
+    assert bool(torch.isfinite(out.float()).all())
+    assert (out.float() - ref).abs().max().item() <= 4e-2
