@@ -197,6 +197,9 @@ int mmt_ce_gather_tokens(const float* x, int nseq, int n_tok, int Lt, const int*
 int mmt_ce_recover(const float* x, int nseq, int n_tok, int Lt, const float* gidx, int Lk, int Ls0, void* out, int C,
                    int out_bf16, void* stream);
 
+/* out[r, :C] = a[r], out[r, C:] = b[r]: channel concatenation of two NHWC maps (RGBT_Fusion_Cat, fusion_utils.py:106). */
+int mmt_concat_cols(const void* a, const void* b, int rows, int C, void* out, int is_bf16, void* stream);
+
 /* rois[b] = (b, xyxy[b] * scale), fp32 [B,5]: the SPM's target_roi (score_decoder.py:37-44). */
 int mmt_spm_rois(const float* xyxy, int B, float scale, float* rois, void* stream);
 

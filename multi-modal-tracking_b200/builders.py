@@ -239,29 +239,35 @@ class _MSDeformAttnBimodal(nn.Module):
 
 
 class _FusionEncoderLayer(nn.Module):
-    def __init__(self, d_model, d_ffn):
+    def __init__(self, d_model, d_ffn, ln_specific=True):
         super().__init__()
         self.self_attn = _MSDeformAttnBimodal(d_model)
-        self.norm1_v, self.norm1_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        if ln_specific:
+            self.norm1_v, self.norm1_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        else:           # DeformableTransformerEncoderLayer deformable_encoder.py:111-137: one norm for both modalities
+            self.norm1 = nn.LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
         self.linear2 = nn.Linear(d_ffn, d_model)
-        self.norm2_v, self.norm2_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        if ln_specific:
+            self.norm2_v, self.norm2_i = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        else:
+            self.norm2 = nn.LayerNorm(d_model)
         nn.init.xavier_uniform_(self.linear1.weight)
         nn.init.xavier_uniform_(self.linear2.weight)
 
 
 class _FusionEncoder(nn.Module):
-    def __init__(self, d_model, layers):
+    def __init__(self, d_model, layers, ln_specific=True):
         super().__init__()
-        self.layers = nn.ModuleList([_FusionEncoderLayer(d_model, 4 * d_model) for _ in range(layers)])
+        self.layers = nn.ModuleList([_FusionEncoderLayer(d_model, 4 * d_model, ln_specific) for _ in range(layers)])
 
 
 class _FusionAttention(nn.Module):
     """Parameter layout of DeformableAttentionFusion_LNSpecific (deformable_encoder_lnspecific.py:23-57)."""
 
-    def __init__(self, d_model, layers):
+    def __init__(self, d_model, layers, ln_specific=True):
         super().__init__()
-        self.encoder = _FusionEncoder(d_model, layers)
+        self.encoder = _FusionEncoder(d_model, layers, ln_specific)
         self.level_embed = nn.Parameter(torch.randn(2, d_model))
 
 
@@ -270,7 +276,19 @@ def _conv_gn(inp, out):
 
 
 FUSION_CLASSES = ("Attention_Fusion_Bimodal_LNSpecific", "Attention_Fusion_Bimodal_LNSpecific_Sum",
-                  "Attention_Fusion_Bimodal_LNSpecific_2")
+                  "Attention_Fusion_Bimodal_LNSpecific_2", "Attention_Fusion_Bimodal", "RGBT_Fusion_Cat")
+
+
+class _FusionCat(nn.Module):
+    """Parameter layout of RGBT_Fusion_Cat (fusion_utils.py:86-110): three bias-free 3x3 convs + BatchNorm + ReLU on
+    the channel concatenation of the two modalities."""
+
+    def __init__(self, channels=768):
+        super().__init__()
+        self.fusion_class = "RGBT_Fusion_Cat"
+        for j, (i, o) in enumerate(((2 * channels, 2 * channels), (2 * channels, channels), (channels, channels)), 1):
+            setattr(self, f"fusion{j}", nn.Conv2d(i, o, kernel_size=3, stride=1, padding=1, bias=False))
+            setattr(self, f"fusion{j}_bn", nn.BatchNorm2d(o))
 
 
 class _Fusion(nn.Module):
@@ -286,7 +304,7 @@ class _Fusion(nn.Module):
         else:
             self.adjust_v = _conv_gn(channels, d_model)
             self.adjust_i = _conv_gn(channels, d_model)
-        self.fusion_attention = _FusionAttention(d_model, layers)
+        self.fusion_attention = _FusionAttention(d_model, layers, ln_specific="LNSpecific" in fusion_class)
         if fusion_class.endswith("_Sum"):
             self.adjust_sum = _conv_gn(d_model, channels)
         elif fusion_class.endswith("_2"):
@@ -541,6 +559,8 @@ def build_mixformer_vit(cfg, train=False) -> MixFormer:
 
 
 def _fusion(cfg):
+    if cfg.MODEL.FUSION_CLASS == "RGBT_Fusion_Cat":
+        return _FusionCat(768)
     return _Fusion(cfg.MODEL.FUSION_CLASS, 768, 512, cfg.MODEL.FUSION_LAYERS)
 
 

@@ -411,6 +411,21 @@ __global__ void xyxy_to_cxcywh_kernel(const float* __restrict__ xyxy, float* __r
   out[b * 4 + 3] = y1 - y0;
 }
 
+// out[r, :C] = a[r, :], out[r, C:2C] = b[r, :]  (torch.cat([v, i], dim=1) of two NHWC maps, fusion_utils.py:106), T rows.
+template <typename T>
+__global__ void concat_cols_kernel(const T* __restrict__ a, const T* __restrict__ b, int rows, int C, T* __restrict__ out) {
+  constexpr int VE = 16 / sizeof(T);
+  const int nv = C / VE;
+  const size_t total = static_cast<size_t>(rows) * 2 * nv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = i % (2 * nv);
+    const size_t r = i / (2 * nv);
+    const T* src = cv < nv ? a + r * C + cv * VE : b + r * C + (cv - nv) * VE;
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(src);
+  }
+}
+
 // rois[b] = (b, xyxy[b] * scale): the target_roi tensor of the SPM (lib/models/mixformer_cvt/score_decoder.py:37-44:
 // normalised box * feature width, batch index = arange(B)).
 __global__ void spm_rois_kernel(const float* __restrict__ xyxy, int B, float scale, float* __restrict__ rois) {
@@ -510,6 +525,15 @@ extern "C" int mmt_im2col3x3(const void* src1, int ld1, int s1, const void* src2
     im2col3x3_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(src1), ld1, s1, reinterpret_cast<const bf16*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<bf16*>(out));
   else
     im2col3x3_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src1), ld1, s1, reinterpret_cast<const float*>(src2), ld2, s2, B, H, W, C, reinterpret_cast<float*>(out));
+  MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_concat_cols(const void* a, const void* b, int rows, int C, void* out, int is_bf16, void* stream) {
+  MMT_CHECK_ARG(a && b && out && rows > 0 && C > 0 && C % (is_bf16 ? 8 : 4) == 0);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = static_cast<size_t>(rows) * 2 * (C / (is_bf16 ? 8 : 4));
+  if (is_bf16) concat_cols_kernel<bf16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), rows, C, reinterpret_cast<bf16*>(out));
+  else concat_cols_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), rows, C, reinterpret_cast<float*>(out));
   MMT_RETURN_LAST_ERROR();
 }
 

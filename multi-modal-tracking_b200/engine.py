@@ -144,6 +144,15 @@ class ForwardEngine:
         from .builders import FUSION_CLASSES
         if cls not in FUSION_CLASSES:
             raise KeyError(f"FUSION_CLASS {cls!r} is not on the accelerated path")
+        if cls == "RGBT_Fusion_Cat":          # three conv3x3 (no bias) + eval BatchNorm + ReLU, fusion_utils.py:86-110
+            convs = []
+            for j in (1, 2, 3):
+                w = g(f"fusion{j}.weight").detach().float()
+                scale = g(f"fusion{j}_bn.weight").detach().float() * (g(f"fusion{j}_bn.running_var").detach().float() + 1e-5).rsqrt()
+                shift = g(f"fusion{j}_bn.bias").detach().float() - g(f"fusion{j}_bn.running_mean").detach().float() * scale
+                wp = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+                convs.append((self._w(wp), _f32(shift, dev)))
+            return {"cat_convs": convs}
         self.d_model = g("fusion_attention.level_embed").shape[1]
         names_in = ("adjust_in", "adjust_in") if cls.endswith("_2") else ("adjust_v", "adjust_i")
         F["in"] = [dict(w=self._w(g(n + ".0.weight").reshape(self.d_model, -1)), b=_f32(g(n + ".0.bias"), dev),
@@ -162,7 +171,10 @@ class ForwardEngine:
                             ("l2", "linear2")):
                 L[nm + "_w"], L[nm + "_b"] = self._w(g(p + key + ".weight")), _f32(g(p + key + ".bias"), dev)
             for j in (1, 2):
-                L[f"ln{j}"] = tuple(_f32(g(p + f"norm{j}_{mm}.{wb}"), dev) for mm in ("v", "i") for wb in ("weight", "bias"))
+                if ("fusion_vi." + p + f"norm{j}_v.weight") in sd:
+                    L[f"ln{j}"] = tuple(_f32(g(p + f"norm{j}_{mm}.{wb}"), dev) for mm in ("v", "i") for wb in ("weight", "bias"))
+                else:       # Attention_Fusion_Bimodal: one LayerNorm for both modalities (deformable_encoder.py:129,137)
+                    L[f"ln{j}"] = (_f32(g(p + f"norm{j}.weight"), dev), _f32(g(p + f"norm{j}.bias"), dev), None, None)
             layers.append(L)
             i += 1
         F["layers"] = layers
@@ -356,6 +368,14 @@ class ForwardEngine:
     def _run_fusion(self, sv, si, B):
         """fusion_vi (fusion_utils.py:270-279 and variants) on search-token rows sv, si [B*HW, 768] -> [B*HW, 768]."""
         F_ = self.fusion
+        if "cat_convs" in F_:                 # RGBT_Fusion_Cat
+            tag = ("fuscat", B)
+            a = ops.concat_cols(sv, si, self._buf(tag, "cat", (B * self.Ls0, 2 * self.dim), self.act))
+            for j, (w, b) in enumerate(F_["cat_convs"]):
+                o = self._buf(tag, f"o{j}", (B * self.Ls0, w.shape[0]), self.act)
+                self._conv3x3(a, B, self.gs, self.gs, a.shape[1], w, b, o, tag)
+                a = o
+            return a
         HW, d, L = self.Ls0, self.d_model, self.Ls0
         tag = ("fus", B)
         src = self._buf(tag, "src", (B, 2 * HW, d), torch.float32)
@@ -403,7 +423,12 @@ class ForwardEngine:
                 src1, s1, src2, s2 = up
                 src = ops.upsample_add(src1, s1, B, H, W, C, self._buf(tag, f"up{H}", (B * H * W, C), self.act), src2, s2)
             return ops.conv3x3(src, B, H, W, C, w, b, ops.ACT_RELU, out)
-        col = self._buf(tag, "col", (self._colmax,), self.act)[: B * H * W * 9 * C].view(B * H * W, 9 * C)
+        need = B * H * W * 9 * C
+        col = self._ws.get("im2col")
+        if col is None or col.numel() < need:       # one growing im2col buffer (fp32 parity mode only)
+            col = torch.empty((need,), device=self.dev, dtype=self.act)
+            self._ws["im2col"] = col
+        col = col[:need].view(B * H * W, 9 * C)
         if up is not None:
             src1, s1, src2, s2 = up
             ops.im2col3x3(src1, s1, B, H, W, C, col, src2, s2)
@@ -419,7 +444,6 @@ class ForwardEngine:
         C = feat.shape[1]
         tag = ("head", B)
         n18, n36, n72 = B * gs * gs, B * 4 * gs * gs, B * 16 * gs * gs
-        self._colmax = max(n18 * 9 * C, n36 * 9 * (ch // 2), n72 * 9 * (ch // 4))
         s1 = self._buf(tag, "s1", (n18, self.s1_width), self.act)
         self._conv3x3(feat, B, gs, gs, C, H["s1_w"], H["s1_b"], s1, tag)
         sl = lambda n: s1[:, self.s1_cols[n][0]: self.s1_cols[n][1]]

@@ -409,6 +409,20 @@ def dwconv5x5(x, w, bias, B, H, W, out):
     return out
 
 
+_concat_cols = _lib.fn("mmt_concat_cols")
+
+
+def concat_cols(a, b, out):
+    _need_cuda(a, b, out)
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous() and a.shape == b.shape and a.dtype == b.dtype
+    assert out.shape == (a.shape[0], 2 * a.shape[1]) and out.dtype == a.dtype
+    _ev = _begin()
+    _lib.check(_concat_cols(_ptr(a), _ptr(b), c_int(a.shape[0]), c_int(a.shape[1]), _ptr(out), c_int(_is_bf16(a)),
+                            _stream()), "mmt_concat_cols")
+    _count(1, "concat_cols", _ev)
+    return out
+
+
 _spm_rois = _lib.fn("mmt_spm_rois")
 
 

@@ -119,8 +119,44 @@ def main_online(sharpen, yaml_name=None, batch=BATCH, variant="mixformer_vit_onl
     np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}{tag}_b{batch}.npz"), **save)
 
 
+EXTRA = [("mixformer_vit_rgbt_shared", "baseline_attention_lasher_newfusion_2layer"),   # Attention_Fusion_Bimodal
+         ("asymmetric_shared", "attention_lasher_cat_3layer")]                           # RGBT_Fusion_Cat
+
+
+def main_extra():
+    """The two remaining fusion classes of the shipped YAMLs (sharpened weights, batch 2)."""
+    for variant, yaml_name in EXTRA:
+        model, cfg = synthetic.make_model(variant, WEIGHT_SEED, yaml_name=yaml_name)
+        sd = model.state_dict()
+        inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+        ref_model, rcfg = ref_shims.build_reference_model(variant, yaml_name)
+        missing, unexpected = ref_model.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        cap = {}
+        orig = ref_model.box_head.get_score_map
+
+        def hooked(x, orig=orig, cap=cap):
+            tl, br = orig(x)
+            cap["maps"] = torch.stack([tl.flatten(1), br.flatten(1)], dim=1)
+            return tl, br
+        ref_model.box_head.get_score_map = hooked
+        with torch.no_grad():
+            out, _ = ref_model(*inputs)
+        ora = O.forward(variant, sd, cfg, *inputs)
+        d_box = (out["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
+        d_map = (cap["maps"] - ora["score_maps"]).abs().max().item()
+        print(f"{variant}/{yaml_name} ({cfg.MODEL.FUSION_CLASS}): oracle vs reference boxes {d_box:.3e} maps {d_map:.3e}")
+        assert d_box <= 1e-5 and d_map <= 2e-4
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}__{yaml_name}_b{BATCH}.npz"),
+                            pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy())
+
+
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "extra" in variants:
+        torch.set_num_threads(8)
+        main_extra()
+        variants = [v for v in variants if v != "extra"]
     torch.set_num_threads(8)
     torch.set_num_threads(8)
     for ov in ("mixformer_vit_online", "mixformer_convmae_online"):

@@ -369,12 +369,16 @@ def fusion_encoder_lnspecific(sd, src_v, src_i):
         p = _sub(sd, f"encoder.layers.{i}.")
         a = msdeform_attn_bimodal(src + pos, ref, src, shapes, _sub(p, "self_attn."))
         src = src + a
-        sv, si = torch.chunk(src, 2, 1)
-        src = torch.cat([_ln(sv, p, "norm1_v", 1e-5), _ln(si, p, "norm1_i", 1e-5)], dim=1)
+        spec = "norm1_v.weight" in p     # LN-specific encoder; else DeformableTransformerEncoderLayer deformable_encoder.py:143-158
+
+        def norm(t, name):
+            if not spec:
+                return _ln(t, p, name, 1e-5)
+            tv, ti = torch.chunk(t, 2, 1)
+            return torch.cat([_ln(tv, p, name + "_v", 1e-5), _ln(ti, p, name + "_i", 1e-5)], dim=1)
+        src = norm(src, "norm1")
         y = F.linear(F.relu(F.linear(src, p["linear1.weight"], p["linear1.bias"])), p["linear2.weight"], p["linear2.bias"])
-        src = src + y
-        sv, si = torch.chunk(src, 2, 1)
-        src = torch.cat([_ln(sv, p, "norm2_v", 1e-5), _ln(si, p, "norm2_i", 1e-5)], dim=1)
+        src = norm(src + y, "norm2")
     return src
 
 
@@ -387,13 +391,20 @@ def fusion_vi(sd, search_v, search_i, fusion_class):
     """Attention_Fusion_Bimodal_LNSpecific{,_Sum,_2}.forward lib/models/mixformer_vit_rgbt/fusion_utils.py:270-279,
     :309-318, :344-353.  sd keys relative to `fusion_vi.`."""
     b, c, h, w = search_v.shape
+    if fusion_class == "RGBT_Fusion_Cat":      # fusion_utils.py:105-110 (eval BatchNorm2d, eps 1e-5)
+        out = torch.cat([search_v, search_i], dim=1)
+        for j in (1, 2, 3):
+            out = F.conv2d(out, sd[f"fusion{j}.weight"], None, padding=1)
+            out = F.relu(F.batch_norm(out, sd[f"fusion{j}_bn.running_mean"], sd[f"fusion{j}_bn.running_var"],
+                                      sd[f"fusion{j}_bn.weight"], sd[f"fusion{j}_bn.bias"], False, 0.0, 1e-5))
+        return out
     if fusion_class == "Attention_Fusion_Bimodal_LNSpecific_2":
         iv, ii = _conv_gn(search_v, sd, "adjust_in"), _conv_gn(search_i, sd, "adjust_in")
     else:
         iv, ii = _conv_gn(search_v, sd, "adjust_v"), _conv_gn(search_i, sd, "adjust_i")
     out = fusion_encoder_lnspecific(_sub(sd, "fusion_attention."), iv, ii)
     ov, oi = torch.chunk(out, 2, 1)
-    if fusion_class == "Attention_Fusion_Bimodal_LNSpecific":
+    if fusion_class in ("Attention_Fusion_Bimodal_LNSpecific", "Attention_Fusion_Bimodal"):
         ov = ov.permute(0, 2, 1).reshape(b, -1, h, w)
         oi = oi.permute(0, 2, 1).reshape(b, -1, h, w)
         return _conv_gn(torch.cat([ov, oi], dim=1), sd, "adjust_cat")
