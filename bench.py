@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default=VARIANT)
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--yaml", default=None, help="experiment file name of the variant (default: the variant's headline YAML)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work (rank 0, N=1)")
     ap.add_argument("--no-profile", action="store_true", help="skip per-GEMM CUDA-event bracketing")
@@ -205,7 +206,7 @@ def main():
     from mmt_b200 import ops, runner, synthetic
 
     variant, B = args.variant, args.batch
-    model, cfg = synthetic.make_model(variant, 0)
+    model, cfg = synthetic.make_model(variant, 0, yaml_name=args.yaml)
     model = model.cuda(local_rank).set_precision(args.precision)
     # device-resident inputs for `value`; pinned host copies for `e2e`
     host_inputs = synthetic.make_inputs(variant, cfg, B, 1 + rank, pin=True)
@@ -367,14 +368,17 @@ def main():
                 "all_gemm_instantiations": {"achieved": a_flops / (a_ms * 1e-3) / 1e12,
                                             "frac": a_flops / (a_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
                                             "launches": a_l, "share_of_step": a_ms / ms}}
-    step_tflops = GFLOP_PER_FRAME.get(variant, 0.0) * value / world / 1e3
+    gf = {("mixformer_vit_online", "baseline_large"): 600.00, ("mixformer_convmae_online", "baseline_large"): 681.93}.get(
+        (variant, args.yaml), GFLOP_PER_FRAME.get(variant, 0.0))
+    step_tflops = gf * value / world / 1e3
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-        "config": {"workload": f"{variant} ({synthetic.DEFAULT_YAML[variant]}.yaml) MixViT-B "
-                               f"{'RGB-T two-modality' if variant != 'mixformer_vit' else 'RGB'} full forward "
-                               f"(128^2 template + online template, 288^2 search), bs={B} sequences per GPU, "
+        "config": {"workload": f"{variant} ({args.yaml or synthetic.DEFAULT_YAML[variant]}.yaml) "
+                               f"{'RGB-T two-modality' if isinstance(dev_inputs[2], list) else 'RGB'} full forward "
+                               f"({cfg.DATA.TEMPLATE.SIZE}^2 template + online template, {cfg.DATA.SEARCH.SIZE}^2 search), "
+                               f"bs={B} sequences per GPU, "
                                "seeded random-init weights, N(0,1) crops",
                    "batch_per_gpu": B, "sequences": n_seq_total, "parallelism": f"sequence-sharded x{world}",
                    "l2": "working set per step (weights 2x209 MB + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
@@ -387,7 +391,7 @@ def main():
         "latency_bs1": lat,
         "cached_template": cached,
     }
-    if world == 1 and args.cpu_budget > 0:
+    if world == 1 and args.cpu_budget > 0 and args.yaml is None:
         v, cores, sample = cpu_port_frames_per_s(variant, args.cpu_budget)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
