@@ -254,6 +254,11 @@ extern "C" int mmt_mixattn_fwd(const void* qkv0, int rows0, const void* qkv1, in
   MMT_RETURN_LAST_ERROR();
 }
 
+namespace mmt {
+int launch_ce_scores_tc(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
+                        float* partial, int* nqt_out, cudaStream_t stream);
+}
+
 extern "C" int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
                              float* partial_ws, float* scores, int is_bf16, void* stream) {
   MMT_CHECK_ARG(qkv && partial_ws && scores && B > 0 && heads > 0 && C == heads * HD && ld >= 3 * C);
@@ -265,9 +270,13 @@ extern "C" int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, i
   dim3 grid(B, heads, nqt);
   cudaError_t e;
   if (is_bf16) {
-    e = cudaFuncSetAttribute(ce_score_partial_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    ce_score_partial_kernel<bf16><<<grid, 256, smem, s>>>(reinterpret_cast<const bf16*>(qkv), ld, C, B, n_tok, Lt, Ls, scale, kt_pad, partial_ws);
+    // bf16 mode: tensor-core kernel (ce_scores_tc.cu); fewer, larger query tiles -> its own nqt
+    MMT_CHECK_ARG(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
+    int nqt_tc = 0;
+    const int rc = launch_ce_scores_tc(qkv, ld, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, &nqt_tc, s);
+    if (rc) return rc;
+    ce_score_reduce_kernel<<<cdiv(B * ktot, 256), 256, 0, s>>>(partial_ws, B, heads, nqt_tc, ktot, 2 * Lt, scores);
+    MMT_RETURN_LAST_ERROR();
   } else {
     e = cudaFuncSetAttribute(ce_score_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
