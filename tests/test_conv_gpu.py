@@ -6,6 +6,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# the torch references must be true fp32 (cuDNN / cuBLAS default to TF32 for convolutions on this GPU)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 # B, H, W, C, N, channel-slice offset of the input inside a wider buffer (None = dense)
 CASES = [(2, 18, 18, 768, 1344, None), (2, 18, 18, 384, 192, 384), (3, 36, 36, 192, 96, None),
          (2, 72, 72, 96, 48, None), (2, 18, 18, 192, 96, None), (2, 18, 18, 48, 1, None), (1, 36, 36, 96, 48, None),
@@ -47,3 +51,29 @@ def test_upsample_add_matches_torch(built_lib):
     bm = b.float().view(B, 2 * gs, 2 * gs, C).permute(0, 3, 1, 2)
     ref = (F.interpolate(am, scale_factor=4) + F.interpolate(bm, scale_factor=2)).permute(0, 2, 3, 1).reshape(-1, C)
     assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 72, 72, 256), (3, 16, 16, 384), (1, 9, 7, 64)])
+def test_dwconv5x5_and_patchify2x2_match_torch(built_lib, shape, dtype):
+    """ConvMAE stem kernels against torch: depthwise Conv2d(E, E, 5, padding 2, groups E) and the 2x2/2 patch matrix."""
+    from mmt_b200 import ops
+    B, H, W, E = shape
+    g = torch.Generator(device="cuda").manual_seed(H + E)
+    x = torch.randn(B * H * W, E, device="cuda", generator=g).to(dtype)
+    w4 = torch.randn(E, 1, 5, 5, device="cuda", generator=g) * 0.2
+    bias = torch.randn(E, device="cuda", generator=g)
+    out = torch.empty_like(x)
+    ops.dwconv5x5(x, w4.reshape(E, 25).t().contiguous(), bias, B, H, W, out)
+    ref = F.conv2d(x.float().view(B, H, W, E).permute(0, 3, 1, 2), w4, bias, padding=2, groups=E)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, E)
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert (out.float() - ref).abs().max().item() <= tol
+    if H % 2 == 0 and W % 2 == 0:
+        xf = x.float().contiguous()
+        pm = torch.empty(B * (H // 2) * (W // 2), 4 * E, device="cuda")
+        ops.patchify2x2(xf, B, H, W, pm)
+        wq = torch.randn(8, E, 2, 2, device="cuda", generator=g)
+        got = pm @ wq.permute(0, 2, 3, 1).reshape(8, -1).t()
+        want = F.conv2d(xf.view(B, H, W, E).permute(0, 3, 1, 2), wq, stride=2).permute(0, 2, 3, 1).reshape(-1, 8)
+        assert (got - want).abs().max().item() <= 1e-3
