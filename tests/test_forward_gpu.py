@@ -299,3 +299,25 @@ def test_other_fusion_classes(built_lib, variant, yaml_name, precision):
         assert d_box <= 1e-4 * cfg.DATA.SEARCH.SIZE and d_map <= 2e-4
     else:
         assert d_box <= 2.0 and d_map <= 2e-2 * np.abs(g["score_maps"]).max()
+
+
+@pytest.mark.parametrize("variant,batch", [("mixformer_vit_rgbt", 64), ("asymmetric_shared_ce", 128)])
+def test_full_size_batch_independence(built_lib, variant, batch):
+    """BASELINE.json configs[1] / configs[3] at their full batch sizes, through size-independent properties: sequences
+    are independent, so (a) a sub-batch gives bit-identical boxes, (b) permuting the sequences permutes the boxes,
+    (c) every box is finite and inside the unit square (cx, cy of a soft-argmax) - in the bf16 tensor-core path."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(variant, 0)
+    model = model.cuda()
+    t, ot, s = synthetic.make_inputs(variant, cfg, batch, 3, device="cuda")
+    _, full = model(t, ot, s)
+    sub = lambda a, idx: [x[idx].contiguous() for x in a]
+    _, first = model(sub(t, slice(0, 5)), sub(ot, slice(0, 5)), sub(s, slice(0, 5)))
+    perm = torch.randperm(batch, generator=torch.Generator().manual_seed(0)).cuda()
+    _, shuffled = model(sub(t, perm), sub(ot, perm), sub(s, perm))
+    torch.cuda.synchronize()
+    assert torch.equal(full[:5], first), "a sub-batch must reproduce its sequences bit for bit"
+    assert torch.equal(full[perm], shuffled), "permuting the sequences must permute the boxes"
+    b = full.view(-1, 4)
+    assert bool(torch.isfinite(b).all()) and bool(((b[:, :2] >= 0) & (b[:, :2] <= 1)).all())
+    assert b[:, :2].std().item() > 1e-3            # boxes differ between sequences (not a constant output)
