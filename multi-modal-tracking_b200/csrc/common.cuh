@@ -49,18 +49,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // Exact-erf GELU (nn.GELU default) for the fp32 path.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// erf-GELU for the bf16 GEMM epilogue: x * Phi(x) with Phi = 0.5 (1 + tanh(g(x))), g an odd degree-7
-// polynomial fitted (least squares on [0,6]) so that tanh(g(x)) = erf(x / sqrt 2) to 1.3e-5 in
-// x*Phi(x) - i.e. this approximates the EXACT erf GELU of nn.GELU(), not the "tanh GELU" (4.7e-4).
-// One MUFU (tanh.approx, rel. err 2^-11) + 9 FP32 ops, so the tile epilogue stays under the MMA
-// time of the tile.  |x| is clamped to 6 where g stops being monotone; tanh(g(6)) == 1 in fp32.
+// erf-GELU for the bf16 GEMM epilogue: x * Phi(x) with Phi = 0.5 (1 + tanh(g(x))), g(x) = x (c0 + c1 u + c2 u^2),
+// u = min(x^2, 64), fitted (weighted least squares on [0, 3.6]) so that tanh(g(x)) = erf(x / sqrt 2) to 3.0e-5 in
+// x * Phi(x) - i.e. this approximates the EXACT erf GELU of nn.GELU(), not the "tanh GELU" (4.7e-4) - and is monotone
+// on |x| <= 8 (beyond, u is clamped and tanh saturates: g(8) = 13.6).  One MUFU (tanh.approx, rel. err 2^-11) + 7
+// FP32/ALU ops per element: the epilogue's instruction stream costs GEMM rate on a power-capped part (fc1: 1448 TF/s
+// without any epilogue math, 1131 with the previous 10-op form - profiles/r1_gemm_bound.md).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-  const float u = xc * xc;
-  float g = fmaf(u, -8.21175444e-06f, -2.60437580e-04f);
-  g = fmaf(g, u, 3.67492532e-02f);
-  g = fmaf(g, u, 7.97674780e-01f);
-  g *= xc;
+  const float u = fminf(x * x, 64.0f);
+  float p = fmaf(u, -3.58004386e-04f, 3.70462776e-02f);
+  p = fmaf(p, u, 7.97462465e-01f);
+  const float g = p * x;
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(g));
   const float hx = 0.5f * x;

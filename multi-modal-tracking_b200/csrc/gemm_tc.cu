@@ -50,6 +50,7 @@ struct GemmEpi {
   int out_fp32;
   int vec_ok;             // all vector-store alignment preconditions hold
   int prefetch;           // L2-prefetch the next tile's A rows (off unless MMT_GEMM_PREFETCH=1; A/B measurements)
+  int tma_store;          // bf16 output tiles leave through TMA stores (tmC valid): plain GEMM, 16-byte aligned rows
   int dbg_flags;          // developer experiments (MMT_GEMM_DBG): 1 = epilogue without global traffic, 2 = every tile
                           // loads the operands of tile 0 (pure L2 hits)
   long long* dbg;         // developer aid (nullptr in production): per-CTA cycle counters, see mmt_dev_gemm_timing
@@ -85,7 +86,7 @@ struct GemmCfg {
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         int M, int N, int K, GemmEpi ep, GemmConv cv) {
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpi ep, GemmConv cv) {
   using Cfg = GemmCfg<BN, PAIR>;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;     // tile-scheduler slot (a pair is one worker)
@@ -418,13 +419,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
           // staging rows are CH * 2 bytes = LPR_H 16-byte vectors; vector j of row `lane` at slot j ^ key
+          // (for CH = 32 this is exactly the TMA SWIZZLE_64B pattern: 16-byte chunk ^ ((row >> 1) & 3))
           constexpr int KD_H = 8 / LPR_H;
+          const bool tma_out = CH == 32 && ep.tma_store && !cv.enabled;
+          if (tma_out) {                       // the previous chunk's bulk store must have read the staging tile
+            if (lane == 0) bulk_wait_read_all();
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < LPR_H; ++j) {
             uint4 w;
             w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
             w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
             stg4[lane * LPR_H + (j ^ ((lane / KD_H) & (LPR_H - 1)))] = w;
+          }
+          if (tma_out) {
+            // one bulk tensor store of the warp's 32 x 32 tile: no per-lane STG, rows beyond M are clipped by the TMA
+            fence_proxy_async_shared();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, smem_u32(stg4), nb, mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0);
+              bulk_commit_group();
+            }
+            continue;
           }
           __syncwarp();
           bf16* obase = reinterpret_cast<bf16*>(ep.out) + nb;
@@ -465,6 +482,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         else mbar_arrive(tempty_bar(as));
       }
     }
+    if (lane == 0) bulk_wait_all();      // outstanding bulk stores of this warp (smem must outlive their reads)
   }
 
   tc_fence_before();
@@ -492,6 +510,20 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64].
+// bf16 output [rows, cols] (leading dimension ld): 32 x 32 boxes, 64-byte swizzle (the epilogue's staging layout)
+static int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld) {
+  auto fn = get_encode_fn();
+  if (!fn) return MMT_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
+}
+
 static int make_tmap_2d(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) return MMT_ERR_UNSUPPORTED;
@@ -516,8 +548,8 @@ static int num_sms() {
 }
 
 // CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles
-static int launch_gemm_pair(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
-                            cudaStream_t stream) {
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const void* W, int ldw, int M, int N, int K,
+                            const GemmEpi& ep, cudaStream_t stream) {
   constexpr int BN = 256;
   using Cfg = GemmCfg<BN, true>;
   CUtensorMap tmB;
@@ -546,14 +578,14 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const void* W, int ldw, int 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GemmConv cv = {};
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, M, N, K, ep, cv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, M, N, K, ep, cv);
   if (e != cudaSuccess) return (int)e;
   MMT_RETURN_LAST_ERROR();
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
-                       const GemmConv& cv, int max_ctas, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const void* W, int ldw, int M, int N, int K,
+                       const GemmEpi& ep, const GemmConv& cv, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tmB;
   int rc = make_tmap_2d(&tmB, W, N, K, ldw, BN);
@@ -569,7 +601,7 @@ static int launch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, in
   const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep, cv);
+  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep, cv);
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -606,20 +638,33 @@ static bool pair_enabled() {
   return g_pair_mode == 1;
 }
 
-static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, const GemmEpi& ep,
+static int g_tmastore_mode = -1;   // MMT_GEMM_TMASTORE=0 keeps the per-lane store epilogue (A/B measurements)
+
+static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, int N, int K, GemmEpi ep,
                          const GemmConv& cv, int max_ctas, cudaStream_t s) {
+  if (g_tmastore_mode < 0) {
+    const char* e = getenv("MMT_GEMM_TMASTORE");
+    g_tmastore_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  // bf16 output of a plain GEMM with 16-byte aligned rows: tiles leave through TMA stores
+  CUtensorMap tmC = tmA;
+  ep.tma_store = 0;
+  if (g_tmastore_mode && !cv.enabled && !ep.out_fp32 && ep.vec_ok && !ep.rowadd) {
+    if (make_tmap_out(&tmC, ep.out, M, N, ep.ldo) == MMT_OK) ep.tma_store = 1;
+    else tmC = tmA;
+  }
   if (!cv.enabled && max_ctas <= 0 && (N % 256) == 0 && cdiv(M, 2 * GEMM_BM) * (N / 256) >= num_sms() / 2 &&
       pair_enabled())
-    return launch_gemm_pair(tmA, W, ldw, M, N, K, ep, s);
+    return launch_gemm_pair(tmA, tmC, W, ldw, M, N, K, ep, s);
   switch (pick_bn(N)) {
-    case 256: return launch_gemm<256>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 192: return launch_gemm<192>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 128: return launch_gemm<128>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 96: return launch_gemm<96>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 64: return launch_gemm<64>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 48: return launch_gemm<48>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    case 32: return launch_gemm<32>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
-    default: return launch_gemm<16>(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 256: return launch_gemm<256>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 192: return launch_gemm<192>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 128: return launch_gemm<128>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 96: return launch_gemm<96>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 64: return launch_gemm<64>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 48: return launch_gemm<48>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    case 32: return launch_gemm<32>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
+    default: return launch_gemm<16>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
   }
 }
 
@@ -704,6 +749,7 @@ extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, 
   ep.bias = bias; ep.resid = nullptr; ep.rowadd = nullptr; ep.out = out;
   ep.ldr = 0; ep.rowadd_period = 0; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
   ep.dbg = nullptr;
+  ep.tma_store = 0;
   ep.dbg_flags = 0;
   ep.prefetch = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
