@@ -51,6 +51,8 @@ struct GemmEpi {
   int vec_ok;             // all vector-store alignment preconditions hold
   int prefetch;           // L2-prefetch the next tile's A rows (off unless MMT_GEMM_PREFETCH=1; A/B measurements)
   int tma_store;          // bf16 output tiles leave through TMA stores (tmC valid): plain GEMM, 16-byte aligned rows
+  int tma_f32;            // PAIR kernel, fp32 output + fp32 residual: residual tiles arrive and result tiles leave by TMA
+                          // (tmR = residual, tmC = output, 32 x 32 fp32 boxes, 128-byte swizzle)
   int dbg_flags;          // developer experiments (MMT_GEMM_DBG): 1 = epilogue without global traffic, 2 = every tile
                           // loads the operands of tile 0 (pure L2 hits)
   long long* dbg;         // developer aid (nullptr in production): per-CTA cycle counters, see mmt_dev_gemm_timing
@@ -75,9 +77,15 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STAGING_WORDS * 4 +
-                                    1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue shared memory per warp: one 4 KB staging tile; PAIR: two 4 KB tiles (fp32 residual / output tiles of the
+  // TMA epilogue, double-buffered; the bf16 epilogue uses 2 KB of it for the packed rows + 512 B for its bias slices)
+  static constexpr int EPI_TILE_BYTES = PAIR ? 8192 : GEMM_STAGING_WORDS * 4;
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_TILE_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  // the dynamic shared memory is declared __align__(1024) (checked at kernel start): no alignment slack is reserved
+  static constexpr int RING_BUDGET = PAIR ? (227 * 1024 - BAR_BYTES - EPI_BYTES) : GEMM_SMEM_BUDGET;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + (PAIR ? 0 : 1024) /*align slack*/ + BAR_BYTES;
   static constexpr int CH = (BN % 32 == 0) ? 32 : 16;  // epilogue column chunk
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                         : (2 * BN <= 256) ? 256 : 512;
@@ -86,15 +94,18 @@ struct GemmCfg {
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpi ep, GemmConv cv) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N,
+                         int K, GemmEpi ep, GemmConv cv) {
   using Cfg = GemmCfg<BN, PAIR>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;     // tile-scheduler slot (a pair is one worker)
   const int n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (PAIR && (smem_u32(smem_raw) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = staging_base + GEMM_EPI_WARPS * GEMM_STAGING_WORDS * 4;
+  const uint32_t bar_base = staging_base + Cfg::EPI_BYTES;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -125,6 +136,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    if (PAIR)
+      for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(bar_base + 256u + 8u * i, 1);   // residual tiles landed
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);   // PAIR: both CTAs' epilogue warps
@@ -256,7 +269,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = warp >> 2;         // which of the two warps sharing the quadrant
     uint4* stg4 = reinterpret_cast<uint4*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
-                  warp * (GEMM_STAGING_WORDS / 4);
+                  warp * (Cfg::EPI_TILE_BYTES / 16);
+    const uint32_t rbar0 = bar_base + 256u + 16u * warp;          // this warp's two residual-tile barriers (PAIR)
+    uint32_t rk = 0;                                               // running chunk counter of the TMA fp32 epilogue
     constexpr int CH = Cfg::CH;
     constexpr int NCH = BN / CH;
     constexpr int VPR = CH / 4;                 // 16-byte fp32 vectors per staged row (8 or 4)
@@ -305,7 +320,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (ep.bias) {
           if (ep.out_fp32) bv[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + cc_f);
         }
-        if (ep.resid && !(ep.dbg_flags & 4)) {
+        if (ep.resid && !(ep.dbg_flags & 4) && !(PAIR && ep.tma_f32 && !cv.enabled)) {
 #pragma unroll
           for (int it = 0; it < IT_F; ++it) {
             const int grow = grow_of(lrow0 + it * (32 / VPR) + rr_f);
@@ -321,7 +336,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // of a chunk, so the warp's bias slices (<= 4 chunks x CH floats) are parked in the upper part of its staging
       // area once per tile and read back as broadcast vectors.
       constexpr int MAXC = (NCH + 1) / 2;           // chunks per warp
+      // (per WARP, never shared between warps: the epilogue warps of a CTA drift apart by up to a tile)
       float* bias_s = reinterpret_cast<float*>(stg4) + 32 * 16;   // after the 32 x 64 B bf16 staging rows
+      const bool f32_tma = PAIR && CH == 32 && ep.tma_f32 && !cv.enabled;
       const bool bias_smem = !ep.out_fp32 && ep.vec_ok && ep.bias != nullptr;
       if (bias_smem) {
         __syncwarp();
@@ -334,6 +351,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      const int grow_w = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0;   // first global row of this warp
+      auto issue_resid = [&](int c, uint32_t k) {     // TMA load of the residual tile of chunk c into buffer k & 1
+        if (lane == 0) {
+          bulk_wait_read_all();                       // the store that last used this buffer has read it
+          const uint32_t bar = rbar0 + 8u * (k & 1u);
+          mbar_expect_tx(bar, 4096);
+          tma_load_2d(smem_u32(stg4) + 4096u * (k & 1u), &tmR, bar, n0 + c * CH, grow_w);
+        }
+      };
+      if (f32_tma && half < NCH && n0 + half * CH + CH <= N) issue_resid(half, rk);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -351,6 +378,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int nb = n0 + c * CH;
         if (nb >= N || (ep.dbg_flags & 1)) continue;
         const bool full = ep.vec_ok && (nb + CH <= N);
+        if (full && f32_tma) {
+          // ---- fp32 output + fp32 residual, CTA-pair kernel: thread == row throughout.  The residual tile was fetched
+          // by TMA into this warp's buffer (128-byte rows, 128B swizzle); the row is updated in place and the tile
+          // leaves by one TMA store - no per-lane global access, full 128-byte lines, loads one chunk ahead.
+          const uint32_t k = rk++;
+          if (c + 2 < NCH && n0 + (c + 2) * CH + CH <= N) issue_resid(c + 2, k + 1);
+          uint4* tile = stg4 + 256 * (k & 1u);                       // 4096 B per buffer
+          // bias: both buffers are in use, so the chunk's 32 values come as 8 warp-uniform (broadcast) L1 loads
+          float4 bq[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bq[j] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          mbar_wait(rbar0 + 8u * (k & 1u), (k >> 1) & 1u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int slot = lane * 8 + (j ^ (lane & 7));
+            const uint4 rw = tile[slot];
+            const float4 b = bq[j];
+            float x[4] = {__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y,
+                          __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w};
+            if (ep.act == MMT_ACT_GELU) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) x[q] = gelu_fast(x[q]);
+            } else if (ep.act == MMT_ACT_RELU) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) x[q] = fmaxf(x[q], 0.f);
+            }
+            uint4 o;
+            o.x = __float_as_uint(x[0] + __uint_as_float(rw.x)); o.y = __float_as_uint(x[1] + __uint_as_float(rw.y));
+            o.z = __float_as_uint(x[2] + __uint_as_float(rw.z)); o.w = __float_as_uint(x[3] + __uint_as_float(rw.w));
+            tile[slot] = o;
+          }
+          fence_proxy_async_shared();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, smem_u32(tile), nb, grow_w);
+            bulk_commit_group();
+          }
+          continue;
+        }
         if (full && ep.out_fp32) {
           // ---- fp32 output: stage raw accumulators (row `lane`, vector j at slot j ^ key(lane)), finish transposed
 #pragma unroll
@@ -524,6 +591,20 @@ static int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, i
   return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
 }
 
+// fp32 [rows, cols] (leading dimension ld): 32 x 32 boxes = 128-byte rows, 128-byte swizzle (residual in / result out)
+static int make_tmap_f32_tile(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld) {
+  auto fn = get_encode_fn();
+  if (!fn) return MMT_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
+}
+
 static int make_tmap_2d(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) return MMT_ERR_UNSUPPORTED;
@@ -548,8 +629,8 @@ static int num_sms() {
 }
 
 // CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles
-static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const void* W, int ldw, int M, int N, int K,
-                            const GemmEpi& ep, cudaStream_t stream) {
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const void* W, int ldw,
+                            int M, int N, int K, const GemmEpi& ep, cudaStream_t stream) {
   constexpr int BN = 256;
   using Cfg = GemmCfg<BN, true>;
   CUtensorMap tmB;
@@ -578,7 +659,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, cons
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GemmConv cv = {};
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, M, N, K, ep, cv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, tmR, M, N, K, ep, cv);
   if (e != cudaSuccess) return (int)e;
   MMT_RETURN_LAST_ERROR();
 }
@@ -601,7 +682,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const voi
   const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep, cv);
+  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC, M, N, K, ep, cv);
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -649,13 +730,21 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
   // bf16 output of a plain GEMM with 16-byte aligned rows: tiles leave through TMA stores
   CUtensorMap tmC = tmA;
   ep.tma_store = 0;
+  ep.tma_f32 = 0;
   if (g_tmastore_mode && !cv.enabled && !ep.out_fp32 && ep.vec_ok && !ep.rowadd) {
     if (make_tmap_out(&tmC, ep.out, M, N, ep.ldo) == MMT_OK) ep.tma_store = 1;
     else tmC = tmA;
   }
   if (!cv.enabled && max_ctas <= 0 && (N % 256) == 0 && cdiv(M, 2 * GEMM_BM) * (N / 256) >= num_sms() / 2 &&
-      pair_enabled())
-    return launch_gemm_pair(tmA, tmC, W, ldw, M, N, K, ep, s);
+      pair_enabled()) {
+    CUtensorMap tmR = tmA;
+    ep.tma_f32 = 0;
+    if (g_tmastore_mode && ep.out_fp32 && ep.resid && ep.vec_ok && !ep.rowadd && (ep.ldo % 4) == 0 && (ep.ldr % 4) == 0 &&
+        make_tmap_f32_tile(&tmC, ep.out, M, N, ep.ldo) == MMT_OK &&
+        make_tmap_f32_tile(&tmR, ep.resid, M, N, ep.ldr) == MMT_OK)
+      ep.tma_f32 = 1;
+    return launch_gemm_pair(tmA, tmC, tmR, W, ldw, M, N, K, ep, s);
+  }
   switch (pick_bn(N)) {
     case 256: return launch_gemm<256>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
     case 192: return launch_gemm<192>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
@@ -750,6 +839,7 @@ extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, 
   ep.ldr = 0; ep.rowadd_period = 0; ep.ldo = ldo; ep.act = act; ep.out_fp32 = out_fp32;
   ep.dbg = nullptr;
   ep.tma_store = 0;
+  ep.tma_f32 = 0;
   ep.dbg_flags = 0;
   ep.prefetch = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
