@@ -211,6 +211,34 @@ int mmt_spm_rois(const float* xyxy, int B, float scale, float* rois, void* strea
 int mmt_prroi_fwd(const float* feat, const float* rois, float* out, int R, int C, int H, int W, int PH, int PW,
                   float spatial_scale, int channels_last, void* stream);
 
+/*
+ * Frame side of the per-frame loop, batched on the device.
+ *
+ * mmt_frame_crop: for n_mod x B uint8 HWC (3-channel) frames - image m*B + b; frames_dev is a DEVICE array of device
+ * pointers, dims_dev a DEVICE int32 [n_mod*B][3] = (H, W, row pitch in bytes) - extract the square window of side
+ * ceil(sqrt(w*h) * factor) centred on the sequence's box (state_dev: DEVICE float64 [B][4] = x, y, w, h, shared by the
+ * modalities), zero-pad it, resize it to out_sz x out_sz with OpenCV's fixed-point INTER_LINEAR, apply the JET colour
+ * map for the modalities whose bit is set in jet_mask (jet_lut_dev: DEVICE uint8 [256][3]), and write
+ * ((x/255) - mean) / std as fp32 [n_mod][B][3][S][S] (out) and/or the uint8 crop [n_mod][B][S][S][3] (out_u8).
+ * resize_factor_dev (DEVICE float64 [B], may be NULL) receives out_sz / crop side.  active_dev (DEVICE uint8 [B] or NULL)
+ * selects the sequences that are processed; the others keep their previous outputs.  A degenerate box (side < 1, where
+ * the reference raises "Too small bounding box.") yields an all-zero crop.
+ * Replaces sample_target lib/train/data/processing_utils.py:15-83 (cv.copyMakeBorder + cv.resize) and
+ * Preprocessor_Multimodal.process lib/test/tracker/tracker_utils.py:37-48 (cv2.applyColorMap, normalisation, H2D).
+ *
+ * mmt_track_update: state <- clip_box(map_box_back(pred * search_size / resize_factor)), margin in pixels, frame sizes
+ * from dims_dev rows 0..B-1; the new state is also written to log_dev (float64 [B][4], may be NULL: e.g. row t of the
+ * sequence's result table).  Replaces the host arithmetic and the per-frame `.tolist()` synchronisation of
+ * MixFormer.track lib/test/tracker/asymmetric_shared_ce.py:99-103,134-140 and clip_box lib/utils/box_ops.py:155-164.
+ */
+int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const double* state_dev,
+                   const unsigned char* active_dev, int B, int n_mod, unsigned jet_mask, double factor, int out_sz,
+                   const unsigned char* jet_lut_dev, float* out, unsigned char* out_u8, double* resize_factor_dev,
+                   void* stream);
+int mmt_track_update(const float* pred_cxcywh, const double* resize_factor_dev, const int* dims_dev, double* state_dev,
+                     double* log_dev, const unsigned char* active_dev, int B, int search_size, double margin,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,192 @@
+// Per-frame glue around the network forward, on the device.
+//
+// The reference does this on the host, one sequence at a time, and synchronises the GPU every frame:
+//   sample_target            lib/train/data/processing_utils.py:15-83   crop window, zero padding, cv.resize
+//   Preprocessor_Multimodal  lib/test/tracker/tracker_utils.py:37-48    JET colour map (infrared), /255, mean/std, CHW
+//   MixFormer.track          lib/test/tracker/asymmetric_shared_ce.py:99-103,134-140   pred box -> frame coordinates
+//   clip_box                 lib/utils/box_ops.py:155-164
+// Here B sequences advance together: the tracker state [B,4] (float64, like the Python floats it replaces) lives in
+// HBM, one kernel turns the uint8 frames into the normalised fp32 crops the backbone embeds, one kernel folds the
+// predicted boxes back into the state.  No host round trip per frame.
+//
+// Bit-exactness: the crop window is float64 arithmetic with round-half-even (`round()`), the resize is OpenCV's
+// fixed-point INTER_LINEAR for uint8 (resize.cpp: 11-bit coefficient pairs from float32 fractions, horizontal pass in
+// int32, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2), BGR2GRAY is its 15-bit fixed point; the
+// uint8 crops therefore equal the reference's byte for byte (tests/test_frames_gpu.py, oracle/frame_oracle.py).
+// Both are HBM/L2-bound gathers: one thread per output pixel, the three channel planes written coalesced.
+#include "common.cuh"
+#include "../../include/mmt_b200.h"
+
+namespace mmt {
+
+struct CropGeom {
+  int crop_sz, x1, y1, xa, xb, ya, yb;   // window origin and the frame range [xa,xb) x [ya,yb) that is copied
+  int H, W, pitch;
+  int valid;
+  double scale;                          // 1 / (S / crop_sz), as cv::resize computes it
+};
+
+// processing_utils.py:31-49, float64 with explicitly rounded operations (no contraction)
+__device__ inline void crop_geometry(const double* st, double factor, int H, int W, CropGeom& g) {
+  const double x = st[0], y = st[1], w = st[2], h = st[3];
+  const double side = __dmul_rn(sqrt(__dmul_rn(w, h)), factor);
+  const double c = ceil(side);
+  g.valid = (c >= 1.0 && c < 1.0e6) ? 1 : 0;        // "Too small bounding box." in the reference; NaN fails both tests
+  g.crop_sz = g.valid ? static_cast<int>(c) : 1;
+  const double half = __dmul_rn(static_cast<double>(g.crop_sz), 0.5);
+  g.x1 = static_cast<int>(rint(__dsub_rn(__dadd_rn(x, __dmul_rn(0.5, w)), half)));    // round(): half to even
+  g.y1 = static_cast<int>(rint(__dsub_rn(__dadd_rn(y, __dmul_rn(0.5, h)), half)));
+  const int x2 = g.x1 + g.crop_sz, y2 = g.y1 + g.crop_sz;
+  g.xa = max(g.x1, 0);
+  g.xb = x2 - max(x2 - W + 1, 0);                   // the reference's "+ 1": the last column is dropped with the overhang
+  g.ya = max(g.y1, 0);
+  g.yb = y2 - max(y2 - H + 1, 0);
+  g.H = H; g.W = W;
+}
+
+// source index and 11-bit weight pair of destination index d (resize.cpp set-up loop, horizontal flavour when
+// `horizontal`: negative index -> (0, weight 0); last column -> single tap)
+__device__ __forceinline__ void linear_tap(int d, double scale, int ssize, bool horizontal, int& s0, int& s1, int& w0,
+                                           int& w1) {
+  float f = static_cast<float>(__dsub_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), 0.5));
+  int s = static_cast<int>(floorf(f));
+  f = __fsub_rn(f, static_cast<float>(s));
+  if (horizontal) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s + 1 >= ssize) {                           // dx >= xmax: D[dx] = S[sx] * ONE
+      s0 = s1 = min(s, ssize - 1);
+      w0 = 2048; w1 = 0;
+      return;
+    }
+    s0 = s; s1 = s + 1;
+  } else {
+    s0 = min(max(s, 0), ssize - 1);
+    s1 = min(max(s + 1, 0), ssize - 1);
+  }
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));      // saturate_cast<short>(cvRound(.)); |.| <= 2048
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256)
+frame_crop_kernel(const uint8_t* const* __restrict__ frames, const int* __restrict__ dims,
+                  const double* __restrict__ state, const uint8_t* __restrict__ active, int B, unsigned jet_mask,
+                  double factor, int S, const uint8_t* __restrict__ jet_lut, float* __restrict__ out,
+                  uint8_t* __restrict__ out_u8, double* __restrict__ resize_factor) {
+  const int img = blockIdx.y;              // m * B + b
+  const int b = img % B, m = img / B;
+  if (active && !active[b]) return;
+  __shared__ CropGeom g;
+  if (threadIdx.x == 0) {
+    crop_geometry(state + 4 * b, factor, dims[3 * img], dims[3 * img + 1], g);
+    g.pitch = dims[3 * img + 2];
+    const double inv = __ddiv_rn(static_cast<double>(S), static_cast<double>(g.crop_sz));
+    g.scale = __ddiv_rn(1.0, inv);
+    if (m == 0 && blockIdx.x == 0 && resize_factor) resize_factor[b] = inv;       // output_sz / crop_sz
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= S * S) return;
+  const int dy = pix / S, dx = pix - dy * S;
+  int sx0, sx1, a0, a1, sy0, sy1, b0, b1;
+  linear_tap(dx, g.scale, g.crop_sz, true, sx0, sx1, a0, a1);
+  linear_tap(dy, g.scale, g.crop_sz, false, sy0, sy1, b0, b1);
+  const uint8_t* __restrict__ base = frames[img];
+  // frame coordinates of the four taps; outside [xa,xb) x [ya,yb) the padded crop is zero
+  const int fx0 = g.x1 + sx0, fx1 = g.x1 + sx1, fy0 = g.y1 + sy0, fy1 = g.y1 + sy1;
+  const bool vx0 = g.valid && fx0 >= g.xa && fx0 < g.xb, vx1 = g.valid && fx1 >= g.xa && fx1 < g.xb;
+  const bool vy0 = fy0 >= g.ya && fy0 < g.yb, vy1 = fy1 >= g.ya && fy1 < g.yb;
+  const uint8_t* r0 = base + static_cast<size_t>(fy0) * g.pitch;
+  const uint8_t* r1 = base + static_cast<size_t>(fy1) * g.pitch;
+  int v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int p00 = (vy0 && vx0) ? r0[fx0 * 3 + c] : 0, p01 = (vy0 && vx1) ? r0[fx1 * 3 + c] : 0;
+    const int p10 = (vy1 && vx0) ? r1[fx0 * 3 + c] : 0, p11 = (vy1 && vx1) ? r1[fx1 * 3 + c] : 0;
+    const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
+    v[c] = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    v[c] = min(max(v[c], 0), 255);
+  }
+  if ((jet_mask >> m) & 1u) {
+    // cv2.applyColorMap on a 3-channel image: BGR2GRAY with channel 0 in the 'B' slot, then the 256-entry table
+    const int gray = (v[0] * 3735 + v[1] * 19235 + v[2] * 9798 + (1 << 14)) >> 15;
+    const uint8_t* e = jet_lut + 3 * gray;
+    v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+  }
+  if (out_u8) {
+    uint8_t* o = out_u8 + (static_cast<size_t>(img) * S * S + pix) * 3;
+    o[0] = static_cast<uint8_t>(v[0]); o[1] = static_cast<uint8_t>(v[1]); o[2] = static_cast<uint8_t>(v[2]);
+  }
+  if (out) {
+    // ((x / 255) - mean) / std, fp32 true divisions (tracker_utils.py:44-47)
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    float* o = out + static_cast<size_t>(img) * 3 * S * S + pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      o[static_cast<size_t>(c) * S * S] =
+          __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[c]), 255.0f), mean[c]), sd[c]);
+  }
+}
+
+// asymmetric_shared_ce.py:99-103 + map_box_back :134-140 + clip_box box_ops.py:155-164; one thread per sequence
+__global__ void track_update_kernel(const float* __restrict__ pred, const double* __restrict__ resize_factor,
+                                    const int* __restrict__ dims, double* __restrict__ state, double* __restrict__ log,
+                                    const uint8_t* __restrict__ active, int B, int search_size, double margin) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double st[4] = {state[4 * b], state[4 * b + 1], state[4 * b + 2], state[4 * b + 3]};
+  if (!active || active[b]) {
+    const double rf = resize_factor[b];
+    // pred_boxes.mean(0) * search_size / resize_factor: fp32 tensor arithmetic (one box per sequence)
+    const float rff = static_cast<float>(rf), ss = static_cast<float>(search_size);
+    double p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = static_cast<double>(__fdiv_rn(__fmul_rn(pred[4 * b + k], ss), rff));
+    const double cx_prev = __dadd_rn(st[0], __dmul_rn(0.5, st[2])), cy_prev = __dadd_rn(st[1], __dmul_rn(0.5, st[3]));
+    const double half_side = __ddiv_rn(__dmul_rn(0.5, static_cast<double>(search_size)), rf);
+    const double cx = __dadd_rn(p[0], __dsub_rn(cx_prev, half_side));
+    const double cy = __dadd_rn(p[1], __dsub_rn(cy_prev, half_side));
+    double x1 = __dsub_rn(cx, __dmul_rn(0.5, p[2])), y1 = __dsub_rn(cy, __dmul_rn(0.5, p[3]));
+    const double w = p[2], h = p[3];
+    const double H = static_cast<double>(dims[3 * b]), W = static_cast<double>(dims[3 * b + 1]);
+    double x2 = __dadd_rn(x1, w), y2 = __dadd_rn(y1, h);
+    x1 = fmin(fmax(0.0, x1), W - margin);
+    x2 = fmin(fmax(margin, x2), W);
+    y1 = fmin(fmax(0.0, y1), H - margin);
+    y2 = fmin(fmax(margin, y2), H);
+    st[0] = x1; st[1] = y1;
+    st[2] = fmax(margin, __dsub_rn(x2, x1));
+    st[3] = fmax(margin, __dsub_rn(y2, y1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) state[4 * b + k] = st[k];
+  }
+  if (log) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) log[4 * b + k] = st[k];
+  }
+}
+
+}  // namespace mmt
+
+extern "C" int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const double* state_dev,
+                              const unsigned char* active_dev, int B, int n_mod, unsigned jet_mask, double factor,
+                              int out_sz, const unsigned char* jet_lut_dev, float* out, unsigned char* out_u8,
+                              double* resize_factor_dev, void* stream) {
+  MMT_CHECK_ARG(frames_dev && dims_dev && state_dev && (out || out_u8));
+  MMT_CHECK_ARG(B > 0 && n_mod > 0 && n_mod <= 8 && out_sz > 0 && out_sz <= 4096 && factor > 0.0);
+  MMT_CHECK_ARG(static_cast<long long>(B) * n_mod <= 65535);
+  MMT_CHECK_ARG(jet_mask == 0u || jet_lut_dev != nullptr);
+  const dim3 grid(mmt::cdiv(out_sz * out_sz, 256), B * n_mod);
+  mmt::frame_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t* const*>(frames_dev), dims_dev, state_dev, active_dev, B, jet_mask, factor, out_sz,
+      jet_lut_dev, out, out_u8, resize_factor_dev);
+  MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_track_update(const float* pred_cxcywh, const double* resize_factor_dev, const int* dims_dev,
+                                double* state_dev, double* log_dev, const unsigned char* active_dev, int B,
+                                int search_size, double margin, void* stream) {
+  MMT_CHECK_ARG(pred_cxcywh && resize_factor_dev && dims_dev && state_dev && B > 0 && search_size > 0);
+  mmt::track_update_kernel<<<mmt::cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred_cxcywh, resize_factor_dev, dims_dev, state_dev, log_dev, active_dev, B, search_size, margin);
+  MMT_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,196 @@
+"""Batched tracker loop with the frame-side work on the device.
+
+The reference tracker class (lib/test/tracker/asymmetric_shared_ce.py:14-140, lib/test/tracker/mixformer_vit.py) handles
+ONE sequence: per frame it crops with cv2 on the host (`sample_target`), colour-maps / normalises / uploads the crop
+(`Preprocessor_Multimodal`), runs the network, pulls the box back with `.tolist()` (a device synchronisation), maps it
+to frame coordinates and clips it in Python.  `BatchedTracker` keeps the same `initialize` / `track` protocol and the
+same arithmetic for B sequences in lock-step, but the host only uploads the raw uint8 frames: crop, resize, colour map,
+normalisation, box map-back and clipping are two CUDA kernels (csrc/frames.cu) around the forward, the tracker state
+lives in HBM as float64, and nothing synchronises until `results()` is read.
+
+torch is used for device memory, streams and events only; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+# cv2.applyColorMap(np.arange(256, dtype=np.uint8)[None], cv2.COLORMAP_JET)[0] of OpenCV 4.13.0 as hex (B, G, R per
+# entry): the table Preprocessor_Multimodal applies to the infrared crop (lib/test/tracker/tracker_utils.py:43).
+JET_LUT_HEX = (
+    "8000008400008800008c00009000009400009800009c0000a00000a40000a80000ac0000b00000b40000b80000bc0000"
+    "c00000c40000c80000cc0000d00000d40000d80000dc0000e00000e40000e80000ec0000f00000f40000f80000fc0000"
+    "ff0000ff0400ff0800ff0c00ff1000ff1400ff1800ff1c00ff2000ff2400ff2800ff2c00ff3000ff3400ff3800ff3c00"
+    "ff4000ff4400ff4800ff4c00ff5000ff5400ff5800ff5c00ff6000ff6400ff6800ff6c00ff7000ff7400ff7800ff7c00"
+    "ff8000ff8400ff8800ff8c00ff9000ff9400ff9800ff9c00ffa000ffa400ffa800ffac00ffb000ffb400ffb800ffbc00"
+    "ffc000ffc400ffc800ffcc00ffd000ffd400ffd800ffdc00ffe000ffe400ffe800ffec00fff000fff400fff800fffc00"
+    "feff02faff06f6ff0af2ff0eeeff12eaff16e6ff1ae2ff1edeff22daff26d6ff2ad2ff2eceff32caff36c6ff3ac2ff3e"
+    "beff42baff46b6ff4ab2ff4eaeff52aaff56a6ff5aa2ff5e9eff629aff6696ff6a92ff6e8eff728aff7686ff7a82ff7e"
+    "7eff827aff8676ff8a72ff8e6eff926aff9666ff9a62ff9e5effa25affa656ffaa52ffae4effb24affb646ffba42ffbe"
+    "3effc23affc636ffca32ffce2effd22affd626ffda22ffde1effe21affe616ffea12ffee0efff20afff606fffa01fffe"
+    "00fcff00f8ff00f4ff00f0ff00ecff00e8ff00e4ff00e0ff00dcff00d8ff00d4ff00d0ff00ccff00c8ff00c4ff00c0ff"
+    "00bcff00b8ff00b4ff00b0ff00acff00a8ff00a4ff00a0ff009cff0098ff0094ff0090ff008cff0088ff0084ff0080ff"
+    "007cff0078ff0074ff0070ff006cff0068ff0064ff0060ff005cff0058ff0054ff0050ff004cff0048ff0044ff0040ff"
+    "003cff0038ff0034ff0030ff002cff0028ff0024ff0020ff001cff0018ff0014ff0010ff000cff0008ff0004ff0000ff"
+    "0000fc0000f80000f40000f00000ec0000e80000e40000e00000dc0000d80000d40000d00000cc0000c80000c40000c0"
+    "0000bc0000b80000b40000b00000ac0000a80000a40000a000009c00009800009400009000008c000088000084000080")
+
+
+def jet_lut_tensor(device) -> torch.Tensor:
+    return torch.frombuffer(bytearray(bytes.fromhex(JET_LUT_HEX)), dtype=torch.uint8).to(device)
+
+
+class FrameUploader:
+    """Raw uint8 frames of one step -> one pinned staging buffer -> one H2D copy on a side stream.
+
+    Frame sizes are fixed per (sequence, modality), so the device pointer table and the (H, W, pitch) table are built
+    once; two staging/device buffer pairs alternate so that the upload of step t+1 overlaps the forward of step t."""
+
+    def __init__(self, shapes, device):
+        # shapes: list over images (modality-major, image m*B + b) of (H, W)
+        self.device = device
+        offs, total = [], 0
+        for (H, W) in shapes:
+            offs.append(total)
+            total += (H * W * 3 + 255) // 256 * 256          # 256-byte aligned frames
+        self.shapes, self.offsets, self.total = list(shapes), offs, total
+        self.pinned = [torch.empty(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.dev = [torch.empty(total, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.ptrs = [torch.tensor([d.data_ptr() + o for o in offs], dtype=torch.int64, device=device) for d in self.dev]
+        self.dims = torch.tensor([[H, W, W * 3] for (H, W) in shapes], dtype=torch.int32, device=device)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self._used = [False, False]
+        self.k = 0
+        self.h2d_bytes = 0
+
+    def upload(self, images) -> int:
+        """images: list over images (same order as `shapes`) of uint8 HWC numpy arrays. Returns the buffer index; the
+        CURRENT stream waits for the copy."""
+        k = self.k
+        self.k ^= 1
+        if self._used[k]:
+            self.copied[k].synchronize()                      # host may overwrite the staging buffer
+        host = self.pinned[k].numpy()
+        for im, (H, W), o in zip(images, self.shapes, self.offsets):
+            if im.shape != (H, W, 3) or im.dtype != np.uint8:
+                raise ValueError(f"frame of shape {im.shape}/{im.dtype}, expected uint8 {(H, W, 3)} (frame sizes are fixed "
+                                 "per sequence)")
+            host[o:o + H * W * 3] = im.reshape(-1)
+        with torch.cuda.stream(self.copy_stream):
+            if self._used[k]:
+                self.copy_stream.wait_event(self.consumed[k])  # kernels of two steps ago have read the device buffer
+            self.dev[k].copy_(self.pinned[k], non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        torch.cuda.current_stream().wait_event(self.copied[k])
+        self._used[k] = True
+        self.h2d_bytes = self.total
+        return k
+
+    def release(self, k: int) -> None:
+        """Call after the last kernel reading device buffer k has been enqueued on the current stream."""
+        self.consumed[k].record(torch.cuda.current_stream())
+
+
+class BatchedTracker:
+    """`initialize` / `track` of the reference tracker class for B sequences at a time.
+
+    network: a model from mmt_b200.builders on a CUDA device (RGB-T: called with [v, i] lists; RGB-only: tensors).
+    params:  object with template_factor, template_size, search_factor, search_size (lib/test/parameter/*.py).
+    update_intervals: the reference's `self.update_intervals` (online template refreshed when frame_id % interval == 0).
+    n_mod: 2 for the RGB-T trackers (modality 1 goes through the JET colour map), 1 for RGB-only.
+    use_template_cache: run `cache_templates()` at template updates and `forward_search()` per frame (symmetric
+    variants; bit-identical boxes).
+    """
+
+    MARGIN = 10.0      # clip_box(..., margin=10), asymmetric_shared_ce.py:103
+
+    def __init__(self, network, params, update_intervals=(), n_mod=2, use_template_cache=False, capacity=1024):
+        self.network = network
+        self.device = next(network.parameters()).device
+        if self.device.type != "cuda":
+            raise NotImplementedError("BatchedTracker needs a CUDA model (no CPU fallback)")
+        self.params = params
+        self.update_intervals = [int(u) for u in update_intervals]
+        self.n_mod = int(n_mod)
+        self.jet_mask = 0b10 if self.n_mod == 2 else 0
+        self.use_cache = bool(use_template_cache)
+        self.capacity = int(capacity)
+        self.frame_id = 0
+        self.B = 0
+        self._lut = jet_lut_tensor(self.device)
+
+    # ------------------------------------------------------------------ helpers
+    def _flatten(self, frames):
+        """list over sequences of [im_v, im_i] (or a single array) -> modality-major list of images."""
+        if self.n_mod == 1:
+            return [f if isinstance(f, np.ndarray) else f[0] for f in frames]
+        return [f[m] for m in range(self.n_mod) for f in frames]
+
+    def _model_args(self, buf):
+        return [buf[m] for m in range(self.n_mod)] if self.n_mod > 1 else buf[0]
+
+    def _crop(self, k, factor, size, out, active=None, rf=None):
+        ops.frame_crop(self.up.ptrs[k], self.up.dims, self.state, factor, size, self.n_mod, self.jet_mask, self._lut,
+                       active=active, out=out, resize_factor=rf)
+
+    # ------------------------------------------------------------------ protocol
+    def initialize(self, frames, init_boxes):
+        """frames: list over B sequences of [image_v, image_i] uint8 HWC RGB arrays (RGB-only: one array each);
+        init_boxes: [B, 4] (x, y, w, h).  asymmetric_shared_ce.py:50-72: template = online template = crop at the
+        initial box, state = initial box."""
+        p = self.params
+        B = self.B = len(frames)
+        imgs = self._flatten(frames)
+        self.up = FrameUploader([im.shape[:2] for im in imgs], self.device)
+        dev = self.device
+        self.state = torch.tensor(np.asarray(init_boxes, dtype=np.float64).reshape(B, 4), device=dev)
+        self.rf = torch.empty(B, dtype=torch.float64, device=dev)
+        self.template = torch.empty((self.n_mod, B, 3, p.template_size, p.template_size), dtype=torch.float32, device=dev)
+        self.online_template = torch.empty_like(self.template)
+        self.search = torch.empty((self.n_mod, B, 3, p.search_size, p.search_size), dtype=torch.float32, device=dev)
+        self.log = torch.zeros((self.capacity, B, 4), dtype=torch.float64, device=dev)
+        self.frame_id = 0
+        k = self.up.upload(imgs)
+        self._crop(k, float(p.template_factor), int(p.template_size), self.template)
+        self.up.release(k)
+        self.online_template.copy_(self.template)
+        self.log[0].copy_(self.state)
+        if self.use_cache:
+            self.network.cache_templates(self._model_args(self.template), self._model_args(self.online_template))
+
+    def track(self, frames, active=None):
+        """One frame for every sequence; returns nothing and does not synchronise (read `results()`)."""
+        p = self.params
+        self.frame_id += 1
+        if self.frame_id >= self.log.shape[0]:
+            self.log = torch.cat([self.log, torch.zeros_like(self.log)], 0)
+        act = None
+        if active is not None:
+            act = torch.from_numpy(np.ascontiguousarray(np.asarray(active, dtype=np.uint8))).to(self.device,
+                                                                                                  non_blocking=True)
+        k = self.up.upload(self._flatten(frames))
+        self._crop(k, float(p.search_factor), int(p.search_size), self.search, active=act, rf=self.rf)
+        with torch.inference_mode():
+            if self.use_cache:
+                _, coords = self.network.forward_search(self._model_args(self.search))
+            else:
+                _, coords = self.network(self._model_args(self.template), self._model_args(self.online_template),
+                                         self._model_args(self.search))
+        ops.track_update(coords.view(-1, 4), self.rf, self.up.dims, self.state, int(p.search_size), self.MARGIN,
+                         log=self.log[self.frame_id], active=act)
+        updated = False
+        for interval in self.update_intervals:
+            if self.frame_id % interval == 0:
+                self._crop(k, float(p.template_factor), int(p.template_size), self.online_template, active=act)
+                updated = True
+        self.up.release(k)
+        if updated and self.use_cache:
+            self.network.cache_templates(self._model_args(self.template), self._model_args(self.online_template))
+
+    def results(self) -> np.ndarray:
+        """[frame_id + 1, B, 4] float64 boxes (x, y, w, h) per frame; row 0 is the initial box.  Synchronises."""
+        return self.log[:self.frame_id + 1].cpu().numpy()

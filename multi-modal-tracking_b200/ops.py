@@ -454,3 +454,55 @@ def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None)
                       c_int(pw), c_float(spatial_scale), c_int(1 if channels_last else 0), _stream()), "mmt_prroi_fwd")
     _count(1, "prroi_pool", _ev)
     return out
+
+
+_frame_crop = _lib.fn("mmt_frame_crop")
+_track_update = _lib.fn("mmt_track_update")
+
+
+def frame_crop(frame_ptrs, dims, state, factor, out_sz, n_mod, jet_mask=0, jet_lut=None, active=None, out=None,
+               out_u8=None, resize_factor=None):
+    """Device-side sample_target + Preprocessor (include/mmt_b200.h: mmt_frame_crop).
+
+    frame_ptrs int64 CUDA [n_mod*B] (device addresses of uint8 HWC frames), dims int32 CUDA [n_mod*B, 3] (H, W, pitch),
+    state float64 CUDA [B, 4].  Returns (out fp32 [n_mod, B, 3, S, S] or None, out_u8, resize_factor float64 [B])."""
+    _need_cuda(frame_ptrs, dims, state)
+    B = state.shape[0]
+    assert frame_ptrs.dtype == torch.int64 and frame_ptrs.numel() == n_mod * B and frame_ptrs.is_contiguous()
+    assert dims.dtype == torch.int32 and tuple(dims.shape) == (n_mod * B, 3) and dims.is_contiguous()
+    assert state.dtype == torch.float64 and tuple(state.shape) == (B, 4) and state.is_contiguous()
+    if out is None and out_u8 is None:
+        out = torch.empty((n_mod, B, 3, out_sz, out_sz), device=state.device, dtype=torch.float32)
+    if out is not None:
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n_mod * B * 3 * out_sz * out_sz
+    if out_u8 is not None:
+        assert out_u8.dtype == torch.uint8 and out_u8.is_contiguous() and out_u8.numel() == n_mod * B * 3 * out_sz * out_sz
+    if resize_factor is None:
+        resize_factor = torch.empty(B, device=state.device, dtype=torch.float64)
+    assert resize_factor.dtype == torch.float64 and resize_factor.numel() == B
+    if active is not None:
+        assert active.dtype == torch.uint8 and active.numel() == B and active.is_cuda
+    if jet_mask:
+        assert jet_lut is not None and jet_lut.dtype == torch.uint8 and jet_lut.numel() == 768 and jet_lut.is_cuda
+    _ev = _begin()
+    _lib.check(_frame_crop(_ptr(frame_ptrs), _ptr(dims), _ptr(state), _ptr(active), c_int(B), c_int(n_mod),
+                           ctypes.c_uint(jet_mask), ctypes.c_double(factor), c_int(out_sz), _ptr(jet_lut), _ptr(out),
+                           _ptr(out_u8), _ptr(resize_factor), _stream()), "mmt_frame_crop")
+    _count(1, "frame_crop", _ev)
+    return out, out_u8, resize_factor
+
+
+def track_update(pred_cxcywh, resize_factor, dims, state, search_size, margin=10.0, log=None, active=None):
+    """state <- clip_box(map_box_back(pred * search_size / resize_factor)) in place (mmt_track_update)."""
+    _need_cuda(pred_cxcywh, resize_factor, dims, state)
+    B = state.shape[0]
+    assert pred_cxcywh.dtype == torch.float32 and pred_cxcywh.numel() == 4 * B and pred_cxcywh.is_contiguous()
+    assert state.dtype == torch.float64 and state.is_contiguous() and resize_factor.dtype == torch.float64
+    assert dims.dtype == torch.int32 and dims.is_contiguous() and dims.shape[0] >= B
+    if log is not None:
+        assert log.dtype == torch.float64 and log.numel() == 4 * B and log.is_contiguous() and log.is_cuda
+    _ev = _begin()
+    _lib.check(_track_update(_ptr(pred_cxcywh), _ptr(resize_factor), _ptr(dims), _ptr(state), _ptr(log), _ptr(active),
+                             c_int(B), c_int(search_size), ctypes.c_double(margin), _stream()), "mmt_track_update")
+    _count(1, "track_update", _ev)
+    return state

@@ -1,0 +1,158 @@
+"""GPU parity of the device-side frame path (csrc/frames.cu through the C ABI, mmt_b200/frames.py) against
+oracle/frame_oracle.py and the fixture produced by the UNMODIFIED reference functions (tests/golden/frames_rgbt.npz):
+uint8 crops bit-exact, normalised fp32 crops bit-exact, float64 tracker state exactly equal, and a closed-loop
+multi-frame run of BatchedTracker against the reference's per-sequence host loop restated with the oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frame_oracle as FO
+from oracle import gen_golden_frames as GG
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(GG.os.path.join(GG.GOLDEN, "frames_rgbt.npz"))
+N_CASES = int(GOLD["n_cases"])
+T_FACTOR, T_SIZE, S_FACTOR, S_SIZE = [float(v) for v in GOLD["params"]]
+
+
+def _upload(images):
+    """list of uint8 HWC arrays -> (device buffers kept alive, int64 pointer table, int32 dims table)."""
+    bufs = [torch.from_numpy(np.ascontiguousarray(im)).cuda() for im in images]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    dims = torch.tensor([[im.shape[0], im.shape[1], im.shape[1] * 3] for im in images], dtype=torch.int32, device="cuda")
+    return bufs, ptrs, dims
+
+
+def test_crops_bit_exact_against_reference_fixture(built_lib):
+    """All fixture cases as ONE batch (B = 8 sequences with different frame sizes, 2 modalities)."""
+    from mmt_b200 import ops, frames
+    vis, inf = zip(*[GG.case_frames(ci) for ci in range(N_CASES)])
+    bufs, ptrs, dims = _upload(list(vis) + list(inf))
+    state = torch.tensor(np.stack([GOLD[f"c{ci}_box"] for ci in range(N_CASES)]), device="cuda")
+    lut = frames.jet_lut_tensor("cuda")
+    for name, factor, size in (("template", T_FACTOR, int(T_SIZE)), ("search", S_FACTOR, int(S_SIZE))):
+        u8 = torch.empty((2, N_CASES, size, size, 3), dtype=torch.uint8, device="cuda")
+        out, _, rf = ops.frame_crop(ptrs, dims, state, factor, size, 2, jet_mask=0b10, jet_lut=lut, out_u8=u8,
+                                    out=torch.empty((2, N_CASES, 3, size, size), device="cuda"))
+        torch.cuda.synchronize()
+        u8, out, rf = u8.cpu().numpy(), out.cpu().numpy(), rf.cpu().numpy()
+        for ci in range(N_CASES):
+            assert rf[ci] == float(GOLD[f"c{ci}_{name}_rf"])
+            for m, tag in ((0, "v"), (1, "i")):
+                assert GG.sha(u8[m, ci]) == str(GOLD[f"c{ci}_{name}_u8_{tag}_sha"]), (ci, name, tag, "uint8 crop")
+                assert GG.sha(out[m, ci]) == str(GOLD[f"c{ci}_{name}_{tag}_sha"]), (ci, name, tag, "normalised crop")
+            if ci in GG.FULL_CASES:
+                assert np.array_equal(u8[0, ci], GOLD[f"c{ci}_{name}_u8_v"])
+                assert np.array_equal(u8[1, ci], GOLD[f"c{ci}_{name}_u8_i"])
+
+
+def test_crop_random_boxes_match_oracle(built_lib):
+    """Seeded boxes all over (and partly outside) frames of odd sizes, several output sizes; active mask honoured."""
+    from mmt_b200 import ops
+    rng = np.random.default_rng(3)
+    B = 12
+    images, boxes = [], []
+    for b in range(B):
+        H, W = int(rng.integers(40, 300)), int(rng.integers(40, 400))
+        images.append(rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+        w, h = rng.uniform(8, W), rng.uniform(8, H)
+        boxes.append([rng.uniform(-0.3 * w, W - 0.7 * w), rng.uniform(-0.3 * h, H - 0.7 * h), w, h])
+    bufs, ptrs, dims = _upload(images)
+    state = torch.tensor(np.array(boxes, dtype=np.float64), device="cuda")
+    for factor, size in ((2.0, 128), (4.5, 288), (5.0, 320), (1.3, 37)):
+        u8 = torch.full((1, B, size, size, 3), 7, dtype=torch.uint8, device="cuda")
+        active = torch.ones(B, dtype=torch.uint8, device="cuda")
+        active[3] = 0
+        _, _, rf = ops.frame_crop(ptrs, dims, state, factor, size, 1, out_u8=u8, active=active)
+        got = u8.cpu().numpy()[0]
+        for b in range(B):
+            if b == 3:
+                assert (got[b] == 7).all()                     # inactive sequence untouched
+                continue
+            want, wrf = FO.sample_target(images[b], boxes[b], factor, size)
+            assert np.array_equal(got[b], want), (b, factor, size)
+            assert rf[b].item() == wrf
+
+
+def test_track_update_matches_reference_fixture(built_lib):
+    from mmt_b200 import ops
+    for ci in range(N_CASES):
+        H, W = GG.CASES[ci][0], GG.CASES[ci][1]
+        preds = GOLD[f"c{ci}_pred_boxes"]
+        n = preds.shape[0]
+        state = torch.tensor(np.tile(GOLD[f"c{ci}_box"], (n, 1)), device="cuda")
+        rf = torch.full((n,), float(GOLD[f"c{ci}_search_rf"]), dtype=torch.float64, device="cuda")
+        dims = torch.tensor([[H, W, W * 3]] * n, dtype=torch.int32, device="cuda")
+        log = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
+        active = torch.ones(n, dtype=torch.uint8, device="cuda")
+        active[n - 1] = 0
+        ops.track_update(torch.from_numpy(preds).cuda(), rf, dims, state, int(S_SIZE), 10.0, log=log, active=active)
+        got = state.cpu().numpy()
+        assert np.array_equal(got[:n - 1], GOLD[f"c{ci}_next_states"][:n - 1])     # float64, exactly
+        assert np.array_equal(got[n - 1], GOLD[f"c{ci}_box"])                       # inactive: state kept
+        assert np.array_equal(log.cpu().numpy(), got)
+
+
+def _video(rng, H, W, T):
+    """A drifting textured scene: every frame differs, so stale crops would be caught."""
+    base = rng.integers(0, 256, (H + 2 * T, W + 2 * T, 3), dtype=np.uint8)
+    return [np.ascontiguousarray(base[t:t + H, 2 * t // 2:2 * t // 2 + W]) for t in range(T)]
+
+
+@pytest.mark.parametrize("variant,use_cache", [("mixformer_vit_rgbt_shared", False), ("mixformer_vit_rgbt_shared", True),
+                                               ("asymmetric_shared_ce", False), ("mixformer_vit", False)])
+def test_batched_tracker_closed_loop_matches_host_loop(built_lib, variant, use_cache):
+    """6 frames x 3 sequences (different frame sizes) with an online-template update at frame 4: BatchedTracker's
+    float64 states must EQUAL those of the reference's per-sequence loop (asymmetric_shared_ce.py:74-111) restated
+    with the oracle crops and the same network, frame after frame."""
+    from mmt_b200 import synthetic, frames
+    model, cfg = synthetic.make_model(variant, 0, sharpen=True)
+    model = model.cuda()
+    n_mod = 1 if variant == "mixformer_vit" else 2
+    params = types.SimpleNamespace(template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE)
+    rng = np.random.default_rng(11)
+    sizes = [(240, 320), (200, 260), (301, 333)]
+    T, B = 6, len(sizes)
+    vids = [[_video(rng, H, W, T) for _ in range(n_mod)] for (H, W) in sizes]          # [b][m][t]
+    init = np.array([[100.0, 80.0, 60.0, 50.0], [20.5, 30.25, 90.0, 40.0], [150.0, 150.0, 33.0, 71.0]])
+    frames_at = lambda t: [[vids[b][m][t] for m in range(n_mod)] if n_mod > 1 else vids[b][0][t] for b in range(B)]
+
+    trk = frames.BatchedTracker(model, params, update_intervals=[4], n_mod=n_mod, use_template_cache=use_cache)
+    trk.initialize(frames_at(0), init)
+    for t in range(1, T):
+        trk.track(frames_at(t))
+    got = trk.results()
+    assert got.shape == (T, B, 4)
+
+    # host loop, sequence by sequence through the oracle; the network itself is the same CUDA model, called on the
+    # batch of oracle crops
+    def crops(t, states, factor, size):
+        per_mod = []
+        for m in range(n_mod):
+            arr = []
+            for b in range(B):
+                c, rf = FO.sample_target(vids[b][m][t], states[b], factor, size)
+                arr.append(FO.normalize(FO.apply_jet(c) if m == 1 else c))
+            per_mod.append(torch.from_numpy(np.stack(arr)).cuda())
+        rfs = [size / FO.crop_geometry(states[b], factor, *sizes[b])[0] for b in range(B)]
+        return (per_mod if n_mod > 1 else per_mod[0]), rfs
+
+    states = [list(map(float, init[b])) for b in range(B)]
+    template, _ = crops(0, states, params.template_factor, params.template_size)
+    online = template
+    want = [np.array(states)]
+    for t in range(1, T):
+        search, rfs = crops(t, states, params.search_factor, params.search_size)
+        _, coords = model(template, online, search)
+        pred = coords.view(-1, 4).cpu().numpy()
+        states = [FO.update_state(states[b], pred[b], rfs[b], params.search_size, *sizes[b], margin=10) for b in range(B)]
+        if t % 4 == 0:
+            online, _ = crops(t, states, params.template_factor, params.template_size)
+        want.append(np.array(states, dtype=np.float64))
+    want = np.stack(want)
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    assert not np.array_equal(got[1], got[T - 1])              # the boxes actually moved

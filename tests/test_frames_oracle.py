@@ -1,0 +1,97 @@
+"""CPU: the frame-side oracle (oracle/frame_oracle.py) against
+  * the fixture written by oracle/gen_golden_frames.py from the UNMODIFIED reference functions (sample_target,
+    Preprocessor_Multimodal, MixFormer.track + clip_box) - tests/golden/frames_rgbt.npz,
+  * OpenCV itself (the reference's third-party resize / colour-map implementation) where cv2 is importable,
+and the host logic of mmt_b200/frames.py that needs no GPU."""
+import numpy as np
+import pytest
+
+from oracle import frame_oracle as FO
+from oracle import gen_golden_frames as GG
+
+GOLD = np.load(GG.os.path.join(GG.GOLDEN, "frames_rgbt.npz"))
+N_CASES = int(GOLD["n_cases"])
+T_FACTOR, T_SIZE, S_FACTOR, S_SIZE = [float(v) for v in GOLD["params"]]
+
+
+def test_fixture_frames_regenerate():
+    for ci in range(N_CASES):
+        im_v, im_i = GG.case_frames(ci)
+        assert GG.sha(im_v) == str(GOLD[f"c{ci}_im_v_sha"]) and GG.sha(im_i) == str(GOLD[f"c{ci}_im_i_sha"]), \
+            "seeded frames differ from the ones the fixture was generated with: rerun oracle/gen_golden_frames.py"
+
+
+@pytest.mark.parametrize("ci", range(N_CASES))
+def test_oracle_crops_match_reference_fixture(ci):
+    im_v, im_i = GG.case_frames(ci)
+    box = GOLD[f"c{ci}_box"].tolist()
+    for name, factor, size in (("template", T_FACTOR, int(T_SIZE)), ("search", S_FACTOR, int(S_SIZE))):
+        cv_, rf = FO.sample_target(im_v, box, factor, size)
+        ci_, _ = FO.sample_target(im_i, box, factor, size)
+        ci_jet = FO.apply_jet(ci_)
+        assert rf == float(GOLD[f"c{ci}_{name}_rf"])
+        assert GG.sha(cv_) == str(GOLD[f"c{ci}_{name}_u8_v_sha"])          # bit-exact byte work
+        assert GG.sha(ci_jet) == str(GOLD[f"c{ci}_{name}_u8_i_sha"])
+        nv, ni = FO.process_multimodal(cv_, ci_)
+        assert GG.sha(nv) == str(GOLD[f"c{ci}_{name}_v_sha"]) and GG.sha(ni) == str(GOLD[f"c{ci}_{name}_i_sha"])
+        if ci in GG.FULL_CASES:
+            assert np.array_equal(cv_, GOLD[f"c{ci}_{name}_u8_v"]) and np.array_equal(ci_jet, GOLD[f"c{ci}_{name}_u8_i"])
+
+
+@pytest.mark.parametrize("ci", range(N_CASES))
+def test_oracle_state_update_matches_reference_fixture(ci):
+    H, W = GG.CASES[ci][0], GG.CASES[ci][1]
+    box = GOLD[f"c{ci}_box"].tolist()
+    rf = float(GOLD[f"c{ci}_search_rf"])
+    for p, want in zip(GOLD[f"c{ci}_pred_boxes"], GOLD[f"c{ci}_next_states"]):
+        got = FO.update_state(box, p, rf, int(S_SIZE), H, W, margin=10)
+        assert [float(v) for v in got] == want.tolist()                    # float64 arithmetic restated exactly
+
+
+def test_crop_geometry_edge_cases():
+    # round-half-even of the window origin, the dropped last column, overhang on every side
+    crop_sz, x1, y1, xa, xb, ya, yb = FO.crop_geometry([10.0, 10.0, 5.0, 5.0], 1.0, 100, 100)
+    assert (crop_sz, x1, y1) == (5, 10, 10) and (xa, xb, ya, yb) == (10, 15, 10, 15)
+    crop_sz, x1, *_ = FO.crop_geometry([10.5, 10.0, 4.0, 4.0], 1.0, 100, 100)       # 12.5 - 2 = 10.5 -> 10 (even)
+    assert x1 == 10
+    crop_sz, x1, *_ = FO.crop_geometry([11.5, 10.0, 4.0, 4.0], 1.0, 100, 100)       # 11.5 -> 12 (even)
+    assert x1 == 12
+    crop_sz, x1, y1, xa, xb, ya, yb = FO.crop_geometry([90.0, 90.0, 10.0, 10.0], 1.0, 100, 100)
+    assert (x1 + crop_sz, xb, yb) == (100, 99, 99)                                    # window reaches W: column W-1 dropped
+    crop_sz, x1, y1, xa, xb, ya, yb = FO.crop_geometry([5.0, 5.0, 30.0, 30.0], 2.0, 50, 40)
+    assert (xa, ya) == (0, 0) and xb == 39 and yb == 49 and crop_sz == 60
+    with pytest.raises(Exception):
+        FO.crop_geometry([5.0, 5.0, 0.0, 3.0], 2.0, 50, 40)
+
+
+def test_resize_and_colormap_match_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        sh, sw = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        dh, dw = [(128, 128), (288, 288), (192, 192), (int(rng.integers(1, 200)), int(rng.integers(1, 200)))][t % 4]
+        if t % 7 == 0:
+            sh, sw = 2 * dh, 2 * dw              # cv::resize switches to its 2x2 area path here; the values coincide
+        if t % 11 == 0:
+            sh, sw = dh, dw
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(src, (dw, dh)), FO.resize_linear_u8(src, dh, dw)), (sh, sw, dh, dw)
+    g = rng.integers(0, 256, (50, 60, 3), dtype=np.uint8)
+    assert np.array_equal(cv2.cvtColor(g, cv2.COLOR_BGR2GRAY), FO.bgr2gray_u8(g))
+    assert np.array_equal(cv2.applyColorMap(g, cv2.COLORMAP_JET), FO.apply_jet(g))
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)[0]
+    assert np.array_equal(lut, FO.jet_lut())
+
+
+def test_product_lut_equals_oracle_lut(built_lib):
+    from mmt_b200 import frames
+    assert frames.JET_LUT_HEX == FO._JET_HEX
+    assert np.array_equal(frames.jet_lut_tensor("cpu").numpy().reshape(256, 3), FO.jet_lut())
+
+
+def test_batched_tracker_refuses_cpu_models(built_lib):
+    import torch
+    from mmt_b200 import frames
+    net = torch.nn.Linear(2, 2)
+    with pytest.raises(NotImplementedError):
+        frames.BatchedTracker(net, params=None)
