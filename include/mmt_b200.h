@@ -222,7 +222,8 @@ int mmt_prroi_fwd(const float* feat, const float* rois, float* out, int R, int C
  * ((x/255) - mean) / std as fp32 [n_mod][B][3][S][S] (out) and/or the uint8 crop [n_mod][B][S][S][3] (out_u8).
  * resize_factor_dev (DEVICE float64 [B], may be NULL) receives out_sz / crop side.  active_dev (DEVICE uint8 [B] or NULL)
  * selects the sequences that are processed; the others keep their previous outputs.  A degenerate box (side < 1, where
- * the reference raises "Too small bounding box.") yields an all-zero crop.
+ * the reference raises "Too small bounding box.") yields an all-zero crop.  workspace: caller-allocated, see
+ * mmt_frame_crop_workspace_bytes; two launches (window geometry + tap tables, then the gather).
  * Replaces sample_target lib/train/data/processing_utils.py:15-83 (cv.copyMakeBorder + cv.resize) and
  * Preprocessor_Multimodal.process lib/test/tracker/tracker_utils.py:37-48 (cv2.applyColorMap, normalisation, H2D).
  *
@@ -234,7 +235,9 @@ int mmt_prroi_fwd(const float* feat, const float* rois, float* out, int R, int C
 int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const double* state_dev,
                    const unsigned char* active_dev, int B, int n_mod, unsigned jet_mask, double factor, int out_sz,
                    const unsigned char* jet_lut_dev, float* out, unsigned char* out_u8, double* resize_factor_dev,
-                   void* stream);
+                   void* workspace, long long workspace_bytes, void* stream);
+/* bytes of 16-byte aligned DEVICE workspace mmt_frame_crop needs (per-image window geometry + resize tap tables) */
+long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz);
 int mmt_track_update(const float* pred_cxcywh, const double* resize_factor_dev, const int* dims_dev, double* state_dev,
                      double* log_dev, const unsigned char* active_dev, int B, int search_size, double margin,
                      void* stream);

@@ -34,7 +34,7 @@ def declared_symbols() -> list[str]:
     with open(HEADER_PATH) as f:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(mmt_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(mmt_[a-z0-9_]+)\s*\(", text)))
 
 
 def check(status: int, what: str) -> None:

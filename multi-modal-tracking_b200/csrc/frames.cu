@@ -13,7 +13,9 @@
 // fixed-point INTER_LINEAR for uint8 (resize.cpp: 11-bit coefficient pairs from float32 fractions, horizontal pass in
 // int32, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2), BGR2GRAY is its 15-bit fixed point; the
 // uint8 crops therefore equal the reference's byte for byte (tests/test_frames_gpu.py, oracle/frame_oracle.py).
-// Both are HBM/L2-bound gathers: one thread per output pixel, the three channel planes written coalesced.
+// Both are HBM/L2-bound gathers.  The crop runs as two launches: a tiny one per image for the window geometry and the
+// S tap entries (all the float64 work), then the gather - thread = output column, 8 rows per block, the three channel
+// planes written coalesced.
 #include "common.cuh"
 #include "../../include/mmt_b200.h"
 
@@ -31,7 +33,8 @@ __device__ inline void crop_geometry(const double* st, double factor, int H, int
   const double x = st[0], y = st[1], w = st[2], h = st[3];
   const double side = __dmul_rn(sqrt(__dmul_rn(w, h)), factor);
   const double c = ceil(side);
-  g.valid = (c >= 1.0 && c < 1.0e6) ? 1 : 0;        // "Too small bounding box." in the reference; NaN fails both tests
+  g.valid = (c >= 1.0 && c < 65536.0) ? 1 : 0;      // "Too small bounding box." in the reference; NaN fails both tests
+                                                    // (tap tables hold 16-bit source indices)
   g.crop_sz = g.valid ? static_cast<int>(c) : 1;
   const double half = __dmul_rn(static_cast<double>(g.crop_sz), 0.5);
   g.x1 = static_cast<int>(rint(__dsub_rn(__dadd_rn(x, __dmul_rn(0.5, w)), half)));    // round(): half to even
@@ -67,13 +70,17 @@ __device__ __forceinline__ void linear_tap(int d, double scale, int ssize, bool 
   w1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
-__global__ void __launch_bounds__(256)
-frame_crop_kernel(const uint8_t* const* __restrict__ frames, const int* __restrict__ dims,
-                  const double* __restrict__ state, const uint8_t* __restrict__ active, int B, unsigned jet_mask,
-                  double factor, int S, const uint8_t* __restrict__ jet_lut, float* __restrict__ out,
-                  uint8_t* __restrict__ out_u8, double* __restrict__ resize_factor) {
-  const int img = blockIdx.y;              // m * B + b
-  const int b = img % B, m = img / B;
+// Tap tables: entry d of image `img` = {s0 | s1 << 16, w0 | w1 << 16} for the horizontal pass followed by the same
+// for the vertical pass (the crop is square and both passes share the scale, but their border rules differ).
+struct TapPair { uint32_t hs, hw, vs, vw; };
+
+// one block per image: window geometry (thread 0), then the S tap entries
+__global__ void __launch_bounds__(128)
+frame_geom_kernel(const int* __restrict__ dims, const double* __restrict__ state, const uint8_t* __restrict__ active,
+                  int B, double factor, int S, CropGeom* __restrict__ geom, TapPair* __restrict__ taps,
+                  double* __restrict__ resize_factor) {
+  const int img = blockIdx.x;
+  const int b = img % B;
   if (active && !active[b]) return;
   __shared__ CropGeom g;
   if (threadIdx.x == 0) {
@@ -81,49 +88,89 @@ frame_crop_kernel(const uint8_t* const* __restrict__ frames, const int* __restri
     g.pitch = dims[3 * img + 2];
     const double inv = __ddiv_rn(static_cast<double>(S), static_cast<double>(g.crop_sz));
     g.scale = __ddiv_rn(1.0, inv);
-    if (m == 0 && blockIdx.x == 0 && resize_factor) resize_factor[b] = inv;       // output_sz / crop_sz
+    if (img < B && resize_factor) resize_factor[b] = inv;       // output_sz / crop_sz
+    geom[img] = g;
   }
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= S * S) return;
-  const int dy = pix / S, dx = pix - dy * S;
-  int sx0, sx1, a0, a1, sy0, sy1, b0, b1;
-  linear_tap(dx, g.scale, g.crop_sz, true, sx0, sx1, a0, a1);
-  linear_tap(dy, g.scale, g.crop_sz, false, sy0, sy1, b0, b1);
+  for (int d = threadIdx.x; d < S; d += blockDim.x) {
+    int s0, s1, w0, w1;
+    TapPair t;
+    linear_tap(d, g.scale, g.crop_sz, true, s0, s1, w0, w1);
+    t.hs = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(s1) << 16);
+    t.hw = static_cast<uint32_t>(w0) | (static_cast<uint32_t>(w1) << 16);
+    linear_tap(d, g.scale, g.crop_sz, false, s0, s1, w0, w1);
+    t.vs = static_cast<uint32_t>(s0) | (static_cast<uint32_t>(s1) << 16);
+    t.vw = static_cast<uint32_t>(w0) | (static_cast<uint32_t>(w1) << 16);
+    taps[static_cast<size_t>(img) * S + d] = t;
+  }
+}
+
+// grid (row groups, images); a block walks ROWS output rows, thread = output column (strided when S > blockDim)
+constexpr int CROP_ROWS = 8;
+
+__global__ void __launch_bounds__(512)
+frame_crop_kernel(const uint8_t* const* __restrict__ frames, const CropGeom* __restrict__ geom,
+                  const TapPair* __restrict__ taps, const uint8_t* __restrict__ active, int B, unsigned jet_mask, int S,
+                  const uint8_t* __restrict__ jet_lut, float* __restrict__ out, uint8_t* __restrict__ out_u8) {
+  const int img = blockIdx.y;              // m * B + b
+  const int b = img % B, m = img / B;
+  if (active && !active[b]) return;
+  __shared__ uint8_t lut[768];
+  const bool jet = (jet_mask >> m) & 1u;
+  if (jet) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = jet_lut[i];
+    __syncthreads();
+  }
+  const CropGeom g = geom[img];
+  const TapPair* __restrict__ tp = taps + static_cast<size_t>(img) * S;
   const uint8_t* __restrict__ base = frames[img];
-  // frame coordinates of the four taps; outside [xa,xb) x [ya,yb) the padded crop is zero
-  const int fx0 = g.x1 + sx0, fx1 = g.x1 + sx1, fy0 = g.y1 + sy0, fy1 = g.y1 + sy1;
-  const bool vx0 = g.valid && fx0 >= g.xa && fx0 < g.xb, vx1 = g.valid && fx1 >= g.xa && fx1 < g.xb;
-  const bool vy0 = fy0 >= g.ya && fy0 < g.yb, vy1 = fy1 >= g.ya && fy1 < g.yb;
-  const uint8_t* r0 = base + static_cast<size_t>(fy0) * g.pitch;
-  const uint8_t* r1 = base + static_cast<size_t>(fy1) * g.pitch;
-  int v[3];
+  const int row0 = blockIdx.x * CROP_ROWS;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  for (int dx = threadIdx.x; dx < S; dx += blockDim.x) {
+    const TapPair tx = tp[dx];
+    const int sx0 = tx.hs & 0xffff, sx1 = tx.hs >> 16, a0 = tx.hw & 0xffff, a1 = tx.hw >> 16;
+    // frame columns of the two taps; outside [xa,xb) the padded crop is zero
+    const int fx0 = g.x1 + sx0, fx1 = g.x1 + sx1;
+    const bool vx0 = g.valid && fx0 >= g.xa && fx0 < g.xb, vx1 = g.valid && fx1 >= g.xa && fx1 < g.xb;
+#pragma unroll 2
+    for (int r = 0; r < CROP_ROWS; ++r) {
+      const int dy = row0 + r;
+      if (dy >= S) break;
+      const TapPair ty = tp[dy];             // warp-uniform
+      const int sy0 = ty.vs & 0xffff, sy1 = ty.vs >> 16, b0 = ty.vw & 0xffff, b1 = ty.vw >> 16;
+      const int fy0 = g.y1 + sy0, fy1 = g.y1 + sy1;
+      const bool vy0 = fy0 >= g.ya && fy0 < g.yb, vy1 = fy1 >= g.ya && fy1 < g.yb;
+      const uint8_t* r0 = base + static_cast<size_t>(fy0) * g.pitch;
+      const uint8_t* r1 = base + static_cast<size_t>(fy1) * g.pitch;
+      int v[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int p00 = (vy0 && vx0) ? r0[fx0 * 3 + c] : 0, p01 = (vy0 && vx1) ? r0[fx1 * 3 + c] : 0;
-    const int p10 = (vy1 && vx0) ? r1[fx0 * 3 + c] : 0, p11 = (vy1 && vx1) ? r1[fx1 * 3 + c] : 0;
-    const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
-    v[c] = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-    v[c] = min(max(v[c], 0), 255);
-  }
-  if ((jet_mask >> m) & 1u) {
-    // cv2.applyColorMap on a 3-channel image: BGR2GRAY with channel 0 in the 'B' slot, then the 256-entry table
-    const int gray = (v[0] * 3735 + v[1] * 19235 + v[2] * 9798 + (1 << 14)) >> 15;
-    const uint8_t* e = jet_lut + 3 * gray;
-    v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
-  }
-  if (out_u8) {
-    uint8_t* o = out_u8 + (static_cast<size_t>(img) * S * S + pix) * 3;
-    o[0] = static_cast<uint8_t>(v[0]); o[1] = static_cast<uint8_t>(v[1]); o[2] = static_cast<uint8_t>(v[2]);
-  }
-  if (out) {
-    // ((x / 255) - mean) / std, fp32 true divisions (tracker_utils.py:44-47)
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
-    float* o = out + static_cast<size_t>(img) * 3 * S * S + pix;
+      for (int c = 0; c < 3; ++c) {
+        const int p00 = (vy0 && vx0) ? r0[fx0 * 3 + c] : 0, p01 = (vy0 && vx1) ? r0[fx1 * 3 + c] : 0;
+        const int p10 = (vy1 && vx0) ? r1[fx0 * 3 + c] : 0, p11 = (vy1 && vx1) ? r1[fx1 * 3 + c] : 0;
+        const int S0 = p00 * a0 + p01 * a1, S1 = p10 * a0 + p11 * a1;
+        v[c] = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        v[c] = min(max(v[c], 0), 255);
+      }
+      if (jet) {
+        // cv2.applyColorMap on a 3-channel image: BGR2GRAY with channel 0 in the 'B' slot, then the 256-entry table
+        const int gray = (v[0] * 3735 + v[1] * 19235 + v[2] * 9798 + (1 << 14)) >> 15;
+        const uint8_t* e = lut + 3 * gray;
+        v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+      }
+      const int pix = dy * S + dx;
+      if (out_u8) {
+        uint8_t* o = out_u8 + (static_cast<size_t>(img) * S * S + pix) * 3;
+        o[0] = static_cast<uint8_t>(v[0]); o[1] = static_cast<uint8_t>(v[1]); o[2] = static_cast<uint8_t>(v[2]);
+      }
+      if (out) {
+        // ((x / 255) - mean) / std, fp32 true divisions (tracker_utils.py:44-47)
+        float* o = out + static_cast<size_t>(img) * 3 * S * S + pix;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      o[static_cast<size_t>(c) * S * S] =
-          __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[c]), 255.0f), mean[c]), sd[c]);
+        for (int c = 0; c < 3; ++c)
+          o[static_cast<size_t>(c) * S * S] =
+              __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[c]), 255.0f), mean[c]), sd[c]);
+      }
+    }
   }
 }
 
@@ -167,18 +214,31 @@ __global__ void track_update_kernel(const float* __restrict__ pred, const double
 
 }  // namespace mmt
 
+extern "C" long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz) {
+  return static_cast<long long>(B) * n_mod * (sizeof(mmt::CropGeom) + sizeof(mmt::TapPair) * static_cast<long long>(out_sz));
+}
+
 extern "C" int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const double* state_dev,
                               const unsigned char* active_dev, int B, int n_mod, unsigned jet_mask, double factor,
                               int out_sz, const unsigned char* jet_lut_dev, float* out, unsigned char* out_u8,
-                              double* resize_factor_dev, void* stream) {
-  MMT_CHECK_ARG(frames_dev && dims_dev && state_dev && (out || out_u8));
+                              double* resize_factor_dev, void* workspace, long long workspace_bytes, void* stream) {
+  MMT_CHECK_ARG(frames_dev && dims_dev && state_dev && (out || out_u8) && workspace);
   MMT_CHECK_ARG(B > 0 && n_mod > 0 && n_mod <= 8 && out_sz > 0 && out_sz <= 4096 && factor > 0.0);
   MMT_CHECK_ARG(static_cast<long long>(B) * n_mod <= 65535);
   MMT_CHECK_ARG(jet_mask == 0u || jet_lut_dev != nullptr);
-  const dim3 grid(mmt::cdiv(out_sz * out_sz, 256), B * n_mod);
-  mmt::frame_crop_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint8_t* const*>(frames_dev), dims_dev, state_dev, active_dev, B, jet_mask, factor, out_sz,
-      jet_lut_dev, out, out_u8, resize_factor_dev);
+  MMT_CHECK_ARG(workspace_bytes >= mmt_frame_crop_workspace_bytes(B, n_mod, out_sz));
+  MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0);
+  const int n_img = B * n_mod;
+  // workspace: [n_img] TapPair tables of out_sz entries (16-byte records), then [n_img] CropGeom
+  mmt::TapPair* taps = reinterpret_cast<mmt::TapPair*>(workspace);
+  mmt::CropGeom* geom = reinterpret_cast<mmt::CropGeom*>(taps + static_cast<size_t>(n_img) * out_sz);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mmt::frame_geom_kernel<<<n_img, 128, 0, st>>>(dims_dev, state_dev, active_dev, B, factor, out_sz, geom, taps,
+                                                resize_factor_dev);
+  const dim3 grid(mmt::cdiv(out_sz, mmt::CROP_ROWS), n_img);
+  const int threads = out_sz <= 512 ? ((out_sz + 31) / 32) * 32 : 256;     // thread = output column
+  mmt::frame_crop_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint8_t* const*>(frames_dev), geom, taps,
+                                                   active_dev, B, jet_mask, out_sz, jet_lut_dev, out, out_u8);
   MMT_RETURN_LAST_ERROR();
 }
 

@@ -248,19 +248,20 @@ class ForwardEngine:
         return self._tiles[key]
 
     # ------------------------------------------------------------------------------------------ backbone
-    def _embed_buf(self, rows):
-        """A-operand buffer of the token-embedding GEMM: one row per token, in final token order."""
-        return self._buf(rows, "patches", (rows, 3 * 256), self.act)
+    def _embed_buf(self, rows, lane=0):
+        """A-operand buffer of the token-embedding GEMM: one row per token, in final token order (one per concurrent
+        stream `lane`)."""
+        return self._buf((rows, lane), "patches", (rows, 3 * 256), self.act)
 
     def _stage_tokens(self, bb, img, buf, tok_off, tok_per_seq):
         """Write the embedding-GEMM input rows of the crops `img` [n,3,S,S] at rows b*tok_per_seq + tok_off + patch.
         MixViT: the 16x16 patch matrix.  (ConvMAE: the conv stem's output, engine_online.ConvMAEOnlineEngine.)"""
         ops.patchify(img, buf, tok_off, tok_per_seq)
 
-    def _embed(self, bb, B, imgs_t, imgs_ot, imgs_s, x):
+    def _embed(self, bb, B, imgs_t, imgs_ot, imgs_s, x, lane=0):
         """Embed the three crops of `B` sequences into x [B*N0, dim] (rows b*N0 + [t | ot | s]): staging of the GEMM
         input in token order, then ONE GEMM with bias and the positional table in the epilogue."""
-        buf = self._embed_buf(x.shape[0])
+        buf = self._embed_buf(x.shape[0], lane)
         n_t = self.gt * self.gt
         self._stage_tokens(bb, imgs_t, buf, 0, self.N0)
         self._stage_tokens(bb, imgs_ot, buf, n_t, self.N0)
@@ -324,26 +325,38 @@ class ForwardEngine:
 
     def _run_backbone(self, bb, x, nseq, tag, stacked):
         """All blocks on x [nseq*N0, dim]; returns the search-token rows [nseq*Ls0, dim] in `act` dtype."""
+        st = self._backbone_begin(x, nseq, stacked)
+        for i in range(len(bb["blocks"])):
+            self._backbone_block(bb, st, i, nseq, tag)
+        return self._backbone_end(st, nseq, tag)
+
+    def _backbone_begin(self, x, nseq, stacked):
         N, Ls = self.N0, self.Ls0
-        cross = stacked and self.variant in CROSS_MODAL
-        per_ln = stacked and self.variant in PER_MODALITY_LN
-        gidx = None
+        st = dict(x=x, N=N, Ls=Ls, gidx=None, ce_i=0, cross=stacked and self.variant in CROSS_MODAL,
+                  per_ln=stacked and self.variant in PER_MODALITY_LN)
         if self.ce_loc:
             key = ("gidx0", nseq, Ls)
             gidx = self._ws.get(key)        # global search-token indices 0..Ls-1 per sequence (float32 like the
             if gidx is None:                # reference, asymmetric_shared_ce.py:397-399); built once per batch size
                 gidx = torch.arange(Ls, device=self.dev, dtype=torch.float32).repeat(nseq, 1).contiguous()
                 self._ws[key] = gidx
+            st["gidx"] = gidx
             self.aux.update(ce_scores=[], ce_keep=[], ce_removed=[])
-        ce_i = 0
-        for i, blk in enumerate(bb["blocks"]):
-            ce_keep = None
-            if i in self.ce_loc:
-                ce_keep = self.ce_keep[ce_i]
-                ce_i += 1
-                if not ce_keep < 1:
-                    ce_keep = None
-            x, N, Ls, gidx = self._block(blk, x, nseq, N, Ls, (nseq * N // 2) if per_ln else 0, cross, tag, ce_keep, gidx)
+        return st
+
+    def _backbone_block(self, bb, st, i, nseq, tag):
+        ce_keep = None
+        if i in self.ce_loc:
+            ce_keep = self.ce_keep[st["ce_i"]]
+            st["ce_i"] += 1
+            if not ce_keep < 1:
+                ce_keep = None
+        st["x"], st["N"], st["Ls"], st["gidx"] = self._block(
+            bb["blocks"][i], st["x"], nseq, st["N"], st["Ls"], (nseq * st["N"] // 2) if st["per_ln"] else 0, st["cross"],
+            tag, ce_keep, st["gidx"])
+
+    def _backbone_end(self, st, nseq, tag):
+        x, N, Ls, gidx = st["x"], st["N"], st["Ls"], st["gidx"]
         self._last_x = (x, N)            # residual stream after the last block (template rows: engine_online.py)
         feat = self._buf(tag, "search_rows", (nseq * self.Ls0, self.dim), self.act)
         if Ls != self.Ls0:
@@ -351,6 +364,61 @@ class ForwardEngine:
         else:
             ops.copy_rows(x, N, self.Lt, Ls, nseq, feat)
         return feat
+
+    # Two independent backbones (mixformer_vit_rgbt: backbone_v / backbone_i never exchange data before the fusion,
+    # mixformer.py:379-380) run on TWO CUDA streams, launches interleaved block by block.  Every kernel of the chain
+    # leaves SMs idle in its last partial wave (the persistent GEMMs: 339 tiles on 74 CTA pairs = 4.58 waves) and the
+    # LayerNorm / attention kernels leave the tensor pipe idle altogether; with a second, independent chain queued
+    # those SMs pick up the other modality's CTAs at once.  Same kernels on the same data: results are bit-identical
+    # to the sequential order.  MMT_TWO_STREAMS=0 restores it (A/B measurements).
+    def _lanes(self):
+        if getattr(self, "_side", None) is None:
+            import os
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
+            self._two_streams = os.environ.get("MMT_TWO_STREAMS", "1") != "0"
+        return self._side
+
+    def set_two_streams(self, on: bool):
+        """Developer / bench switch: run the two modality backbones of mixformer_vit_rgbt sequentially on one stream
+        (per-launch CUDA-event brackets are only meaningful without a concurrent second chain)."""
+        self._lanes()
+        self._two_streams = bool(on)
+        return self
+
+    def _run_two_backbones(self, B, t, ot, s, x, wait):
+        M1 = B * self.N0
+        side = self._lanes()
+        main = torch.cuda.current_stream()
+        if not self._two_streams:
+            feats = []
+            for m in range(2):
+                xm = x[m * M1:(m + 1) * M1]
+                wait(m)
+                self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm)
+                feats.append(self._run_backbone(self.bbs[m], xm, B, ("bb", B, m), False))
+            return feats
+        self._fork_ev.record(main)
+        side.wait_event(self._fork_ev)
+        lanes = (main, side)
+        sts = []
+        for m in range(2):
+            with torch.cuda.stream(lanes[m]):
+                xm = x[m * M1:(m + 1) * M1]
+                wait(m)
+                self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm, lane=m)
+                sts.append(self._backbone_begin(xm, B, False))
+        for i in range(self.depth):
+            for m in range(2):
+                with torch.cuda.stream(lanes[m]):
+                    self._backbone_block(self.bbs[m], sts[m], i, B, ("bb", B, m))
+        feats = []
+        for m in range(2):
+            with torch.cuda.stream(lanes[m]):
+                feats.append(self._backbone_end(sts[m], B, ("bb", B, m)))
+        self._join_ev.record(side)
+        main.wait_event(self._join_ev)
+        return feats
 
     # ------------------------------------------------------------------------------------------ fusion
     def _conv1x1_gn(self, a, p, B, HW, out, tag, out_seq_rows=0, out_row_off=0):
@@ -512,14 +580,8 @@ class ForwardEngine:
         B = s[0].shape[0]
         M1 = B * self.N0
         x = self._buf(B, "x", (2 * M1, self.dim), torch.float32)
-        if self.variant == "mixformer_vit_rgbt":      # two independent streams (mixformer.py:379-380)
-            feats = []
-            for m in range(2):
-                xm = x[m * M1:(m + 1) * M1]
-                wait(m)
-                self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm)
-                feats.append(self._run_backbone(self.bbs[m], xm, B, ("bb", B, m), False))
-            sv, si = feats
+        if self.variant == "mixformer_vit_rgbt":      # two independent backbones (mixformer.py:379-380)
+            sv, si = self._run_two_backbones(B, t, ot, s, x, wait)
         else:                                          # batch-stacked modalities, shared weights
             for m in range(2):
                 wait(m)

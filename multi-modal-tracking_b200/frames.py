@@ -45,41 +45,72 @@ def jet_lut_tensor(device) -> torch.Tensor:
 class FrameUploader:
     """Raw uint8 frames of one step -> one pinned staging buffer -> one H2D copy on a side stream.
 
-    Frame sizes are fixed per (sequence, modality), so the device pointer table and the (H, W, pitch) table are built
-    once; two staging/device buffer pairs alternate so that the upload of step t+1 overlaps the forward of step t."""
+    Every image slot (modality-major, image m*B + b) owns a fixed-capacity region, so the device pointer table is built
+    once; the (H, W, pitch) table changes only when a slot switches to a sequence of another frame size.  Two
+    staging/device buffer pairs alternate so that the upload of step t+1 overlaps the forward of step t."""
 
-    def __init__(self, shapes, device):
-        # shapes: list over images (modality-major, image m*B + b) of (H, W)
+    def __init__(self, shapes, device, capacity_hw=None):
+        # shapes: list over images of (H, W); capacity_hw: (H, W) every slot must be able to hold (default: its own)
         self.device = device
-        offs, total = [], 0
-        for (H, W) in shapes:
-            offs.append(total)
-            total += (H * W * 3 + 255) // 256 * 256          # 256-byte aligned frames
-        self.shapes, self.offsets, self.total = list(shapes), offs, total
-        self.pinned = [torch.empty(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.dev = [torch.empty(total, dtype=torch.uint8, device=device) for _ in range(2)]
-        self.ptrs = [torch.tensor([d.data_ptr() + o for o in offs], dtype=torch.int64, device=device) for d in self.dev]
-        self.dims = torch.tensor([[H, W, W * 3] for (H, W) in shapes], dtype=torch.int32, device=device)
+        self.shapes = [tuple(int(v) for v in sh) for sh in shapes]
+        cap = [max(H * W, (capacity_hw[0] * capacity_hw[1]) if capacity_hw else 0) * 3 for (H, W) in self.shapes]
+        self.capacity = [(c + 255) // 256 * 256 for c in cap]          # 256-byte aligned regions
+        self.offsets = [int(v) for v in np.concatenate([[0], np.cumsum(self.capacity)[:-1]])]
+        self.total = int(sum(self.capacity))
+        self.pinned = [torch.empty(self.total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.dev = [torch.empty(self.total, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.ptrs = [torch.tensor([d.data_ptr() + o for o in self.offsets], dtype=torch.int64, device=device)
+                     for d in self.dev]
+        self._dims_host = torch.tensor([[H, W, W * 3] for (H, W) in self.shapes], dtype=torch.int32).pin_memory()
+        self.dims = self._dims_host.to(device)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         self._used = [False, False]
         self.k = 0
         self.h2d_bytes = 0
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        n_thr = min(8, os.cpu_count() or 1)
+        self._pool = ThreadPoolExecutor(max_workers=n_thr) if n_thr > 1 else None
 
-    def upload(self, images) -> int:
-        """images: list over images (same order as `shapes`) of uint8 HWC numpy arrays. Returns the buffer index; the
-        CURRENT stream waits for the copy."""
+    def set_shape(self, idx: int, H: int, W: int) -> None:
+        """Image slot idx now carries H x W frames (a new sequence entered the slot).  Stream-ordered on the current
+        stream: kernels already enqueued keep seeing the old table."""
+        if H * W * 3 > self.capacity[idx]:
+            raise ValueError(f"frame {H}x{W} exceeds the slot capacity ({self.capacity[idx]} bytes): construct the "
+                             "uploader with a larger capacity_hw")
+        self.shapes[idx] = (int(H), int(W))
+        # a fresh pinned row per update: the asynchronous copy below may still be reading the previous one
+        row = torch.tensor([[H, W, W * 3]], dtype=torch.int32).pin_memory()
+        self._dims_host[idx] = row[0]
+        self.dims[idx:idx + 1].copy_(row, non_blocking=True)
+        self._keep = getattr(self, "_keep", [])[-64:] + [row]
+
+    def upload(self, images, skip=None) -> int:
+        """images: list over image slots of uint8 HWC numpy arrays (entries of slots listed in `skip` are ignored and
+        may be None).  Returns the buffer index; the CURRENT stream waits for the copy."""
         k = self.k
         self.k ^= 1
         if self._used[k]:
             self.copied[k].synchronize()                      # host may overwrite the staging buffer
         host = self.pinned[k].numpy()
-        for im, (H, W), o in zip(images, self.shapes, self.offsets):
+        nbytes = 0
+        jobs = []
+        for i, (im, (H, W), o) in enumerate(zip(images, self.shapes, self.offsets)):
+            if skip is not None and skip[i]:
+                continue
             if im.shape != (H, W, 3) or im.dtype != np.uint8:
-                raise ValueError(f"frame of shape {im.shape}/{im.dtype}, expected uint8 {(H, W, 3)} (frame sizes are fixed "
-                                 "per sequence)")
-            host[o:o + H * W * 3] = im.reshape(-1)
+                raise ValueError(f"frame of shape {im.shape}/{im.dtype}, expected uint8 {(H, W, 3)} for image slot {i}")
+            jobs.append((host[o:o + H * W * 3].reshape(H, W, 3), im))
+            nbytes += H * W * 3
+        # the packing memcpy (~1 MB per frame) is the host-side cost of a step: numpy releases the GIL while copying,
+        # so a few threads bring it well under the device step time
+        if len(jobs) >= 8 and self._pool is not None:
+            list(self._pool.map(lambda j: np.copyto(j[0], j[1]), jobs))
+        else:
+            for dst, src in jobs:
+                np.copyto(dst, src)
         with torch.cuda.stream(self.copy_stream):
             if self._used[k]:
                 self.copy_stream.wait_event(self.consumed[k])  # kernels of two steps ago have read the device buffer
@@ -87,7 +118,7 @@ class FrameUploader:
             self.copied[k].record(self.copy_stream)
         torch.cuda.current_stream().wait_event(self.copied[k])
         self._used[k] = True
-        self.h2d_bytes = self.total
+        self.h2d_bytes = nbytes
         return k
 
     def release(self, k: int) -> None:
@@ -127,7 +158,7 @@ class BatchedTracker:
     def _flatten(self, frames):
         """list over sequences of [im_v, im_i] (or a single array) -> modality-major list of images."""
         if self.n_mod == 1:
-            return [f if isinstance(f, np.ndarray) else f[0] for f in frames]
+            return [f if (f is None or isinstance(f, np.ndarray)) else f[0] for f in frames]
         return [f[m] for m in range(self.n_mod) for f in frames]
 
     def _model_args(self, buf):
@@ -138,22 +169,23 @@ class BatchedTracker:
                        active=active, out=out, resize_factor=rf)
 
     # ------------------------------------------------------------------ protocol
-    def initialize(self, frames, init_boxes):
+    def initialize(self, frames, init_boxes, capacity_hw=None):
         """frames: list over B sequences of [image_v, image_i] uint8 HWC RGB arrays (RGB-only: one array each);
         init_boxes: [B, 4] (x, y, w, h).  asymmetric_shared_ce.py:50-72: template = online template = crop at the
-        initial box, state = initial box."""
+        initial box, state = initial box.  capacity_hw: largest (H, W) a slot may be switched to by reset_slot()."""
         p = self.params
         B = self.B = len(frames)
         imgs = self._flatten(frames)
-        self.up = FrameUploader([im.shape[:2] for im in imgs], self.device)
+        self.up = FrameUploader([im.shape[:2] for im in imgs], self.device, capacity_hw)
         dev = self.device
         self.state = torch.tensor(np.asarray(init_boxes, dtype=np.float64).reshape(B, 4), device=dev)
         self.rf = torch.empty(B, dtype=torch.float64, device=dev)
         self.template = torch.empty((self.n_mod, B, 3, p.template_size, p.template_size), dtype=torch.float32, device=dev)
         self.online_template = torch.empty_like(self.template)
-        self.search = torch.empty((self.n_mod, B, 3, p.search_size, p.search_size), dtype=torch.float32, device=dev)
+        self.search = torch.zeros((self.n_mod, B, 3, p.search_size, p.search_size), dtype=torch.float32, device=dev)
         self.log = torch.zeros((self.capacity, B, 4), dtype=torch.float64, device=dev)
-        self.frame_id = 0
+        self.frame_id = 0                       # steps taken (row of the result table)
+        self.frame_ids = np.zeros(B, dtype=np.int64)     # per slot: frames tracked since its sequence was initialised
         k = self.up.upload(imgs)
         self._crop(k, float(p.template_factor), int(p.template_size), self.template)
         self.up.release(k)
@@ -162,17 +194,48 @@ class BatchedTracker:
         if self.use_cache:
             self.network.cache_templates(self._model_args(self.template), self._model_args(self.online_template))
 
+    def reset_slot(self, b, frames_b, init_box):
+        """Slot b starts a NEW sequence (the batched harness refills finished slots): state = init box, template =
+        online template = crop of the given first frame; the other slots are untouched.  The slot's next track() frame
+        is frame 1 of the new sequence; its initial box is written to the current row of the result table."""
+        if self.use_cache:
+            raise NotImplementedError("reset_slot with use_template_cache: the template cache is per batch")
+        p = self.params
+        imgs = [frames_b] if self.n_mod == 1 else list(frames_b)
+        for m, im in enumerate(imgs):
+            self.up.set_shape(m * self.B + b, im.shape[0], im.shape[1])
+        one = torch.zeros(self.B, dtype=torch.uint8)
+        one[b] = 1
+        act = one.to(self.device)
+        self.state[b:b + 1].copy_(torch.tensor(np.asarray(init_box, dtype=np.float64).reshape(1, 4)))
+        full = [None] * (self.n_mod * self.B)
+        skip = [True] * (self.n_mod * self.B)
+        for m, im in enumerate(imgs):
+            full[m * self.B + b], skip[m * self.B + b] = im, False
+        k = self.up.upload(full, skip=skip)
+        self._crop(k, float(p.template_factor), int(p.template_size), self.template, active=act)
+        self.up.release(k)
+        self.online_template[:, b].copy_(self.template[:, b])
+        self.log[self.frame_id, b].copy_(self.state[b])
+        self.frame_ids[b] = 0
+
     def track(self, frames, active=None):
-        """One frame for every sequence; returns nothing and does not synchronise (read `results()`)."""
+        """One frame for every (active) sequence; returns nothing and does not synchronise (read `results()`).
+        active: optional [B] bools - inactive slots keep state, crops and templates (their `frames` entry may be None)."""
         p = self.params
         self.frame_id += 1
         if self.frame_id >= self.log.shape[0]:
             self.log = torch.cat([self.log, torch.zeros_like(self.log)], 0)
-        act = None
+        act, act_np, skip = None, None, None
         if active is not None:
-            act = torch.from_numpy(np.ascontiguousarray(np.asarray(active, dtype=np.uint8))).to(self.device,
-                                                                                                  non_blocking=True)
-        k = self.up.upload(self._flatten(frames))
+            act_np = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
+            act = torch.from_numpy(act_np).to(self.device)
+            skip = [not act_np[i % self.B] for i in range(self.n_mod * self.B)]
+        live = np.ones(self.B, dtype=bool) if act_np is None else act_np.astype(bool)
+        self.frame_ids[live] += 1
+        imgs = self._flatten([f if f is not None else [None] * self.n_mod for f in frames]) if active is not None \
+            else self._flatten(frames)
+        k = self.up.upload(imgs, skip=skip)
         self._crop(k, float(p.search_factor), int(p.search_size), self.search, active=act, rf=self.rf)
         with torch.inference_mode():
             if self.use_cache:
@@ -182,15 +245,19 @@ class BatchedTracker:
                                          self._model_args(self.search))
         ops.track_update(coords.view(-1, 4), self.rf, self.up.dims, self.state, int(p.search_size), self.MARGIN,
                          log=self.log[self.frame_id], active=act)
+        # online-template refresh: `for update_i in update_intervals: if frame_id % update_i == 0` per slot
+        # (asymmetric_shared_ce.py:106-114), from the frame just tracked at the NEW state
         updated = False
         for interval in self.update_intervals:
-            if self.frame_id % interval == 0:
-                self._crop(k, float(p.template_factor), int(p.template_size), self.online_template, active=act)
+            due = live & (self.frame_ids % interval == 0)
+            if due.any():
+                due_dev = None if due.all() else torch.from_numpy(due.astype(np.uint8)).to(self.device)
+                self._crop(k, float(p.template_factor), int(p.template_size), self.online_template, active=due_dev)
                 updated = True
         self.up.release(k)
         if updated and self.use_cache:
             self.network.cache_templates(self._model_args(self.template), self._model_args(self.online_template))
 
     def results(self) -> np.ndarray:
-        """[frame_id + 1, B, 4] float64 boxes (x, y, w, h) per frame; row 0 is the initial box.  Synchronises."""
+        """[frame_id + 1, B, 4] float64 boxes (x, y, w, h) per step; row 0 is the initial box.  Synchronises."""
         return self.log[:self.frame_id + 1].cpu().numpy()

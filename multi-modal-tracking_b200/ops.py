@@ -457,6 +457,9 @@ def prroi_pool(feat, rois, ph, pw, spatial_scale, channels_last=False, out=None)
 
 
 _frame_crop = _lib.fn("mmt_frame_crop")
+_frame_crop_ws = _lib.lib.mmt_frame_crop_workspace_bytes
+_frame_crop_ws.restype = ctypes.c_longlong
+_FRAME_WS = {}
 _track_update = _lib.fn("mmt_track_update")
 
 
@@ -484,11 +487,17 @@ def frame_crop(frame_ptrs, dims, state, factor, out_sz, n_mod, jet_mask=0, jet_l
         assert active.dtype == torch.uint8 and active.numel() == B and active.is_cuda
     if jet_mask:
         assert jet_lut is not None and jet_lut.dtype == torch.uint8 and jet_lut.numel() == 768 and jet_lut.is_cuda
+    need = int(_frame_crop_ws(c_int(B), c_int(n_mod), c_int(out_sz)))
+    key = (state.device, torch.cuda.current_stream().cuda_stream)
+    ws = _FRAME_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _FRAME_WS[key] = torch.empty(need, dtype=torch.uint8, device=state.device)   # stream-ordered reuse
     _ev = _begin()
     _lib.check(_frame_crop(_ptr(frame_ptrs), _ptr(dims), _ptr(state), _ptr(active), c_int(B), c_int(n_mod),
                            ctypes.c_uint(jet_mask), ctypes.c_double(factor), c_int(out_sz), _ptr(jet_lut), _ptr(out),
-                           _ptr(out_u8), _ptr(resize_factor), _stream()), "mmt_frame_crop")
-    _count(1, "frame_crop", _ev)
+                           _ptr(out_u8), _ptr(resize_factor), _ptr(ws), ctypes.c_longlong(ws.numel()), _stream()),
+               "mmt_frame_crop")
+    _count(2, "frame_crop", _ev)
     return out, out_u8, resize_factor
 
 

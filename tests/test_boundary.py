@@ -125,6 +125,6 @@ def test_training_and_cpu_are_refused():
     x = synthetic.make_inputs("mixformer_vit", cfg, 1)
     with pytest.raises(NotImplementedError):
         model(*x)                                   # no CPU fallback
-    cfg2 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "RGBT_Fusion_Cat"})
-    with pytest.raises(KeyError):
+    cfg2 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "Attention_Fusion_512"})
+    with pytest.raises(KeyError):                   # a fusion class no shipped YAML names: refused loudly, no fallback
         builders.build_mixformer_vit_rgbt(cfg2)

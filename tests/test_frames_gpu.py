@@ -156,3 +156,53 @@ def test_batched_tracker_closed_loop_matches_host_loop(built_lib, variant, use_c
     want = np.stack(want)
     assert np.array_equal(got, want), np.abs(got - want).max()
     assert not np.array_equal(got[1], got[T - 1])              # the boxes actually moved
+
+
+def test_run_sequences_refills_slots_and_writes_reference_files(built_lib, tmp_path):
+    """5 sequences of different lengths / frame sizes through 2 slots: every sequence's boxes must equal the reference's
+    one-sequence-at-a-time loop (oracle crops, same network, batch 1), whatever shared the batch with it; the result
+    files have the reference's format (running.py:31-37: int boxes, tab separated; "%f" times)."""
+    from mmt_b200 import synthetic, evaluation
+    variant = "mixformer_vit_rgbt_shared"
+    model, cfg = synthetic.make_model(variant, 0, sharpen=True)
+    model = model.cuda()
+    params = types.SimpleNamespace(template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE)
+    rng = np.random.default_rng(21)
+    shapes = [(120, 160, 4), (200, 150, 7), (90, 90, 1), (160, 240, 5), (131, 177, 6)]      # H, W, frames
+    seqs = []
+    for i, (H, W, T) in enumerate(shapes):
+        vids = [_video(rng, H, W, T), _video(rng, H, W, T)]
+        box = [W * 0.3, H * 0.25, W * 0.3, H * 0.4]
+        seqs.append(evaluation.SequenceSpec(f"seq{i}", "synthetic", list(zip(vids[0], vids[1])), box))
+    got = evaluation.run_sequences(model, params, seqs, results_dir=str(tmp_path), batch=2, update_intervals=[3], n_mod=2)
+    assert sorted(got) == [f"seq{i}" for i in range(5)]
+
+    for s in seqs:
+        H, W = s.frames[0][0].shape[:2]
+        state = list(s.init_bbox)
+
+        def crop(t, state, factor, size):
+            arr = []
+            for m in range(2):
+                c, _ = FO.sample_target(s.frames[t][m], state, factor, size)
+                arr.append(torch.from_numpy(FO.normalize(FO.apply_jet(c) if m == 1 else c)[None]).cuda())
+            return arr, size / FO.crop_geometry(state, factor, H, W)[0]
+
+        template, _ = crop(0, state, params.template_factor, params.template_size)
+        online = template
+        want = [list(state)]
+        for t in range(1, len(s.frames)):
+            search, rf = crop(t, state, params.search_factor, params.search_size)
+            _, coords = model(template, online, search)
+            state = FO.update_state(state, coords.view(-1, 4).cpu().numpy()[0], rf, params.search_size, H, W, margin=10)
+            if t % 3 == 0:
+                online, _ = crop(t, state, params.template_factor, params.template_size)
+            want.append([float(v) for v in state])
+        want = np.array(want, dtype=np.float64)
+        assert got[s.name].shape == want.shape
+        assert np.array_equal(got[s.name], want), (s.name, np.abs(got[s.name] - want).max())
+        saved = np.loadtxt(tmp_path / "synthetic" / f"{s.name}.txt", delimiter="\t", ndmin=2)
+        assert np.array_equal(saved, want.astype(int))
+        times = np.loadtxt(tmp_path / "synthetic" / f"{s.name}_time.txt", ndmin=1)
+        assert times.shape == (len(s.frames),) and (times >= 0).all()

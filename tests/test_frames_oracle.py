@@ -95,3 +95,25 @@ def test_batched_tracker_refuses_cpu_models(built_lib):
     net = torch.nn.Linear(2, 2)
     with pytest.raises(NotImplementedError):
         frames.BatchedTracker(net, params=None)
+
+
+def test_result_files_have_the_reference_format(built_lib, tmp_path):
+    """running.py:31-37: boxes `np.array(data).astype(int)` saved with delimiter tab / "%d"; times with "%f"."""
+    from mmt_b200 import evaluation
+    seq = evaluation.SequenceSpec("car1", "lasher", ["a.jpg", "b.jpg"], [1, 2, 3, 4])
+    boxes = np.array([[10.9, 20.2, 30.5, 40.0], [-0.7, 5.99, 7.0, 8.49]])
+    evaluation.save_tracker_output(str(tmp_path), seq, boxes, [0.25, 0.5])
+    text = (tmp_path / "lasher" / "car1.txt").read_text()
+    assert text == "10\t20\t30\t40\n0\t5\t7\t8\n"                       # astype(int) truncates toward zero
+    assert (tmp_path / "lasher" / "car1_time.txt").read_text() == "0.250000\n0.500000\n"
+
+
+def test_sequence_spec_from_reference_and_empty_shard(built_lib):
+    import types
+    from mmt_b200 import evaluation
+    ref_seq = types.SimpleNamespace(name="s", dataset="d", frames=[("v0", "i0"), ("v1", "i1")],
+                                    init_info=lambda: {"init_bbox": ([1.0, 2.0, 3.0, 4.0], [1.5, 2.5, 3.5, 4.5])})
+    spec = evaluation.SequenceSpec.from_reference(ref_seq)
+    assert spec.init_bbox == [1.0, 2.0, 3.0, 4.0] and spec.frames == ref_seq.frames        # the RGB box, as the tracker uses
+    # rank 3 of 4 owns nothing of a 2-sequence dataset: returns without touching the (absent) GPU
+    assert evaluation.run_sequences(None, None, [spec, spec], rank=3, world_size=4) == {}
