@@ -78,9 +78,20 @@ struct TapPair { uint32_t hs, hw, vs, vw; };
 __global__ void __launch_bounds__(128)
 frame_geom_kernel(const int* __restrict__ dims, const double* __restrict__ state, const uint8_t* __restrict__ active,
                   int B, double factor, int S, CropGeom* __restrict__ geom, TapPair* __restrict__ taps,
-                  double* __restrict__ resize_factor) {
+                  double* __restrict__ resize_factor, const uint8_t* __restrict__ jet_lut, float* __restrict__ norm_tab) {
   const int img = blockIdx.x;
   const int b = img % B;
+  if (img == 0) {
+    // ((v / 255) - mean) / std for every byte value, fp32 true divisions (tracker_utils.py:44-47): [c][v], followed by
+    // the same through the JET table ([c][gray]) - the gather kernel turns two divisions per value into one lookup
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8, v = i & 255;
+      norm_tab[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), mean[c]), sd[c]);
+      if (jet_lut)
+        norm_tab[768 + i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(jet_lut[3 * v + c]), 255.0f), mean[c]), sd[c]);
+    }
+  }
   if (active && !active[b]) return;
   __shared__ CropGeom g;
   if (threadIdx.x == 0) {
@@ -111,21 +122,23 @@ constexpr int CROP_ROWS = 8;
 __global__ void __launch_bounds__(512)
 frame_crop_kernel(const uint8_t* const* __restrict__ frames, const CropGeom* __restrict__ geom,
                   const TapPair* __restrict__ taps, const uint8_t* __restrict__ active, int B, unsigned jet_mask, int S,
-                  const uint8_t* __restrict__ jet_lut, float* __restrict__ out, uint8_t* __restrict__ out_u8) {
+                  const uint8_t* __restrict__ jet_lut, const float* __restrict__ norm_tab, float* __restrict__ out,
+                  uint8_t* __restrict__ out_u8) {
   const int img = blockIdx.y;              // m * B + b
   const int b = img % B, m = img / B;
   if (active && !active[b]) return;
   __shared__ uint8_t lut[768];
+  __shared__ float ntab[768];              // this image's value -> normalised fp32 table ([c][v] or [c][gray])
   const bool jet = (jet_mask >> m) & 1u;
-  if (jet) {
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = jet_lut[i];
-    __syncthreads();
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    ntab[i] = norm_tab[(jet ? 768 : 0) + i];
+    if (jet) lut[i] = jet_lut[i];
   }
+  __syncthreads();
   const CropGeom g = geom[img];
   const TapPair* __restrict__ tp = taps + static_cast<size_t>(img) * S;
   const uint8_t* __restrict__ base = frames[img];
   const int row0 = blockIdx.x * CROP_ROWS;
-  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
   for (int dx = threadIdx.x; dx < S; dx += blockDim.x) {
     const TapPair tx = tp[dx];
     const int sx0 = tx.hs & 0xffff, sx1 = tx.hs >> 16, a0 = tx.hw & 0xffff, a1 = tx.hw >> 16;
@@ -151,11 +164,15 @@ frame_crop_kernel(const uint8_t* const* __restrict__ frames, const CropGeom* __r
         v[c] = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
         v[c] = min(max(v[c], 0), 255);
       }
+      int key[3] = {v[0], v[1], v[2]};       // index into the normalisation table per channel
       if (jet) {
         // cv2.applyColorMap on a 3-channel image: BGR2GRAY with channel 0 in the 'B' slot, then the 256-entry table
         const int gray = (v[0] * 3735 + v[1] * 19235 + v[2] * 9798 + (1 << 14)) >> 15;
-        const uint8_t* e = lut + 3 * gray;
-        v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+        key[0] = key[1] = key[2] = gray;
+        if (out_u8) {
+          const uint8_t* e = lut + 3 * gray;
+          v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+        }
       }
       const int pix = dy * S + dx;
       if (out_u8) {
@@ -163,12 +180,9 @@ frame_crop_kernel(const uint8_t* const* __restrict__ frames, const CropGeom* __r
         o[0] = static_cast<uint8_t>(v[0]); o[1] = static_cast<uint8_t>(v[1]); o[2] = static_cast<uint8_t>(v[2]);
       }
       if (out) {
-        // ((x / 255) - mean) / std, fp32 true divisions (tracker_utils.py:44-47)
         float* o = out + static_cast<size_t>(img) * 3 * S * S + pix;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          o[static_cast<size_t>(c) * S * S] =
-              __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v[c]), 255.0f), mean[c]), sd[c]);
+        for (int c = 0; c < 3; ++c) o[static_cast<size_t>(c) * S * S] = ntab[c * 256 + key[c]];
       }
     }
   }
@@ -215,7 +229,8 @@ __global__ void track_update_kernel(const float* __restrict__ pred, const double
 }  // namespace mmt
 
 extern "C" long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz) {
-  return static_cast<long long>(B) * n_mod * (sizeof(mmt::CropGeom) + sizeof(mmt::TapPair) * static_cast<long long>(out_sz));
+  return static_cast<long long>(B) * n_mod * (sizeof(mmt::CropGeom) + sizeof(mmt::TapPair) * static_cast<long long>(out_sz)) +
+         2 * 768 * static_cast<long long>(sizeof(float));
 }
 
 extern "C" int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const double* state_dev,
@@ -229,16 +244,19 @@ extern "C" int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev
   MMT_CHECK_ARG(workspace_bytes >= mmt_frame_crop_workspace_bytes(B, n_mod, out_sz));
   MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0);
   const int n_img = B * n_mod;
-  // workspace: [n_img] TapPair tables of out_sz entries (16-byte records), then [n_img] CropGeom
+  // workspace: [n_img] TapPair tables of out_sz entries (16-byte records), 2 x [3][256] fp32 normalisation tables, then
+  // [n_img] CropGeom
   mmt::TapPair* taps = reinterpret_cast<mmt::TapPair*>(workspace);
-  mmt::CropGeom* geom = reinterpret_cast<mmt::CropGeom*>(taps + static_cast<size_t>(n_img) * out_sz);
+  float* norm_tab = reinterpret_cast<float*>(taps + static_cast<size_t>(n_img) * out_sz);
+  mmt::CropGeom* geom = reinterpret_cast<mmt::CropGeom*>(norm_tab + 2 * 768);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mmt::frame_geom_kernel<<<n_img, 128, 0, st>>>(dims_dev, state_dev, active_dev, B, factor, out_sz, geom, taps,
-                                                resize_factor_dev);
+                                                resize_factor_dev, jet_mask ? jet_lut_dev : nullptr, norm_tab);
   const dim3 grid(mmt::cdiv(out_sz, mmt::CROP_ROWS), n_img);
   const int threads = out_sz <= 512 ? ((out_sz + 31) / 32) * 32 : 256;     // thread = output column
   mmt::frame_crop_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint8_t* const*>(frames_dev), geom, taps,
-                                                   active_dev, B, jet_mask, out_sz, jet_lut_dev, out, out_u8);
+                                                   active_dev, B, jet_mask, out_sz, jet_lut_dev, norm_tab, out,
+                                                   out_u8);
   MMT_RETURN_LAST_ERROR();
 }
 
