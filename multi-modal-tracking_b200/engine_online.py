@@ -214,8 +214,8 @@ class ConvMAEOnlineEngine(OnlineEngine):
             st[f"blocks{stage}"] = blocks
         self.stem = st
 
-    def _embed_buf(self, rows):
-        return self._buf(rows, "pe4_in", (rows, self.dim), self.act)
+    def _embed_buf(self, rows, lane=0):
+        return self._buf((rows, lane), "pe4_in", (rows, self.dim), self.act)
 
     def _ln_act(self, x, ln, gelu, out, **remap):
         if out.dtype == torch.float32:

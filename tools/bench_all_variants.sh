@@ -1,7 +1,7 @@
 #!/bin/bash
 # Developer tool: one bench line per covered configuration (BASELINE.json configs 1-5), results into gpurun_out/variants.jsonl
 out=gpurun_out/variants.jsonl; : > $out
-run() { python bench.py --steps 20 --warmup 3 --cpu-budget 0 --no-latency "$@" 2>/dev/null | tail -1 >> $out; }
+run() { python bench.py --steps 20 --warmup 3 --cpu-budget 0 --no-latency --no-frame-path "$@" 2>/dev/null | tail -1 >> $out; }
 run --variant mixformer_vit --batch 64
 run --variant mixformer_vit_rgbt --batch 64
 run --variant mixformer_vit_rgbt_shared --batch 64
