@@ -238,6 +238,14 @@ int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const dou
                    void* workspace, long long workspace_bytes, void* stream);
 /* bytes of 16-byte aligned DEVICE workspace mmt_frame_crop needs (per-image window geometry + resize tap tables) */
 long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz);
+/*
+ * Online (SPM) trackers: score bookkeeping of the online-template candidate, per sequence:
+ *   s = sigmoid(logits[b]) (fp32); max_score[b] *= decay; take[b] = s > 0.5 && s > max_score[b]; if take: max_score[b] = s.
+ * take_dev (DEVICE uint8 [B]) is then the `active` mask of the mmt_frame_crop call that refreshes the candidate crop.
+ * Replaces MixFormerOnline.track lib/test/tracker/mixformer_convmae_online.py:99,105-113 (pred_score.item() host sync).
+ */
+int mmt_online_score_update(const float* logits, double* max_score_dev, unsigned char* take_dev,
+                            const unsigned char* active_dev, int B, double decay, void* stream);
 int mmt_track_update(const float* pred_cxcywh, const double* resize_factor_dev, const int* dims_dev, double* state_dev,
                      double* log_dev, const unsigned char* active_dev, int B, int search_size, double margin,
                      void* stream);

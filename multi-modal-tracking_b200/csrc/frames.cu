@@ -226,7 +226,34 @@ __global__ void track_update_kernel(const float* __restrict__ pred, const double
   }
 }
 
+// lib/test/tracker/mixformer_convmae_online.py:99,105-113 (same in mixformer_vit_online.py): pred_score =
+// sigmoid(logit) (fp32), max_pred_score *= decay, the online-template candidate is replaced when
+// pred_score > 0.5 and pred_score > max_pred_score.  One thread per sequence; max_score is the float64 Python float.
+__global__ void online_score_update_kernel(const float* __restrict__ logits, double* __restrict__ max_score,
+                                           uint8_t* __restrict__ take, const uint8_t* __restrict__ active, int B,
+                                           double decay) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint8_t t = 0;
+  if (!active || active[b]) {
+    const float sc = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logits[b])));      // torch.sigmoid, fp32
+    const double m = __dmul_rn(max_score[b], decay);
+    const double s = static_cast<double>(sc);
+    t = (s > 0.5 && s > m) ? 1 : 0;
+    max_score[b] = t ? s : m;
+  }
+  take[b] = t;
+}
+
 }  // namespace mmt
+
+extern "C" int mmt_online_score_update(const float* logits, double* max_score_dev, unsigned char* take_dev,
+                                       const unsigned char* active_dev, int B, double decay, void* stream) {
+  MMT_CHECK_ARG(logits && max_score_dev && take_dev && B > 0);
+  mmt::online_score_update_kernel<<<mmt::cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, max_score_dev, take_dev, active_dev, B, decay);
+  MMT_RETURN_LAST_ERROR();
+}
 
 extern "C" long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz) {
   return static_cast<long long>(B) * n_mod * (sizeof(mmt::CropGeom) + sizeof(mmt::TapPair) * static_cast<long long>(out_sz)) +

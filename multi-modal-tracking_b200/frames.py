@@ -261,3 +261,70 @@ class BatchedTracker:
     def results(self) -> np.ndarray:
         """[frame_id + 1, B, 4] float64 boxes (x, y, w, h) per step; row 0 is the initial box.  Synchronises."""
         return self.log[:self.frame_id + 1].cpu().numpy()
+
+
+class OnlineBatchedTracker(BatchedTracker):
+    """`MixFormerOnline` (lib/test/tracker/mixformer_convmae_online.py:12-140, mixformer_vit_online.py) for B sequences
+    with `online_size == 1`: every frame runs the full forward with the SPM score head; the crop at the new box becomes
+    the online-template CANDIDATE when its score beats 0.5 and the running maximum (`mmt_online_score_update` + a masked
+    `mmt_frame_crop`, no score read-back); every `update_interval` frames the candidate replaces the online template and
+    the bookkeeping restarts from the first template.  `online_size > 1` (the per-sequence `set_online`/`forward_test`
+    cache of the reference, which assumes batch 1 - mixformer_vit/mixformer.py:238) is served per sequence by the
+    model's own `set_online`/`forward_test` and is not batched here."""
+
+    def __init__(self, network, params, update_interval=200, max_score_decay=1.0, capacity=1024):
+        super().__init__(network, params, update_intervals=(), n_mod=1, use_template_cache=False, capacity=capacity)
+        self.update_interval = int(update_interval)
+        self.max_score_decay = float(max_score_decay)
+
+    def initialize(self, frames, init_boxes, capacity_hw=None):
+        super().initialize(frames, init_boxes, capacity_hw)
+        self.max_score = torch.full((self.B,), -1.0, dtype=torch.float64, device=self.device)
+        self.take = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
+        self.online_max_template = self.template.clone()
+        self.scores = torch.zeros((self.log.shape[0], self.B), dtype=torch.float32, device=self.device)
+
+    def reset_slot(self, b, frames_b, init_box):
+        super().reset_slot(b, frames_b, init_box)
+        self.max_score[b:b + 1].fill_(-1.0)
+        self.online_max_template[:, b].copy_(self.template[:, b])
+
+    def track(self, frames, active=None):
+        p = self.params
+        self.frame_id += 1
+        if self.frame_id >= self.log.shape[0]:
+            self.log = torch.cat([self.log, torch.zeros_like(self.log)], 0)
+            self.scores = torch.cat([self.scores, torch.zeros_like(self.scores)], 0)
+        act, act_np, skip = None, None, None
+        if active is not None:
+            act_np = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
+            act = torch.from_numpy(act_np).to(self.device)
+            skip = [not a for a in act_np]
+        live = np.ones(self.B, dtype=bool) if act_np is None else act_np.astype(bool)
+        self.frame_ids[live] += 1
+        k = self.up.upload(self._flatten(frames), skip=skip)
+        self._crop(k, float(p.search_factor), int(p.search_size), self.search, active=act, rf=self.rf)
+        with torch.inference_mode():
+            out, coords = self.network(self.template[0], self.online_template[0], self.search[0], run_score_head=True)
+        logits = out["pred_scores"].reshape(-1).contiguous()
+        self.scores[self.frame_id].copy_(logits)
+        ops.track_update(coords.view(-1, 4), self.rf, self.up.dims, self.state, int(p.search_size), self.MARGIN,
+                         log=self.log[self.frame_id], active=act)
+        ops.online_score_update(logits, self.max_score, self.take, self.max_score_decay, active=act)
+        self._crop(k, float(p.template_factor), int(p.template_size), self.online_max_template, active=self.take)
+        self.up.release(k)
+        due = live & (self.frame_ids % self.update_interval == 0)
+        if due.all():
+            self.online_template.copy_(self.online_max_template)
+            self.online_max_template.copy_(self.template)
+            self.max_score.fill_(-1.0)
+        else:
+            for b in np.nonzero(due)[0]:
+                b = int(b)
+                self.online_template[:, b].copy_(self.online_max_template[:, b])
+                self.online_max_template[:, b].copy_(self.template[:, b])
+                self.max_score[b:b + 1].fill_(-1.0)
+
+    def score_logits(self) -> np.ndarray:
+        """[frame_id + 1, B] raw SPM logits per step (row 0 unused).  Synchronises."""
+        return self.scores[:self.frame_id + 1].cpu().numpy()

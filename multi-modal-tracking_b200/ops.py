@@ -515,3 +515,19 @@ def track_update(pred_cxcywh, resize_factor, dims, state, search_size, margin=10
                              c_int(B), c_int(search_size), ctypes.c_double(margin), _stream()), "mmt_track_update")
     _count(1, "track_update", _ev)
     return state
+
+
+_online_score_update = _lib.fn("mmt_online_score_update")
+
+
+def online_score_update(logits, max_score, take, decay=1.0, active=None):
+    """max_score (float64 [B]) and take (uint8 [B]) updated in place from the SPM logits (mmt_online_score_update)."""
+    _need_cuda(logits, max_score, take)
+    B = max_score.numel()
+    assert logits.dtype == torch.float32 and logits.numel() == B and logits.is_contiguous()
+    assert max_score.dtype == torch.float64 and take.dtype == torch.uint8 and take.numel() == B
+    _ev = _begin()
+    _lib.check(_online_score_update(_ptr(logits), _ptr(max_score), _ptr(take), _ptr(active), c_int(B),
+                                    ctypes.c_double(decay), _stream()), "mmt_online_score_update")
+    _count(1, "online_score_update", _ev)
+    return take

@@ -189,3 +189,56 @@ def update_state(state, pred_box_f32: np.ndarray, resize_factor: float, search_s
     cx_real = cx + (cx_prev - half_side)
     cy_real = cy + (cy_prev - half_side)
     return clip_box([cx_real - 0.5 * w, cy_real - 0.5 * h, w, h], H, W, margin=margin)
+
+
+def sigmoid_f32(logit) -> float:
+    """`pred_scores.view(1).sigmoid().item()`: fp32 sigmoid widened to a Python float."""
+    x = np.float32(logit)
+    return float(np.float32(1.0) / (np.float32(1.0) + np.exp(-x, dtype=np.float32)))
+
+
+def online_score_step(max_score: float, logit, decay: float = 1.0):
+    """lib/test/tracker/mixformer_convmae_online.py:99,105-113: returns (new max_pred_score, take) where `take` means the
+    crop at the new box becomes `online_max_template`."""
+    s = sigmoid_f32(logit)
+    m = max_score * decay
+    take = s > 0.5 and s > m
+    return (s if take else m), take
+
+
+class OnlineTrackerOracle:
+    """MixFormerOnline with online_size == 1 (mixformer_convmae_online.py:62-128) for one RGB sequence; `network` is a
+    callable (template, online_template, search) -> (pred_box_f32[4] cxcywh, logit)."""
+
+    def __init__(self, network, template_factor, template_size, search_factor, search_size, update_interval,
+                 max_score_decay=1.0):
+        self.net = network
+        self.tf, self.ts, self.sf, self.ss = template_factor, template_size, search_factor, search_size
+        self.update_interval, self.decay = update_interval, max_score_decay
+
+    def _crop(self, image, state, factor, size):
+        c, rf = sample_target(image, state, factor, size)
+        return normalize(c), rf
+
+    def initialize(self, image, init_box):
+        self.template, _ = self._crop(image, list(init_box), self.tf, self.ts)
+        self.online_template = self.template
+        self.online_max_template = self.template
+        self.max_pred_score = -1.0
+        self.state = [float(v) for v in init_box]
+        self.frame_id = 0
+
+    def track(self, image):
+        H, W = image.shape[:2]
+        self.frame_id += 1
+        search, rf = self._crop(image, self.state, self.sf, self.ss)
+        pred, logit = self.net(self.template, self.online_template, search)
+        self.state = update_state(self.state, pred, rf, self.ss, H, W, margin=10)
+        self.max_pred_score, take = online_score_step(self.max_pred_score, logit, self.decay)
+        if take:
+            self.online_max_template, _ = self._crop(image, self.state, self.tf, self.ts)
+        if self.frame_id % self.update_interval == 0:
+            self.online_template = self.online_max_template
+            self.max_pred_score = -1
+            self.online_max_template = self.template
+        return self.state

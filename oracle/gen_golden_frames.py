@@ -65,6 +65,82 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def seeded_video(seed, H, W, T):
+    """A drifting textured scene (every frame differs): list of T uint8 RGB frames."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (H + 2 * T, W + 3 * T, 3), dtype=np.uint8)
+    # smooth a little so that interpolation is not pure noise
+    base = ((base.astype(np.uint16) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    return [np.ascontiguousarray(base[2 * t:2 * t + H, 3 * t:3 * t + W]) for t in range(T)]
+
+
+ONLINE = dict(seed=4242, H=200, W=260, T=13, box=(90.0, 70.0, 48.0, 36.0), update_interval=5, template_factor=2.0,
+              template_size=128, search_factor=4.5, search_size=288)
+
+
+def online_script(T):
+    """Seeded (pred box, SPM logit) per frame: the stub network's outputs.  Logits are spaced well apart (no near ties)
+    and exercise every branch: below 0.5, new maximum, lower than the running maximum, right after a commit."""
+    rng = np.random.default_rng(99)
+    preds = np.stack([rng.uniform(0.4, 0.6, T), rng.uniform(0.4, 0.6, T), rng.uniform(0.15, 0.3, T), rng.uniform(0.15, 0.3, T)], 1)
+    logits = np.array([0.0, -1.0, 0.8, 0.3, 2.0, -0.5, 1.1, -2.0, -0.2, 0.6, 3.0, 0.1, 1.7][:T], dtype=np.float32)
+    return preds.astype(np.float32), logits
+
+
+def main_online(out):
+    """One RGB sequence through the UNMODIFIED MixFormerOnline.initialize/track (lib/test/tracker/
+    mixformer_convmae_online.py:62-128, online_size 1) with a stub network; asserts OnlineTrackerOracle agrees."""
+    from lib.test.tracker import mixformer_convmae_online as trk
+    from lib.test.tracker.tracker_utils import Preprocessor_wo_mask
+    o = ONLINE
+    vid = seeded_video(o["seed"], o["H"], o["W"], o["T"])
+    preds, logits = online_script(o["T"])
+    stub = types.SimpleNamespace()
+    stub.params = types.SimpleNamespace(search_factor=o["search_factor"], search_size=o["search_size"],
+                                        template_factor=o["template_factor"], template_size=o["template_size"], vis_attn=0)
+    stub.preprocessor = Preprocessor_wo_mask()
+    stub.online_size, stub.update_interval, stub.max_score_decay = 1, o["update_interval"], 1.0
+    stub.save_all_boxes, stub.debug = False, False
+    stub.cfg = None
+    seen = []
+
+    def net(template, online_template, search, run_score_head=True):
+        t = stub.frame_id
+        seen.append((sha(template[0].numpy()), sha(online_template[0].numpy()), sha(search[0].numpy())))
+        return {"pred_boxes": torch.from_numpy(preds[t]).view(1, 1, 4), "pred_scores": torch.tensor([logits[t]])}, None
+
+    stub.network = net
+    stub.map_box_back = types.MethodType(trk.MixFormerOnline.map_box_back, stub)
+    trk.MixFormerOnline.initialize(stub, vid[0], {"init_bbox": list(o["box"])})
+    states, maxs = [list(o["box"])], [-1.0]
+    for t in range(1, o["T"]):
+        res = trk.MixFormerOnline.track(stub, vid[t])
+        states.append([float(v) for v in res["target_bbox"]])
+        maxs.append(float(stub.max_pred_score))
+    # the oracle must reproduce states, running maxima and WHICH crops were fed to the network at every frame
+    seen_o = []
+
+    def net_o(template, online_template, search):
+        t = orc.frame_id
+        seen_o.append((sha(template), sha(online_template), sha(search)))
+        return preds[t], logits[t]
+
+    orc = FO.OnlineTrackerOracle(net_o, o["template_factor"], o["template_size"], o["search_factor"], o["search_size"],
+                                 o["update_interval"])
+    orc.initialize(vid[0], o["box"])
+    for t in range(1, o["T"]):
+        st = orc.track(vid[t])
+        assert [float(v) for v in st] == states[t], (t, st, states[t])
+        assert float(orc.max_pred_score) == maxs[t], (t, orc.max_pred_score, maxs[t])
+    assert seen_o == seen
+    assert len({s[1] for s in seen}) >= 3, "the online template must actually change during the sequence"
+    out["online_states"] = np.array(states, dtype=np.float64)
+    out["online_max_scores"] = np.array(maxs, dtype=np.float64)
+    out["online_inputs_sha"] = np.array(seen)
+    out["online_video_sha"] = sha(np.stack(vid))
+    print("online tracker case: ok,", len({s[1] for s in seen}), "distinct online templates")
+
+
 FULL_CASES = (0, 2)        # cases whose uint8 crops are stored in full; the others are stored as SHA-256 digests
 
 
@@ -135,6 +211,7 @@ def main():
         for k, v in rec.items():
             out[f"c{ci}_{k}"] = v
         print(f"case {ci} ({note}): ok, search rf {rec['search_rf']:.6f}")
+    main_online(out)
     out["n_cases"] = np.int64(len(CASES))
     out["params"] = np.array([template_factor, template_size, search_factor, search_size], dtype=np.float64)
     path = os.path.join(GOLDEN, "frames_rgbt.npz")

@@ -206,3 +206,90 @@ def test_run_sequences_refills_slots_and_writes_reference_files(built_lib, tmp_p
         assert np.array_equal(saved, want.astype(int))
         times = np.loadtxt(tmp_path / "synthetic" / f"{s.name}_time.txt", ndmin=1)
         assert times.shape == (len(s.frames),) and (times >= 0).all()
+
+
+class _ScriptedOnlineNet(torch.nn.Module):
+    """Stands in for the online model: replays scripted (box, logit) pairs per sequence and records digests of the
+    crops it is given - so that the device-side bookkeeping can be compared with the reference-run fixture."""
+
+    def __init__(self, scripts):
+        super().__init__()
+        self.anchor = torch.nn.Parameter(torch.zeros(1))
+        self.scripts = scripts          # per sequence: (preds [T,4] f32, logits [T] f32)
+        self.t = 0
+        self.seen = []
+
+    def forward(self, template, online_template, search, run_score_head=True):
+        self.t += 1
+        torch.cuda.synchronize()
+        self.seen.append([(GG.sha(template[b].cpu().numpy()), GG.sha(online_template[b].cpu().numpy()),
+                           GG.sha(search[b].cpu().numpy())) for b in range(search.shape[0])])
+        boxes = torch.tensor(np.stack([p[self.t] for p, _ in self.scripts]), device="cuda").view(-1, 1, 4)
+        logits = torch.tensor(np.array([l[self.t] for _, l in self.scripts], dtype=np.float32), device="cuda")
+        return {"pred_boxes": boxes, "pred_scores": logits}, boxes
+
+
+def test_online_batched_tracker_matches_reference_fixture(built_lib):
+    """OnlineBatchedTracker (score-driven online-template candidate, periodic commit) with a scripted network: slots 0 and
+    2 replay the fixture sequence that went through the UNMODIFIED MixFormerOnline class - their float64 states and the
+    digests of every crop handed to the network must equal the fixture; slot 1 runs a different sequence / script."""
+    from mmt_b200 import frames
+    o = GG.ONLINE
+    vid = GG.seeded_video(o["seed"], o["H"], o["W"], o["T"])
+    other = GG.seeded_video(7, 150, 190, o["T"])
+    preds, logits = GG.online_script(o["T"])
+    preds2, logits2 = preds[::-1].copy(), (-logits[::-1]).copy()
+    net = _ScriptedOnlineNet([(preds, logits), (preds2, logits2), (preds, logits)]).cuda()
+    params = types.SimpleNamespace(template_factor=o["template_factor"], template_size=o["template_size"],
+                                   search_factor=o["search_factor"], search_size=o["search_size"])
+    trk = frames.OnlineBatchedTracker(net, params, update_interval=o["update_interval"])
+    trk.initialize([vid[0], other[0], vid[0]], [o["box"], (40.0, 30.0, 50.0, 60.0), o["box"]])
+    for t in range(1, o["T"]):
+        trk.track([vid[t], other[t], vid[t]])
+    got = trk.results()
+    for slot in (0, 2):
+        assert np.array_equal(got[:, slot], GOLD["online_states"])
+        assert np.array_equal(np.array([s[slot] for s in net.seen]), GOLD["online_inputs_sha"])
+    # slot 1 against the oracle loop with its own script
+    seen = []
+
+    def net_o(template, online_template, search):
+        seen.append((GG.sha(template), GG.sha(online_template), GG.sha(search)))
+        return preds2[orc.frame_id], logits2[orc.frame_id]
+
+    orc = FO.OnlineTrackerOracle(net_o, o["template_factor"], o["template_size"], o["search_factor"], o["search_size"],
+                                 o["update_interval"])
+    orc.initialize(other[0], (40.0, 30.0, 50.0, 60.0))
+    want = [[40.0, 30.0, 50.0, 60.0]] + [[float(v) for v in orc.track(other[t])] for t in range(1, o["T"])]
+    assert np.array_equal(got[:, 1], np.array(want))
+    assert [s[1] for s in net.seen] == seen
+    assert np.array_equal(trk.score_logits()[1:, 0], logits[1:])
+
+
+def test_online_batched_tracker_with_the_real_online_model(built_lib):
+    """Closed loop with mixformer_vit_online (SPM score head on the device): states equal the per-sequence oracle loop
+    driven by the same model."""
+    from mmt_b200 import synthetic, frames
+    model, cfg = synthetic.make_model("mixformer_vit_online", 0, sharpen=True)
+    model = model.cuda()
+    params = types.SimpleNamespace(template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE)
+    T = 7
+    vids = [GG.seeded_video(31, 180, 240, T), GG.seeded_video(32, 222, 201, T)]
+    init = [(80.0, 60.0, 50.0, 40.0), (30.0, 90.0, 70.0, 45.0)]
+    trk = frames.OnlineBatchedTracker(model, params, update_interval=3)
+    trk.initialize([v[0] for v in vids], init)
+    for t in range(1, T):
+        trk.track([v[t] for v in vids])
+    got, got_logits = trk.results(), trk.score_logits()
+    for b in range(2):
+        def net(template, online_template, search):
+            out, coords = model(*[torch.from_numpy(a[None]).cuda() for a in (template, online_template, search)],
+                                run_score_head=True)
+            return coords.view(-1, 4).cpu().numpy()[0], out["pred_scores"].reshape(-1).cpu().numpy()[0]
+
+        orc = FO.OnlineTrackerOracle(net, 2.0, params.template_size, 4.5, params.search_size, 3)
+        orc.initialize(vids[b][0], init[b])
+        want = [list(map(float, init[b]))] + [[float(v) for v in orc.track(vids[b][t])] for t in range(1, T)]
+        assert np.array_equal(got[:, b], np.array(want)), (b, np.abs(got[:, b] - np.array(want)).max())
+    assert np.isfinite(got_logits).all()

@@ -117,3 +117,38 @@ def test_sequence_spec_from_reference_and_empty_shard(built_lib):
     assert spec.init_bbox == [1.0, 2.0, 3.0, 4.0] and spec.frames == ref_seq.frames        # the RGB box, as the tracker uses
     # rank 3 of 4 owns nothing of a 2-sequence dataset: returns without touching the (absent) GPU
     assert evaluation.run_sequences(None, None, [spec, spec], rank=3, world_size=4) == {}
+
+
+def test_online_tracker_oracle_matches_reference_fixture():
+    """OnlineTrackerOracle against the UNMODIFIED MixFormerOnline.initialize/track run (fixture): states, running maximum
+    scores and WHICH crops reach the network at every frame (template, online template, search digests)."""
+    o = GG.ONLINE
+    vid = GG.seeded_video(o["seed"], o["H"], o["W"], o["T"])
+    assert GG.sha(np.stack(vid)) == str(GOLD["online_video_sha"])
+    preds, logits = GG.online_script(o["T"])
+    seen = []
+
+    def net(template, online_template, search):
+        t = orc.frame_id
+        seen.append((GG.sha(template), GG.sha(online_template), GG.sha(search)))
+        return preds[t], logits[t]
+
+    orc = FO.OnlineTrackerOracle(net, o["template_factor"], o["template_size"], o["search_factor"], o["search_size"],
+                                 o["update_interval"])
+    orc.initialize(vid[0], o["box"])
+    for t in range(1, o["T"]):
+        st = orc.track(vid[t])
+        assert [float(v) for v in st] == GOLD["online_states"][t].tolist()
+        assert float(orc.max_pred_score) == float(GOLD["online_max_scores"][t])
+    assert np.array_equal(np.array(seen), GOLD["online_inputs_sha"])
+
+
+def test_online_score_step_branches():
+    m, take = FO.online_score_step(-1.0, 0.0)          # sigmoid(0) = 0.5: not > 0.5
+    assert (m, take) == (-1.0, False)
+    m, take = FO.online_score_step(-1.0, 0.8)
+    assert take and abs(m - 0.6899744) < 1e-6
+    m2, take = FO.online_score_step(m, 0.3)            # 0.574 > 0.5 but below the running maximum
+    assert (m2, take) == (m, False)
+    m3, take = FO.online_score_step(m, 0.3, decay=0.5)  # the maximum decays first: 0.345 < 0.574
+    assert take and abs(m3 - 0.5744425) < 1e-6
