@@ -54,7 +54,7 @@ def test_golden_boxes_are_not_degenerate():
     """The sharpened seeded weights must give boxes away from the crop centre, otherwise the 0.5 px bound
     would hold for any implementation ('parity at random init')."""
     for f in sorted(os.listdir(GOLDEN)):
-        if "_plain_" in f or "__" in f:
+        if "_plain_" in f or "__" in f or f.startswith("frames_"):
             continue      # default-init weight set: flat maps by construction (used for the bf16 tolerances)
         g = np.load(os.path.join(GOLDEN, f))
         cxcy = g["pred_boxes"].reshape(-1, 4)[:, :2] * 288
