@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline work (rank 0, N=1)")
     ap.add_argument("--no-profile", action="store_true", help="skip per-GEMM CUDA-event bracketing")
     ap.add_argument("--no-latency", action="store_true", help="skip the bs=1 per-frame latency measurement")
+    ap.add_argument("--graph", action="store_true", help="developer A/B: replay the bs=B forward as one CUDA graph in the "
+                                                        "resident-input region")
     ap.add_argument("--no-frame-path", action="store_true", help="skip the BatchedTracker (uint8 frames in) measurement")
     ap.add_argument("--breakdown", action="store_true",
                     help="developer aid: after the timed regions, run 3 more steps with EVERY op bracketed by CUDA "
@@ -298,6 +300,8 @@ def main():
         out, coords = model(*dev_inputs)
         return runner.gather_boxes(coords.view(-1, 4))
 
+    if args.graph:
+        model.enable_cuda_graph(True)
     # L2: one step touches >= 2 x 104.7 M bf16 weights (two streams) + ~1 GB of activations, far beyond the 126 MB L2
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -313,6 +317,8 @@ def main():
         e1.record()
         barrier()
     launches = ops.LAUNCHES
+    if args.graph:
+        model.enable_cuda_graph(False)
     # ---- roofline pass: the same K steps again with every tensor-core GEMM launch bracketed by CUDA events on its
     # stream.  The two-backbone variant runs its modality chains on two concurrent streams in the headline region, where
     # brackets of one chain would include the other chain's kernels: this pass runs the chains back to back on one stream

@@ -488,6 +488,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           // staging rows are CH * 2 bytes = LPR_H 16-byte vectors; vector j of row `lane` at slot j ^ key
           // (for CH = 32 this is exactly the TMA SWIZZLE_64B pattern: 16-byte chunk ^ ((row >> 1) & 3))
           constexpr int KD_H = 8 / LPR_H;
+          if (ep.dbg_flags & 8) {
+            // experiment: no shared-memory staging at all - thread == row, CH bf16 = CH/8 16-byte stores per thread
+            const int grow = grow_of(lrow0 + lane);
+            if (grow >= 0) {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + static_cast<size_t>(grow) * ep.ldo + nb);
+#pragma unroll
+              for (int j = 0; j < LPR_H; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                o[j] = w;
+              }
+            }
+            continue;
+          }
           const bool tma_out = CH == 32 && ep.tma_store && !cv.enabled;
           if (tma_out) {                       // the previous chunk's bulk store must have read the staging tile
             if (lane == 0) bulk_wait_read_all();
