@@ -149,6 +149,87 @@ __global__ void msda_bimodal_kernel(const T* __restrict__ value, const float* __
   store_vec<T>(o + static_cast<size_t>(HW) * M * D, acc, 2);
 }
 
+// bf16 fast path of the fused bimodal op for P = 4 (2 levels x 4 points = 8 samples): EIGHT lanes per (b, pos, head).
+// Lane j of a group owns sample j's scalar work (logit, offset, pixel coordinates) and channels [8j, 8j + 8) of the
+// head: the per-sample scalars travel by width-8 shuffles, every corner fetch is one 16-byte load per lane (a 128-byte
+// row segment per group), and a warp covers four heads - a quarter of the instructions of the warp-per-head mapping
+// above.  Arithmetic and summation order per channel are the same as in msda_bimodal_kernel (bit-identical results).
+__device__ __forceinline__ void acc_bf16x8(float (&r)[8], float w, const uint4& v) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    const float2 f = __bfloat1622float2(h);
+    r[2 * i] = fmaf(w, f.x, r[2 * i]);
+    r[2 * i + 1] = fmaf(w, f.y, r[2 * i + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+msda_bimodal_bf16_p4_kernel(const bf16* __restrict__ value, const float* __restrict__ offw, int ldo_w,
+                            bf16* __restrict__ out, int B, int H, int W, int M) {
+  constexpr int D = 64, P = 4, NS = 8;
+  const int HW = H * W;
+  const size_t total = static_cast<size_t>(B) * HW * M;
+  size_t grp = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3;
+  const int gl = threadIdx.x & 7;
+  const bool live = grp < total;
+  if (!live) grp = total - 1;                 // keep the whole warp in the shuffles
+  const int m = grp % M;
+  const size_t bp = grp / M;
+  const int pos = bp % HW;
+  const int b = bp / HW;
+  const int py = pos / W, px = pos % W;
+  const float* row = offw + bp * ldo_w;
+  const float logit = __ldg(row + M * 2 * P * 2 + m * NS + gl);
+  const float2 off = __ldg(reinterpret_cast<const float2*>(row + m * (NS * 2)) + gl);
+  float mx = logit;
+#pragma unroll
+  for (int o = 1; o < NS; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, NS));
+  const float e = expf(logit - mx);
+  float den = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) den += __shfl_sync(0xffffffffu, e, i, NS);     // same order as the sequential sum
+  const float a_own = e * (1.f / den);
+  const float ref_x = (px + 0.5f) / W, ref_y = (py + 0.5f) / H;
+  const float lx = ref_x + off.x / W, ly = ref_y + off.y / H;
+  const float h_own = ly * H - 0.5f, w_own = lx * W - 0.5f;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int pix_stride = M * D;
+#pragma unroll
+  for (int sidx = 0; sidx < NS; ++sidx) {
+    const float h_im = __shfl_sync(0xffffffffu, h_own, sidx, NS);
+    const float w_im = __shfl_sync(0xffffffffu, w_own, sidx, NS);
+    const float a = __shfl_sync(0xffffffffu, a_own, sidx, NS);
+    if (!(h_im > -1.f && w_im > -1.f && h_im < H && w_im < W)) continue;
+    const bf16* vbase = value + (static_cast<size_t>(b) * 2 * HW + (sidx / P) * HW) * pix_stride + m * D + gl * 8;
+    const int h_low = static_cast<int>(floorf(h_im)), w_low = static_cast<int>(floorf(w_im));
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = 0.f;
+    auto corner = [&](int y, int x, float wgt) {
+      acc_bf16x8(r, wgt, __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(y * W + x) * pix_stride)));
+    };
+    if (h_low >= 0 && w_low >= 0) corner(h_low, w_low, hh * hw);
+    if (h_low >= 0 && w_high <= W - 1) corner(h_low, w_high, hh * lw);
+    if (h_high <= H - 1 && w_low >= 0) corner(h_high, w_low, lh * hw);
+    if (h_high <= H - 1 && w_high <= W - 1) corner(h_high, w_high, lh * lw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, r[i], acc[i]);
+  }
+  if (!live) return;
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  bf16* op = out + (static_cast<size_t>(b) * 2 * HW + pos) * pix_stride + m * D + gl * 8;
+  *reinterpret_cast<uint4*>(op) = o;
+  *reinterpret_cast<uint4*>(op + static_cast<size_t>(HW) * pix_stride) = o;
+}
+
 }  // namespace mmt
 
 using namespace mmt;
@@ -191,6 +272,15 @@ extern "C" int mmt_msda_bimodal_fwd(const void* value, const float* offw, int ld
   const size_t warps = static_cast<size_t>(B) * H * W * M;
   const int block = 256;
   const int grid = static_cast<int>((warps * 32 + block - 1) / block);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(offw) & 7) == 0) && (ld_offw % 2 == 0);
+  if (is_bf16 && P == 4 && al16) {
+    const size_t groups = warps;                 // one 8-lane group per (b, pos, head)
+    const int grid8 = static_cast<int>((groups * 8 + block - 1) / block);
+    msda_bimodal_bf16_p4_kernel<<<grid8, block, 0, s>>>(reinterpret_cast<const bf16*>(value), offw, ld_offw,
+                                                        reinterpret_cast<bf16*>(out), B, H, W, M);
+    MMT_RETURN_LAST_ERROR();
+  }
   if (is_bf16) msda_bimodal_kernel<bf16><<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(value), offw, ld_offw, reinterpret_cast<bf16*>(out), B, H, W, M, P);
   else msda_bimodal_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(value), offw, ld_offw, reinterpret_cast<float*>(out), B, H, W, M, P);
   MMT_RETURN_LAST_ERROR();
