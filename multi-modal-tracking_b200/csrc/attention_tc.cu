@@ -362,6 +362,322 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   stamp(7);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent form of the same kernel: at most two CTAs per SM walk the work items (query tile, head) with a fixed
+// stride, so the per-CTA fixed costs of the one-shot kernel above - TMEM allocation, barrier initialisation, the first
+// TMA round trip, the epilogue / teardown tail: ~8 k of the ~22 k cycles of a search tile (profiles/
+// r1_attention_phases.md) - are paid once per CTA or hidden: the producer warp runs ahead into the next item (Q is
+// double-buffered, the K/V ring simply continues), the MMA warp starts the next item's S = Q K^T while the softmax
+// warps are still in the previous item's epilogue.  Barrier phases run on counters that continue across items:
+//   q_full/q_empty[2]  Q buffer n & 1 of the CTA's n-th item (q_empty: committed after the item's last S MMA)
+//   s_full/s_empty, p_full/p_empty   one phase per 128-key super-block, counted over all items
+//   o_full/o_empty     one phase per item (o_empty: the eight softmax warps have read O in the epilogue - the next
+//                      item's first P V MMA overwrites it)
+// Items are ordered tile-major with the head fastest; the host sorts the tile table by key count (heavy first), so a
+// stride walk gives every CTA the same mix of 4-block search tiles and 1-block template tiles.
+constexpr int ATP_SMEM = 2 * ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 256 + 3072;
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int C,
+                       const AttnTileTC* __restrict__ tiles, int n_items, int heads, bf16* __restrict__ out, int ldo,
+                       float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;                                  // two Q buffers
+  const uint32_t ring_smem = q_smem + 2 * ATC_Q_BYTES;
+  const uint32_t bar_base = ring_smem + ATC_STAGES * ATC_BLK_BYTES;
+  auto kv_full = [&](int s) { return bar_base + 8u * s; };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (ATC_STAGES + s); };
+  auto q_full = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + b); };
+  auto q_empty = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + 2 + b); };
+  const uint32_t s_full = bar_base + 8u * (2 * ATC_STAGES + 4);
+  const uint32_t s_empty = bar_base + 8u * (2 * ATC_STAGES + 5);
+  const uint32_t p_full = bar_base + 8u * (2 * ATC_STAGES + 6);
+  const uint32_t p_empty = bar_base + 8u * (2 * ATC_STAGES + 7);
+  const uint32_t o_full = bar_base + 8u * (2 * ATC_STAGES + 8);
+  const uint32_t o_empty = bar_base + 8u * (2 * ATC_STAGES + 9);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * ATC_STAGES + 10);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
+  // [2 block parities][2 halves][128] row maxima + [2 halves][128] row sums of the epilogue
+  float* smax = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm0);
+    prefetch_tmap(&tm1);
+    for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(q_full(b), 1); mbar_init(q_empty(b), 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);   // one arrive per softmax warp
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, ATC_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t tmem_o = tmem_base;
+  const uint32_t tmem_p = tmem_base + 192u;
+  const uint32_t tmem_s = tmem_base + 64u;
+
+  // key-box bookkeeping of one tile (same as the one-shot kernel)
+  struct Plan {
+    int nblk_seg[3];
+    int nb, nsb;
+  };
+  auto make_plan = [](const AttnTileTC& t) {
+    Plan p;
+    p.nb = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      p.nblk_seg[s] = s < t.nseg ? (t.k_len[s] + ATC_KB - 1) / ATC_KB : 0;
+      p.nb += p.nblk_seg[s];
+    }
+    p.nsb = (p.nb + 1) >> 1;
+    return p;
+  };
+  auto locate = [](const AttnTileTC& t, const Plan& p, int blk, int& row0, int& len, int& buf) {
+    const bool ghost = blk >= p.nb;
+    if (ghost) blk = p.nb - 1;
+    int s = 0;
+    if (blk >= p.nblk_seg[0]) { blk -= p.nblk_seg[0]; s = 1; if (blk >= p.nblk_seg[1]) { blk -= p.nblk_seg[1]; s = 2; } }
+    row0 = t.k_row0[s] + blk * ATC_KB;
+    len = ghost ? 0 : min(ATC_KB, t.k_len[s] - blk * ATC_KB);
+    buf = t.k_buf[s];
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const AttnTileTC t = tiles[item / heads];
+        const int h = item % heads;
+        const Plan pl = make_plan(t);
+        const int qb = n & 1;
+        mbar_wait(q_empty(qb), ((n >> 1) & 1u) ^ 1u);          // the S MMAs of item n-2 have read this buffer
+        mbar_expect_tx(q_full(qb), ATC_Q_BYTES);
+        tma_load_2d(q_smem + qb * ATC_Q_BYTES, &tm0, q_full(qb), h * ATC_HD, t.q_row0);
+        tma_load_2d(q_smem + qb * ATC_Q_BYTES + ATC_Q_BYTES / 2, &tm0, q_full(qb), h * ATC_HD, t.q_row0 + 64);
+        auto load_blk = [&](int blk, int col) {
+          int row0, len, buf;
+          locate(t, pl, blk, row0, len, buf);
+          mbar_wait(kv_empty(stage), phase ^ 1u);
+          mbar_expect_tx(kv_full(stage), ATC_BLK_BYTES);
+          tma_load_2d(ring_smem + stage * ATC_BLK_BYTES, buf ? &tm1 : &tm0, kv_full(stage), col, row0);
+          if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+        };
+        for (int sb = 0; sb <= pl.nsb; ++sb) {                                  // K_sb, then V_(sb-1)
+          if (sb < pl.nsb) { load_blk(2 * sb, C + h * ATC_HD); load_blk(2 * sb + 1, C + h * ATC_HD); }
+          if (sb >= 1) { load_blk(2 * sb - 2, 2 * C + h * ATC_HD); load_blk(2 * sb - 1, 2 * C + h * ATC_HD); }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 2 * ATC_KB);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, ATC_HD);
+      int stage = 0;           // always even here: a super-block is the stage pair (stage, stage + 1)
+      uint32_t phase = 0;
+      uint32_t g = 0;          // S super-blocks issued so far (all items)
+      uint32_t jj = 0;         // P V super-blocks issued so far
+      auto wait_pair = [&]() {
+        mbar_wait(kv_full(stage), phase);
+        mbar_wait(kv_full(stage + 1), phase);
+        tc_fence_after();
+      };
+      auto release_pair = [&]() {
+        mma_commit(kv_empty(stage));
+        mma_commit(kv_empty(stage + 1));
+        stage += 2;
+        if (stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
+      };
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const AttnTileTC t = tiles[item / heads];
+        const Plan pl = make_plan(t);
+        const int qb = n & 1;
+        mbar_wait(q_full(qb), (n >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t qdesc = make_kmajor_sw128_desc(q_smem + qb * ATC_Q_BYTES);
+        for (int sb = 0; sb <= pl.nsb; ++sb) {
+          if (sb < pl.nsb) {
+            mbar_wait(s_empty, (g & 1u) ^ 1u);
+            wait_pair();
+            const uint64_t kdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);   // 128 key rows
+#pragma unroll
+            for (int k = 0; k < ATC_HD / 16; ++k)
+              mma_bf16_ss(tmem_s, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k ? 1u : 0u);
+            mma_commit(s_full);
+            if (sb == pl.nsb - 1) mma_commit(q_empty(qb));       // last read of this item's Q
+            release_pair();
+            ++g;
+          }
+          if (sb >= 1) {
+            const int j = sb - 1;
+            mbar_wait(p_full, jj & 1u);
+            if (j == 0) mbar_wait(o_empty, (n & 1u) ^ 1u);       // the previous item's epilogue has read O
+            wait_pair();
+            tc_fence_after();
+            const uint64_t vdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2 * ATC_KB / 16; ++k)   // 16 keys per MMA: P advances 8 TMEM columns, V 16 rows = 2 KB
+              mma_bf16_ts(tmem_o, tmem_p + 8u * k, vdesc + 128u * k, idesc_o, (j | k) ? 1u : 0u);
+            mma_commit(p_empty);
+            release_pair();
+            ++jj;
+          }
+        }
+        mma_commit(o_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps (two threads per query row)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;               // which 32 of a block's 64 keys this thread handles
+    const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem_s + lane_off + 64u * half;
+    const uint32_t o_addr = tmem_o + lane_off + 32u * half;
+    uint32_t g = 0;               // super-blocks processed so far (all items)
+    int n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const AttnTileTC t = tiles[item / heads];
+      const int h = item % heads;
+      const Plan pl = make_plan(t);
+      float m_row = -INFINITY;      // lazy running maximum (raw score units)
+      float mc = 0.f;               // m_row * scale_log2e
+      float l_row = 0.f;            // this thread's part of the row sum
+      auto row_max = [&](const uint32_t (&v)[32], int lim0, float m) {
+        if (lim0 >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < lim0) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        return m;
+      };
+      auto probs = [&](uint32_t (&v)[32], int lim0) {
+        uint32_t* pk = v;
+        if (lim0 >= 32) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
+            const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
+            const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
+            l_row += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        } else if (lim0 <= 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc));
+            if (2 * i >= lim0) p0 = 0.f;
+            if (2 * i + 1 >= lim0) p1 = 0.f;
+            l_row += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+        }
+      };
+      const bool warp_live = quad * 32 < t.q_rows;
+      for (int j = 0; j < pl.nsb; ++j, ++g) {
+        int row0, len, buf;
+        locate(t, pl, 2 * j + half, row0, len, buf);
+        mbar_wait(s_full, g & 1u);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(s_addr, v0);
+        tmem_ld_32x32(s_addr + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
+        float bm = row_max(v0, len, -INFINITY);
+        bm = row_max(v1, len - 32, bm);
+        float* ex = smax + (g & 1u) * 256;
+        ex[half * 128 + r] = bm;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
+        bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
+        float factor = 1.f;
+        bool moved = false;
+        if ((bm - m_row) * scale_log2e > 8.f) {
+          factor = ex2_approx((m_row - bm) * scale_log2e);   // 0 on the first block
+          m_row = bm;
+          mc = m_row * scale_log2e;
+          l_row *= factor;
+          moved = warp_live;
+        }
+        probs(v0, warp_live ? len : 0);
+        mbar_wait(p_empty, (g & 1u) ^ 1u);          // the PV MMAs of the previous super-block (any item) have completed
+        tc_fence_after();
+        if (j > 0 && __any_sync(0xffffffffu, moved)) {
+          uint32_t o[32];
+          tmem_ld_32x32(o_addr, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+          tmem_st_32x32(o_addr, o);
+        }
+        tmem_st_32x16(tmem_p + lane_off + 32u * half, v0);
+        probs(v1, warp_live ? len - 32 : 0);
+        tmem_st_32x16(tmem_p + lane_off + 32u * half + 16u, v1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // epilogue: O / L -> bf16 -> out (this thread: 32 of the 64 head channels)
+      mbar_wait(o_full, n & 1u);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_32x32(o_addr, o);
+      float* exl = smax + 512;                      // dedicated row-sum exchange buffer
+      exl[half * 128 + r] = l_row;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      l_row += exl[(half ^ 1) * 128 + r];
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);          // O may be overwritten by the next item's first P V
+      if (r < t.q_rows) {
+        const float inv = 1.f / l_row;
+        uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD + 32 * half);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          dst[c] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ATC_TMEM_COLS);
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -396,6 +712,30 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
   if (rc) return rc;
   rc = make_qkv_tmap(&tm1, qkv1, rows1, 3 * C, ld);
   if (rc) return rc;
+  static int persist = -1;     // MMT_ATTN_PERSIST=0 selects the one-shot kernel (A/B measurements)
+  if (persist < 0) {
+    const char* e = getenv("MMT_ATTN_PERSIST");
+    persist = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (persist) {
+    static bool attr_p = false;
+    static int n_sm = 0;
+    if (!attr_p) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATP_SMEM);
+      if (e != cudaSuccess) return (int)e;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      attr_p = true;
+    }
+    const int n_items = n_tiles * heads;
+    const int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
+    attn_tc_persist_kernel<<<grid, ATC_THREADS, ATP_SMEM, stream>>>(
+        tm0, tm1, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), n_items, heads, reinterpret_cast<bf16*>(out), ldo,
+        scale * 1.4426950408889634f);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MMT_OK : (int)e;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);

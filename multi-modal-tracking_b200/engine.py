@@ -243,7 +243,7 @@ class ForwardEngine:
                     add(base, Lt, [(base, Lt)])
                     add(base + Lt, Ls, [(b * N, Lt), ((B + b) * N, Lt), (base + Lt, Ls)])
             max_keys = 2 * Lt + Ls
-        t = torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev)
+        t = torch.from_numpy(ops.order_tiles(recs)).to(self.dev)
         self._tiles[key] = (t, max_keys)
         return self._tiles[key]
 
@@ -613,7 +613,7 @@ class ForwardEngine:
                     q0 = sq * rows_per_seq + o
                     recs.append([q0, min(128, rows_per_seq - o), q0, len(segs)] + [sg[1] for sg in pad] +
                                 [sg[2] for sg in pad] + [sg[0] for sg in pad] + [0, 0, 0])
-            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), max_keys)
+            hit = (torch.from_numpy(ops.order_tiles(recs)).to(self.dev), max_keys)
             self._tiles[key] = hit
         return hit
 

@@ -121,7 +121,7 @@ class OnlineEngine(ForwardEngine):
                 segs = list(key_segs) + [(0, 0, 0)] * (3 - len(key_segs))
                 recs.append([o, min(128, rows - o), o, len(key_segs)] + [sg[1] for sg in segs] + [sg[2] for sg in segs] +
                             [sg[0] for sg in segs] + [0, 0, 0])
-            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), sum(sg[2] for sg in key_segs))
+            hit = (torch.from_numpy(ops.order_tiles(recs)).to(self.dev), sum(sg[2] for sg in key_segs))
             self._tiles[key] = hit
         return hit
 

@@ -318,6 +318,16 @@ def msda_bimodal(value, offw, out, B, H, W, M=8, D=64, P=4):
     return out
 
 
+def order_tiles(recs):
+    """Attention tile records (see mmt_mixattn_fwd) as an int32 array ordered by key count, heavy first (stable): the
+    persistent kernel hands items (tile, head) to its CTAs with a fixed stride, which balances only if cost varies
+    slowly along the table.  The order of the records is free - each carries its own query and output rows."""
+    import numpy as np
+    a = np.asarray(recs, dtype=np.int32).reshape(-1, 16)
+    keys = a[:, 7:10].sum(1).astype(np.int64) * 256 + a[:, 1]           # key count, then live query rows
+    return np.ascontiguousarray(a[np.argsort(-keys, kind="stable")])
+
+
 def mixattn(qkv0, qkv1, C, heads, tiles, max_keys, out, scale):
     _need_cuda(qkv0, tiles, out)
     assert tiles.dtype == torch.int32 and tiles.is_contiguous() and tiles.shape[1] == 16

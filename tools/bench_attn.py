@@ -14,6 +14,8 @@ iters = 3 if (len(sys.argv) > 2 and sys.argv[2] == "short") else 20
 N = Lt + Ls
 qkv = torch.randn(nseq * N, 3 * C, device="cuda").to(torch.bfloat16)
 tiles, segs = _tiles(nseq, N, Lt, Ls, cross)
+if os.environ.get("SORT_TILES", "1") != "0":
+    tiles = torch.from_numpy(ops.order_tiles(tiles.numpy()))
 tiles = tiles.cuda()
 out = torch.empty(nseq * N, C, device="cuda", dtype=torch.bfloat16)
 mk = max(sum(l for _, l in s[2]) for s in segs)
