@@ -142,7 +142,10 @@ def frame_path_bench(model, cfg, variant, B, steps, dev, cpu_budget):
     init = np.stack([rng.uniform(100, 400, B), rng.uniform(100, 300, B), rng.uniform(30, 120, B), rng.uniform(30, 120, B)], 1)
     params = types.SimpleNamespace(template_factor=float(cfg.TEST.TEMPLATE_FACTOR), template_size=int(cfg.TEST.TEMPLATE_SIZE),
                                    search_factor=float(cfg.TEST.SEARCH_FACTOR), search_size=int(cfg.TEST.SEARCH_SIZE))
-    trk = F.BatchedTracker(model, params, update_intervals=[10 ** 9], n_mod=n_mod, capacity=steps + 8)
+    # the two-stream tracker class feeds both modalities through Preprocessor_wo_mask (no colour map), the others apply
+    # JET to the infrared crop (Preprocessor_Multimodal)
+    trk = F.BatchedTracker(model, params, update_intervals=[10 ** 9], n_mod=n_mod, capacity=steps + 8,
+                           jet_mask=0 if variant == "mixformer_vit_rgbt" else None)
     trk.initialize(sets[0], init)
     for t in range(3):
         trk.track(sets[t & 1])
@@ -190,7 +193,7 @@ def frame_path_bench(model, cfg, variant, B, steps, dev, cpu_budget):
             for m in range(n_mod):
                 im = sets[0][b][m] if n_mod > 1 else sets[0][b]
                 c, _ = FO.sample_target(im, list(init[b]), params.search_factor, params.search_size)
-                FO.normalize(FO.apply_jet(c) if m == 1 else c)
+                FO.normalize(FO.apply_jet(c) if (m == 1 and variant != "mixformer_vit_rgbt") else c)
             n += 1
         out["cpu_frame_side"] = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": f"{n} sequence-frames of sample_target + Preprocessor through oracle/frame_oracle.py "

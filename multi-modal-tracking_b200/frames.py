@@ -132,14 +132,15 @@ class BatchedTracker:
     network: a model from mmt_b200.builders on a CUDA device (RGB-T: called with [v, i] lists; RGB-only: tensors).
     params:  object with template_factor, template_size, search_factor, search_size (lib/test/parameter/*.py).
     update_intervals: the reference's `self.update_intervals` (online template refreshed when frame_id % interval == 0).
-    n_mod: 2 for the RGB-T trackers (modality 1 goes through the JET colour map), 1 for RGB-only.
+    n_mod: 2 for the RGB-T trackers, 1 for RGB-only.  jet_mask: which modalities get the JET colour map (see below).
     use_template_cache: run `cache_templates()` at template updates and `forward_search()` per frame (symmetric
     variants; bit-identical boxes).
     """
 
     MARGIN = 10.0      # clip_box(..., margin=10), asymmetric_shared_ce.py:103
 
-    def __init__(self, network, params, update_intervals=(), n_mod=2, use_template_cache=False, capacity=1024):
+    def __init__(self, network, params, update_intervals=(), n_mod=2, use_template_cache=False, capacity=1024,
+                 jet_mask=None):
         self.network = network
         self.device = next(network.parameters()).device
         if self.device.type != "cuda":
@@ -147,7 +148,10 @@ class BatchedTracker:
         self.params = params
         self.update_intervals = [int(u) for u in update_intervals]
         self.n_mod = int(n_mod)
-        self.jet_mask = 0b10 if self.n_mod == 2 else 0
+        # bit m set: modality m goes through the JET colour map.  Default = Preprocessor_Multimodal (infrared only), the
+        # preprocessor of the shared / unibackbone / asymmetric trackers; the two-stream tracker
+        # (lib/test/tracker/mixformer_vit_rgbt.py:25,85-86) uses Preprocessor_wo_mask for both modalities: jet_mask=0.
+        self.jet_mask = (0b10 if self.n_mod == 2 else 0) if jet_mask is None else int(jet_mask)
         self.use_cache = bool(use_template_cache)
         self.capacity = int(capacity)
         self.frame_id = 0
