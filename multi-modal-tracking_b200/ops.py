@@ -324,7 +324,10 @@ def order_tiles(recs):
     slowly along the table.  The order of the records is free - each carries its own query and output rows."""
     import numpy as np
     a = np.asarray(recs, dtype=np.int32).reshape(-1, 16)
-    keys = a[:, 7:10].sum(1).astype(np.int64) * 256 + a[:, 1]           # key count, then live query rows
+    # key count only, stable: the query tiles of one sequence keep their neighbourhood, so the CTAs that share a
+    # sequence's K / V slices run at the same time and the second reader hits L2 (sorting the 68-row tail tiles away
+    # from their 128-row siblings cost +70 % DRAM reads, profiles/r1d_launches_final.md)
+    keys = a[:, 7:10].sum(1).astype(np.int64)
     return np.ascontiguousarray(a[np.argsort(-keys, kind="stable")])
 
 
