@@ -239,6 +239,15 @@ int mmt_frame_crop(const void* const* frames_dev, const int* dims_dev, const dou
 /* bytes of 16-byte aligned DEVICE workspace mmt_frame_crop needs (per-image window geometry + resize tap tables) */
 long long mmt_frame_crop_workspace_bytes(int B, int n_mod, int out_sz);
 /*
+ * Preprocessor on the device: uint8 HWC crops [n_img, size, size, 3] -> fp32 [n_img, 3, size, size] = ((x/255) - mean)/std;
+ * image i belongs to modality i / per_mod, modalities whose bit is set in jet_mask get cv2.applyColorMap(JET) first
+ * (jet_lut_dev: DEVICE uint8 [256][3]).  Replaces Preprocessor_wo_mask.process / Preprocessor_Multimodal.process
+ * lib/test/tracker/tracker_utils.py:24-48 after their `torch.tensor(img_arr).cuda()` upload.
+ */
+int mmt_preprocess_u8(const unsigned char* crops_u8, float* out, int n_img, int size, int per_mod, unsigned jet_mask,
+                      const unsigned char* jet_lut_dev, void* stream);
+
+/*
  * Online (SPM) trackers: score bookkeeping of the online-template candidate, per sequence:
  *   s = sigmoid(logits[b]) (fp32); max_score[b] *= decay; take[b] = s > 0.5 && s > max_score[b]; if take: max_score[b] = s.
  * take_dev (DEVICE uint8 [B]) is then the `active` mask of the mmt_frame_crop call that refreshes the candidate crop.

@@ -245,7 +245,53 @@ __global__ void online_score_update_kernel(const float* __restrict__ logits, dou
   take[b] = t;
 }
 
+// Preprocessor_*.process on the device (lib/test/tracker/tracker_utils.py:24-48): uint8 HWC crops [n, S, S, 3] ->
+// ((x / 255) - mean) / std as fp32 [n, 3, S, S]; images whose bit is set in jet_bits (bit = image / per_mod) go through
+// cv2.applyColorMap(JET) first.  The reference uploads the uint8 crop and converts on the GPU as well
+// (`torch.tensor(img_arr).cuda().float()`), so this is its H2D volume: 1 byte per value.
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int n_img, int pix_per_img, int per_mod,
+                     unsigned jet_mask, const uint8_t* __restrict__ jet_lut) {
+  __shared__ float ntab[2][768];
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, v = i & 255;
+    ntab[0][i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), mean[c]), sd[c]);
+    ntab[1][i] = jet_mask ? __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(jet_lut[3 * v + c]), 255.0f), mean[c]), sd[c])
+                          : 0.f;
+  }
+  __syncthreads();
+  const size_t total = static_cast<size_t>(n_img) * pix_per_img;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int img = static_cast<int>(i / pix_per_img);
+    const int pix = static_cast<int>(i - static_cast<size_t>(img) * pix_per_img);
+    const uint8_t* p = in + i * 3;
+    const int v0 = p[0], v1 = p[1], v2 = p[2];
+    const bool jet = (jet_mask >> (img / per_mod)) & 1u;
+    float* o = out + static_cast<size_t>(img) * 3 * pix_per_img + pix;
+    if (jet) {
+      const int gray = (v0 * 3735 + v1 * 19235 + v2 * 9798 + (1 << 14)) >> 15;
+      o[0] = ntab[1][gray]; o[pix_per_img] = ntab[1][256 + gray]; o[2 * static_cast<size_t>(pix_per_img)] = ntab[1][512 + gray];
+    } else {
+      o[0] = ntab[0][v0]; o[pix_per_img] = ntab[0][256 + v1]; o[2 * static_cast<size_t>(pix_per_img)] = ntab[0][512 + v2];
+    }
+  }
+}
+
 }  // namespace mmt
+
+extern "C" int mmt_preprocess_u8(const unsigned char* crops_u8, float* out, int n_img, int size, int per_mod,
+                                 unsigned jet_mask, const unsigned char* jet_lut_dev, void* stream) {
+  MMT_CHECK_ARG(crops_u8 && out && n_img > 0 && size > 0 && per_mod > 0);
+  MMT_CHECK_ARG(jet_mask == 0u || jet_lut_dev != nullptr);
+  const size_t total = static_cast<size_t>(n_img) * size * size;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  mmt::preprocess_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(crops_u8, out, n_img, size * size, per_mod,
+                                                                                 jet_mask, jet_lut_dev);
+  MMT_RETURN_LAST_ERROR();
+}
 
 extern "C" int mmt_online_score_update(const float* logits, double* max_score_dev, unsigned char* take_dev,
                                        const unsigned char* active_dev, int B, double decay, void* stream) {

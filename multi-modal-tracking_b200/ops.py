@@ -544,3 +544,21 @@ def online_score_update(logits, max_score, take, decay=1.0, active=None):
                                     ctypes.c_double(decay), _stream()), "mmt_online_score_update")
     _count(1, "online_score_update", _ev)
     return take
+
+
+_preprocess_u8 = _lib.fn("mmt_preprocess_u8")
+
+
+def preprocess_u8(crops_u8, out, per_mod, jet_mask=0, jet_lut=None):
+    """uint8 [n, S, S, 3] CUDA crops -> normalised fp32 [n, 3, S, S] (mmt_preprocess_u8)."""
+    _need_cuda(crops_u8, out)
+    n, S = crops_u8.shape[0], crops_u8.shape[1]
+    assert crops_u8.dtype == torch.uint8 and crops_u8.is_contiguous() and tuple(crops_u8.shape) == (n, S, S, 3)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n * 3 * S * S
+    if jet_mask:
+        assert jet_lut is not None and jet_lut.is_cuda and jet_lut.dtype == torch.uint8 and jet_lut.numel() == 768
+    _ev = _begin()
+    _lib.check(_preprocess_u8(_ptr(crops_u8), _ptr(out), c_int(n), c_int(S), c_int(per_mod), ctypes.c_uint(jet_mask),
+                              _ptr(jet_lut), _stream()), "mmt_preprocess_u8")
+    _count(1, "preprocess_u8", _ev)
+    return out

@@ -293,3 +293,51 @@ def test_online_batched_tracker_with_the_real_online_model(built_lib):
         want = [list(map(float, init[b]))] + [[float(v) for v in orc.track(vids[b][t])] for t in range(1, T)]
         assert np.array_equal(got[:, b], np.array(want)), (b, np.abs(got[:, b] - np.array(want)).max())
     assert np.isfinite(got_logits).all()
+
+
+def test_preprocess_u8_matches_oracle(built_lib):
+    """mmt_preprocess_u8 (Preprocessor_*.process on the device) bit for bit against the oracle, with and without JET."""
+    from mmt_b200 import ops, frames
+    rng = np.random.default_rng(17)
+    crops = rng.integers(0, 256, (6, 37, 37, 3), dtype=np.uint8)
+    lut = frames.jet_lut_tensor("cuda")
+    out = torch.empty((6, 3, 37, 37), device="cuda")
+    ops.preprocess_u8(torch.from_numpy(crops).cuda(), out, per_mod=3, jet_mask=0b10, jet_lut=lut)   # images 3..5: modality 1
+    got = out.cpu().numpy()
+    for i in range(6):
+        want = FO.normalize(FO.apply_jet(crops[i]) if i >= 3 else crops[i])
+        assert np.array_equal(got[i], want), i
+
+
+@pytest.mark.parametrize("variant", ["mixformer_vit_rgbt_shared", "mixformer_vit"])
+def test_framestep_uint8_crops_and_resident_templates(built_lib, variant):
+    """FrameStep with uint8 HWC crops (uploaded as bytes, normalised on the device) gives the boxes of the model called
+    on oracle-normalised fp32 crops; resident templates + step(None, None, search) gives the same boxes again."""
+    from mmt_b200 import synthetic, runner
+    model, cfg = synthetic.make_model(variant, 0, sharpen=True)
+    model = model.cuda()
+    rgbt = variant != "mixformer_vit"
+    B, ts, ss = 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.SEARCH.SIZE
+    rng = np.random.default_rng(23)
+    u8 = lambda size: rng.integers(0, 256, (B, size, size, 3), dtype=np.uint8)
+    norm = lambda a, m: torch.from_numpy(np.stack([FO.normalize(FO.apply_jet(x) if m == 1 else x) for x in a])).cuda()
+    if rgbt:
+        t, ot, s = [u8(ts), u8(ts)], [u8(ts), u8(ts)], [u8(ss), u8(ss)]
+        ref_args = [[norm(a[m], m) for m in range(2)] for a in (t, ot, s)]
+        host = [[torch.from_numpy(a[m]) for m in range(2)] for a in (t, ot, s)]
+    else:
+        t, ot, s = u8(ts), u8(ts), u8(ss)
+        ref_args = [norm(a, 0) for a in (t, ot, s)]
+        host = [torch.from_numpy(a) for a in (t, ot, s)]
+    _, want = model(*ref_args)
+    want = want.view(-1, 4).cpu()
+    fs = runner.FrameStep(model)
+    got = fs.step(*host).clone()
+    assert torch.equal(got, want)
+    assert fs.h2d_bytes == (2 if rgbt else 1) * B * 3 * (2 * ts * ts + ss * ss)          # one byte per value
+    fs.set_templates(host[0], host[1])
+    got2 = fs.step(None, None, host[2]).clone()
+    assert torch.equal(got2, want)
+    assert fs.h2d_bytes == (2 if rgbt else 1) * B * 3 * ss * ss
+    with pytest.raises(RuntimeError):
+        runner.FrameStep(model).step(None, None, host[2])
