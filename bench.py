@@ -11,9 +11,11 @@ Sequences are independent, so N GPUs run N x 64 sequences with no data-path coll
 all-gather per step brings the [64,4] boxes of every rank together (never inside the forward).
 
 Printed (rank 0, ONE JSON line): `value` = frames/s with inputs resident in HBM; `e2e` = the same through
-FrameStep.step() with pinned HOST crops (H2D + forward + D2H of the boxes inside the timed region); `roofline` =
-the tcgen05 GEMM kernel class timed per launch with CUDA events inside the timed region, against the measured
-cuBLAS bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU port of the reference forward (oracle/) on the
+FrameStep.step() with pinned HOST buffers in the reference tracker loop's data flow (templates resident on the device,
+uint8 search crops H2D + device Preprocessor + full forward + D2H of the boxes + synchronise, every step;
+`e2e_fp32_crops`: all crops as fp32 host tensors every step); `frame_path` = raw uint8 frames in through BatchedTracker;
+`roofline` = the tcgen05 GEMM kernel timed per launch with CUDA events in a second pass of the same K steps, against the
+measured cuBLAS bf16 peak of MEASURED_PEAKS.json; `cpu_baseline` = the CPU port of the reference forward (oracle/) on the
 host cores, bounded sample.  `--impl reference` times only that CPU port (the reference is Python + torch and
 /root/reference does not travel to the GPU box; the port is pinned against the unmodified reference by
 oracle/gen_golden.py).
