@@ -228,8 +228,12 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": max(1, warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{VARIANT} (experiments/mixformer_vit_rgbt/attention_lasher_newfusion_2layer.yaml) "
-                               f"MixViT-B RGB-T forward, bs={BATCH} per GPU; each step = {sample}-frame sample"},
+        "config": {"workload": f"{VARIANT} ({synthetic.DEFAULT_YAML[VARIANT]}.yaml) RGB-T two-modality full forward "
+                               f"({cfg.DATA.TEMPLATE.SIZE}^2 template + online template, {cfg.DATA.SEARCH.SIZE}^2 search), "
+                               f"bs={BATCH} sequences per GPU, seeded random-init weights, N(0,1) crops",
+                   "batch_per_gpu": BATCH, "sequences": BATCH * max(1, args.gpus),
+                   "parallelism": f"sequence-sharded x{max(1, args.gpus)}",
+                   "sample": f"each step = a {sample}-sequence-frame sample of the bs={BATCH} workload on the host cores"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} steps x {sample} sequence-frames, CPU port of the reference forward "
                                    "(oracle/mixformer_oracle.py, pinned against the unmodified reference)"},
