@@ -341,3 +341,66 @@ def test_framestep_uint8_crops_and_resident_templates(built_lib, variant):
     assert fs.h2d_bytes == (2 if rgbt else 1) * B * 3 * ss * ss
     with pytest.raises(RuntimeError):
         runner.FrameStep(model).step(None, None, host[2])
+
+
+def test_dropin_tracker_class_protocol(built_lib):
+    """`trackers.get_tracker_class(variant)(params, dataset)` with the reference's initialize / track protocol
+    (lib/test/evaluation/tracker_rgbt.py:100-184): per-frame {"target_bbox": [x, y, w, h]} equal to the reference loop
+    restated with the oracle and the same network; the online class against OnlineTrackerOracle."""
+    from mmt_b200 import synthetic, trackers
+    T = 6
+    # RGB-T, Preprocessor_Multimodal variant
+    cfg = synthetic.load_variant_config("mixformer_vit_rgbt_unibackbone")
+    params = types.SimpleNamespace(cfg=cfg, template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE, checkpoint=None, save_all_boxes=False)
+    torch.manual_seed(0)
+    cls = trackers.get_tracker_class("mixformer_vit_rgbt_unibackbone")
+    trk = cls(params, "lasher")
+    synthetic.sharpen_(trk.network, torch.Generator().manual_seed(1000))
+    trk.network.load_state_dict(trk.network.state_dict())                 # re-pack the engine arena after the edit
+    trk.update_intervals = [2]
+    vid = [GG.seeded_video(51, 190, 250, T), GG.seeded_video(52, 190, 250, T)]
+    box = [70.0, 50.0, 66.0, 48.0]
+    assert trk.initialize([vid[0][0], vid[1][0]], {"init_bbox": (box, box)}) is None
+    got = [trk.track([vid[0][t], vid[1][t]])["target_bbox"] for t in range(1, T)]
+    assert all(isinstance(g, list) and len(g) == 4 and all(isinstance(v, float) for v in g) for g in got)
+
+    def crops(t, state, factor, size):
+        out = []
+        for m in range(2):
+            c, _ = FO.sample_target(vid[m][t], state, factor, size)
+            out.append(torch.from_numpy(FO.normalize(FO.apply_jet(c) if m == 1 else c)[None]).cuda())
+        return out, size / FO.crop_geometry(state, factor, 190, 250)[0]
+
+    state = list(box)
+    template, _ = crops(0, state, 2.0, params.template_size)
+    online = template
+    for t in range(1, T):
+        search, rf = crops(t, state, 4.5, params.search_size)
+        _, coords = trk.network(template, online, search)
+        state = FO.update_state(state, coords.view(-1, 4).cpu().numpy()[0], rf, params.search_size, 190, 250, margin=10)
+        if t % 2 == 0:
+            online, _ = crops(t, state, 2.0, params.template_size)
+        assert got[t - 1] == [float(v) for v in state], t
+
+    # online (SPM) class
+    cfg = synthetic.load_variant_config("mixformer_vit_online")
+    params = types.SimpleNamespace(cfg=cfg, template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE, checkpoint=None, save_all_boxes=False,
+                                   update_interval=2)
+    torch.manual_seed(0)
+    otrk = trackers.get_tracker_class("mixformer_vit_online")(params, "lasot")
+    otrk.initialize(vid[0][0], {"init_bbox": box})
+    got = [otrk.track(vid[0][t])["target_bbox"] for t in range(1, T)]
+
+    def net(template, online_template, search):
+        out, coords = otrk.network(*[torch.from_numpy(a[None]).cuda() for a in (template, online_template, search)],
+                                   run_score_head=True)
+        return coords.view(-1, 4).cpu().numpy()[0], out["pred_scores"].reshape(-1).cpu().numpy()[0]
+
+    orc = FO.OnlineTrackerOracle(net, 2.0, params.template_size, 4.5, params.search_size, 2)
+    orc.initialize(vid[0][0], box)
+    for t in range(1, T):
+        assert got[t - 1] == [float(v) for v in orc.track(vid[0][t])], t
+    with pytest.raises(KeyError):
+        trackers.get_tracker_class("no_such_variant")
