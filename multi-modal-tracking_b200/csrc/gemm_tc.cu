@@ -760,7 +760,17 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
       ep.tma_f32 = 1;
     return launch_gemm_pair(tmA, tmC, tmR, W, ldw, M, N, K, ep, s);
   }
-  switch (pick_bn(N)) {
+  int bn = pick_bn(N);
+  // Small problems (bs = 1 latency: M = 452 rows per modality) leave most SMs idle with wide tiles - 4 x 3 tiles for
+  // fc2 - and then the serial K loop of one CTA is the launch time.  Narrow the tile until the grid covers the machine
+  // (never below 64 columns; only for plain GEMMs whose N the narrower tile divides).  MMT_GEMM_NARROW=0 disables (A/B).
+  static int narrow = -1;
+  if (narrow < 0) { const char* e = getenv("MMT_GEMM_NARROW"); narrow = (e && e[0] == '0') ? 0 : 1; }
+  if (narrow && !cv.enabled && max_ctas <= 0) {
+    const int m_tiles = cdiv(M, GEMM_BM);
+    while (bn > 64 && (bn % 2) == 0 && (N % (bn / 2)) == 0 && m_tiles * cdiv(N, bn) < num_sms()) bn /= 2;
+  }
+  switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
     case 192: return launch_gemm<192>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
     case 128: return launch_gemm<128>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);
