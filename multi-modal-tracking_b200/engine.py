@@ -376,6 +376,7 @@ class ForwardEngine:
             self._side = torch.cuda.Stream(device=self.dev)
             self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
             self._two_streams = os.environ.get("MMT_TWO_STREAMS", "1") != "0"
+            self._head_lanes = os.environ.get("MMT_HEAD_LANES", "1") != "0"      # A/B switch of _run_head's two lanes
         return self._side
 
     def set_two_streams(self, on: bool):
@@ -515,31 +516,45 @@ class ForwardEngine:
         self._conv3x3(feat, B, gs, gs, C, H["s1_w"], H["s1_b"], s1, tag)
         sl = lambda n: s1[:, self.s1_cols[n][0]: self.s1_cols[n][1]]
         x4s, a3s, a4s = [], [], []
-        for c in ("tl", "br"):
-            x2 = self._buf(tag, "x2" + c, (n18, ch // 2), self.act)
-            self._conv3x3(sl(f"conv1_{c}"), B, gs, gs, ch, H[f"conv2_{c}_w"], H[f"conv2_{c}_b"], x2, tag)
-            # up-1: conv3(up2(adjust1(x)) + up2(x2)) at 2gs x 2gs
-            x3 = self._buf(tag, "x3" + c, (n36, ch // 4), self.act)
-            self._conv3x3(None, B, 2 * gs, 2 * gs, ch // 2, H[f"conv3_{c}_w"], H[f"conv3_{c}_b"], x3, tag,
-                          up=(sl(f"adjust1_{c}"), 2, x2, 2))
-            # up-2: conv4(up4(adjust2(x)) + up2(x3)) at 4gs x 4gs
-            x4 = self._buf(tag, "x4" + c, (n72, ch // 8), self.act)
-            self._conv3x3(None, B, 4 * gs, 4 * gs, ch // 4, H[f"conv4_{c}_w"], H[f"conv4_{c}_b"], x4, tag,
-                          up=(sl(f"adjust2_{c}"), 4, x3, 2))
-            # side branches: adjust3 on x2 (gs), adjust4 on x3 (2gs)
-            a = x2
-            for j, co in enumerate((ch // 4, ch // 8, 1)):
-                o = self._buf(tag, f"a3{c}{j}", (n18, co), self.act)
-                self._conv3x3(a, B, gs, gs, a.shape[1], H[f"adjust3_{c}.{j}_w"], H[f"adjust3_{c}.{j}_b"], o, tag)
-                a = o
-            a3s.append(a)
-            a = x3
-            for j, co in enumerate((ch // 8, 1)):
-                o = self._buf(tag, f"a4{c}{j}", (n36, co), self.act)
-                self._conv3x3(a, B, 2 * gs, 2 * gs, a.shape[1], H[f"adjust4_{c}.{j}_w"], H[f"adjust4_{c}.{j}_b"], o, tag)
-                a = o
-            a4s.append(a)
-            x4s.append(x4)
+        # the two corner branches share only s1: the bottom-right chain runs on the side stream (small-N convolutions
+        # with one-wave grids - each alone leaves most SMs idle)
+        side = self._lanes()
+        main = torch.cuda.current_stream()
+        lanes = (main, side) if (self.bf16 and self._two_streams and self._head_lanes) else (main, main)
+        if lanes[1] is not main:
+            self._fork_ev.record(main)
+            side.wait_event(self._fork_ev)
+        for ci, c in enumerate(("tl", "br")):
+            with torch.cuda.stream(lanes[ci]):
+                tag = ("head", B, c)
+                x2 = self._buf(tag, "x2" + c, (n18, ch // 2), self.act)
+                self._conv3x3(sl(f"conv1_{c}"), B, gs, gs, ch, H[f"conv2_{c}_w"], H[f"conv2_{c}_b"], x2, tag)
+                # up-1: conv3(up2(adjust1(x)) + up2(x2)) at 2gs x 2gs
+                x3 = self._buf(tag, "x3" + c, (n36, ch // 4), self.act)
+                self._conv3x3(None, B, 2 * gs, 2 * gs, ch // 2, H[f"conv3_{c}_w"], H[f"conv3_{c}_b"], x3, tag,
+                              up=(sl(f"adjust1_{c}"), 2, x2, 2))
+                # up-2: conv4(up4(adjust2(x)) + up2(x3)) at 4gs x 4gs
+                x4 = self._buf(tag, "x4" + c, (n72, ch // 8), self.act)
+                self._conv3x3(None, B, 4 * gs, 4 * gs, ch // 4, H[f"conv4_{c}_w"], H[f"conv4_{c}_b"], x4, tag,
+                              up=(sl(f"adjust2_{c}"), 4, x3, 2))
+                # side branches: adjust3 on x2 (gs), adjust4 on x3 (2gs)
+                a = x2
+                for j, co in enumerate((ch // 4, ch // 8, 1)):
+                    o = self._buf(tag, f"a3{c}{j}", (n18, co), self.act)
+                    self._conv3x3(a, B, gs, gs, a.shape[1], H[f"adjust3_{c}.{j}_w"], H[f"adjust3_{c}.{j}_b"], o, tag)
+                    a = o
+                a3s.append(a)
+                a = x3
+                for j, co in enumerate((ch // 8, 1)):
+                    o = self._buf(tag, f"a4{c}{j}", (n36, co), self.act)
+                    self._conv3x3(a, B, 2 * gs, 2 * gs, a.shape[1], H[f"adjust4_{c}.{j}_w"], H[f"adjust4_{c}.{j}_b"], o,
+                                  tag)
+                    a = o
+                a4s.append(a)
+                x4s.append(x4)
+        if lanes[1] is not main:
+            self._join_ev.record(side)
+            main.wait_event(self._join_ev)
         S = 4 * gs
         maps = torch.empty((B, 2, S * S), device=self.dev, dtype=torch.float32) if want_maps else None
         xyxy = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
