@@ -30,6 +30,32 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
   }
 }
 
+// bf16 output, P % 8 == 0, W % 8 == 0, 16-byte aligned image rows: a thread converts 8 consecutive pixels of one
+// image row (two 16-byte loads) into one 16-byte store - the same values at the same places as patchify_kernel.
+__global__ void __launch_bounds__(256)
+patchify_bf16x8_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W, int P,
+                       int tok_off, int tok_per_seq) {
+  const int gw = W / P;
+  const int b = blockIdx.x / (H / P);
+  const int py = blockIdx.x % (H / P);
+  const int K = Cin * P * P;
+  const int w8 = W / 8;
+  const int n = Cin * P * w8;  // 8-pixel units of this patch-row
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = (i % w8) * 8;
+    const int ky = (i / w8) % P;
+    const int c = i / (w8 * P);
+    const float4* src = reinterpret_cast<const float4*>(img + ((static_cast<size_t>(b) * Cin + c) * H + (py * P + ky)) * W + x);
+    const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1);           // streamed: every pixel is read exactly once
+    const int px = x / P, kx = x % P;
+    const size_t row = static_cast<size_t>(b) * tok_per_seq + tok_off + py * gw + px;
+    uint4 w;
+    w.x = pack_bf16x2(v0.x, v0.y); w.y = pack_bf16x2(v0.z, v0.w);
+    w.z = pack_bf16x2(v1.x, v1.y); w.w = pack_bf16x2(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(out + row * K + c * P * P + ky * P + kx) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim, one warp per row, two-pass statistics in registers.
 // gamma/beta set m = (row / period) & 1 (period <= 0: always set 0) implements the modality-specific
@@ -451,7 +477,10 @@ extern "C" int mmt_patchify(const float* img, void* out, int B, int Cin, int H, 
   MMT_CHECK_ARG(img && out && B > 0 && Cin > 0 && P > 0 && H % P == 0 && W % P == 0);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = B * (H / P);
-  if (out_bf16) patchify_kernel<bf16><<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
+  const bool vec8 = out_bf16 && (P % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec8) patchify_bf16x8_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
+  else if (out_bf16) patchify_kernel<bf16><<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
   else patchify_kernel<float><<<grid, 256, 0, s>>>(img, reinterpret_cast<float*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
   MMT_RETURN_LAST_ERROR();
 }
