@@ -68,7 +68,7 @@ def _load(frame, reader, n_mod):
 
 
 def run_sequences(network, params, sequences, results_dir=None, batch=64, update_intervals=(), n_mod=2,
-                  reader=read_image_rgb, rank=0, world_size=1, capacity_hw=None):
+                  reader=read_image_rgb, rank=0, world_size=1, capacity_hw=None, tracker_factory=None):
     """Track every sequence owned by `rank`; returns {name: [T, 4] float64 boxes} and writes the reference's result
     files when results_dir is given.  `sequences`: SequenceSpec list (or reference Sequence objects)."""
     specs = [s if isinstance(s, SequenceSpec) else SequenceSpec.from_reference(s) for s in sequences]
@@ -82,7 +82,11 @@ def run_sequences(network, params, sequences, results_dir=None, batch=64, update
         hw = [np.shape(_load(s.frames[0], reader, n_mod)[0] if n_mod > 1 else _load(s.frames[0], reader, n_mod))[:2]
               for s in mine]
         capacity_hw = (max(h for h, _ in hw), max(w for _, w in hw))
-    trk = BatchedTracker(network, params, update_intervals=update_intervals, n_mod=n_mod, use_template_cache=False)
+    # tracker_factory: the slot scheduler below only needs initialize / reset_slot / track / frame_id / log (tests drive
+    # it with a recording stand-in; the product always uses BatchedTracker)
+    make = tracker_factory or (lambda: BatchedTracker(network, params, update_intervals=update_intervals, n_mod=n_mod,
+                                                      use_template_cache=False))
+    trk = make()
     slots = [queue.popleft() for _ in range(B)]
     first = [_load(s.frames[0], reader, n_mod) for s in slots]
     t0 = time.perf_counter()
@@ -95,7 +99,8 @@ def run_sequences(network, params, sequences, results_dir=None, batch=64, update
 
     def finish(b):
         s = slots[b]
-        rows = trk.log[start[b]:start[b] + len(s.frames), b].cpu().numpy()      # synchronises; once per sequence
+        # synchronises, once per sequence; an owned copy (the slot's next sequence reuses the table's current row)
+        rows = trk.log[start[b]:start[b] + len(s.frames), b].cpu().numpy().copy()
         out[s.name] = rows
         if results_dir is not None:
             save_tracker_output(results_dir, s, rows, times[b])

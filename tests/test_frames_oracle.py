@@ -152,3 +152,74 @@ def test_online_score_step_branches():
     assert (m2, take) == (m, False)
     m3, take = FO.online_score_step(m, 0.3, decay=0.5)  # the maximum decays first: 0.345 < 0.574
     assert take and abs(m3 - 0.5744425) < 1e-6
+
+
+class _RecordingTracker:
+    """Stand-in for BatchedTracker (CPU): boxes are a function of (sequence tag, frame index) read from the frames
+    themselves, so that the slot scheduler's bookkeeping can be checked exactly."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.frame_id = 0
+        self.calls = []
+
+    def _box(self, frame):
+        tag, t = int(frame[0][0, 0, 0]), int(frame[0][0, 0, 1])
+        return [float(tag), float(t), 1.0, 1.0]
+
+    def initialize(self, frames, init_boxes, capacity_hw=None):
+        self.B = len(frames)
+        self.log = self.torch.zeros((4, self.B, 4), dtype=self.torch.float64)
+        for b in range(self.B):
+            self.log[0, b] = self.torch.tensor(init_boxes[b], dtype=self.torch.float64)
+        self.calls.append(("init", self.B, capacity_hw))
+
+    def reset_slot(self, b, frames_b, init_box):
+        self.log[self.frame_id, b] = self.torch.tensor(init_box, dtype=self.torch.float64)
+        self.calls.append(("reset", b, int(frames_b[0][0, 0, 0])))
+
+    def track(self, frames, active=None):
+        self.frame_id += 1
+        if self.frame_id >= self.log.shape[0]:
+            self.log = self.torch.cat([self.log, self.torch.zeros_like(self.log)], 0)
+        live = [True] * self.B if active is None else list(active)
+        for b in range(self.B):
+            if live[b]:
+                assert frames[b] is not None
+                self.log[self.frame_id, b] = self.torch.tensor(self._box(frames[b]), dtype=self.torch.float64)
+        self.calls.append(("track", tuple(live)))
+
+
+def test_run_sequences_slot_scheduler(built_lib, tmp_path):
+    """Host logic of the batched runner: 5 sequences of lengths 3, 1, 4, 2, 3 through 2 slots - every sequence gets its
+    own frames in order, a finished slot is refilled (or goes inactive), single-frame sequences end at initialisation,
+    the result files hold one row per frame."""
+    from mmt_b200 import evaluation
+
+    def frame(tag, t, hw=(6, 8)):
+        f = np.zeros(hw + (3,), dtype=np.uint8)
+        f[0, 0, 0], f[0, 0, 1] = tag, t
+        return [f, f]
+
+    lengths = [3, 1, 4, 2, 3]
+    seqs = [evaluation.SequenceSpec(f"s{i}", "syn", [frame(i + 1, t, (6 + i, 8)) for t in range(n)], [i, i, 5, 5])
+            for i, n in enumerate(lengths)]
+    trk = _RecordingTracker()
+    out = evaluation.run_sequences(None, None, seqs, results_dir=str(tmp_path), batch=2, tracker_factory=lambda: trk)
+    assert sorted(out) == [f"s{i}" for i in range(5)]
+    for i, n in enumerate(lengths):
+        rows = out[f"s{i}"]
+        assert rows.shape == (n, 4)
+        assert rows[0].tolist() == [i, i, 5, 5]                                  # the initial box
+        for t in range(1, n):
+            assert rows[t].tolist() == [i + 1, t, 1.0, 1.0], (i, t, rows)        # own frames, in order
+        saved = np.loadtxt(tmp_path / "syn" / f"s{i}.txt", delimiter="\t", ndmin=2)
+        assert saved.shape == (n, 4)
+        assert np.loadtxt(tmp_path / "syn" / f"s{i}_time.txt", ndmin=1).shape == (n,)
+    assert trk.calls[0] == ("init", 2, (10, 8))                                   # capacity = largest first frame
+    assert [c for c in trk.calls if c[0] == "reset"] == [("reset", 1, 3), ("reset", 0, 4), ("reset", 0, 5)]
+    assert trk.calls[-1] == ("track", (True, False))                               # the tail runs with one live slot
+    # sharding: rank 1 of 2 owns s1 and s3 only
+    out1 = evaluation.run_sequences(None, None, seqs, batch=2, rank=1, world_size=2, tracker_factory=_RecordingTracker)
+    assert sorted(out1) == ["s1", "s3"]
