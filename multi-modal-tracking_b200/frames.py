@@ -96,13 +96,14 @@ class FrameUploader:
             self.copied[k].synchronize()                      # host may overwrite the staging buffer
         host = self.pinned[k].numpy()
         nbytes = 0
-        jobs = []
+        jobs, spans = [], []
         for i, (im, (H, W), o) in enumerate(zip(images, self.shapes, self.offsets)):
             if skip is not None and skip[i]:
                 continue
             if im.shape != (H, W, 3) or im.dtype != np.uint8:
                 raise ValueError(f"frame of shape {im.shape}/{im.dtype}, expected uint8 {(H, W, 3)} for image slot {i}")
             jobs.append((host[o:o + H * W * 3].reshape(H, W, 3), im))
+            spans.append((o, H * W * 3))
             nbytes += H * W * 3
         # the packing memcpy (~1 MB per frame) is the host-side cost of a step: numpy releases the GIL while copying,
         # so a few threads bring it well under the device step time
@@ -114,7 +115,11 @@ class FrameUploader:
         with torch.cuda.stream(self.copy_stream):
             if self._used[k]:
                 self.copy_stream.wait_event(self.consumed[k])  # kernels of two steps ago have read the device buffer
-            self.dev[k].copy_(self.pinned[k], non_blocking=True)
+            if skip is None:
+                self.dev[k].copy_(self.pinned[k], non_blocking=True)          # every slot is live: one copy
+            else:
+                for o, n in spans:                                             # only the live slots' regions travel
+                    self.dev[k][o:o + n].copy_(self.pinned[k][o:o + n], non_blocking=True)
             self.copied[k].record(self.copy_stream)
         torch.cuda.current_stream().wait_event(self.copied[k])
         self._used[k] = True
