@@ -413,7 +413,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           fence_proxy_async_shared();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, smem_u32(tile), nb, grow_w);
+            if (ep.dbg_flags & 16) tma_store_2d_hint(&tmC, smem_u32(tile), nb, grow_w, l2_policy_evict_last());
+            else tma_store_2d(&tmC, smem_u32(tile), nb, grow_w);
             bulk_commit_group();
           }
           continue;
@@ -520,7 +521,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             fence_proxy_async_shared();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, smem_u32(stg4), nb, mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0);
+              const int r0 = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0;
+              if (ep.dbg_flags & 32) tma_store_2d_hint(&tmC, smem_u32(stg4), nb, r0, l2_policy_evict_first());
+              else tma_store_2d(&tmC, smem_u32(stg4), nb, r0);
               bulk_commit_group();
             }
             continue;
