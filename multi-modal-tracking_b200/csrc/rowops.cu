@@ -56,6 +56,29 @@ patchify_bf16x8_kernel(const float* __restrict__ img, bf16* __restrict__ out, in
   }
 }
 
+// P % 4 == 0 (the ConvMAE stem's 4x4 / stride-4 convolution): 4 pixels per thread, one 16-byte load, one 8-byte store
+__global__ void __launch_bounds__(256)
+patchify_bf16x4_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W, int P,
+                       int tok_off, int tok_per_seq) {
+  const int gw = W / P;
+  const int b = blockIdx.x / (H / P);
+  const int py = blockIdx.x % (H / P);
+  const int K = Cin * P * P;
+  const int w4 = W / 4;
+  const int n = Cin * P * w4;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = (i % w4) * 4;
+    const int ky = (i / w4) % P;
+    const int c = i / (w4 * P);
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(img + ((static_cast<size_t>(b) * Cin + c) * H + (py * P + ky)) * W + x));
+    const int px = x / P, kx = x % P;
+    const size_t row = static_cast<size_t>(b) * tok_per_seq + tok_off + py * gw + px;
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y); w.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + row * K + c * P * P + ky * P + kx) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim, one warp per row, two-pass statistics in registers.
 // gamma/beta set m = (row / period) & 1 (period <= 0: always set 0) implements the modality-specific
@@ -479,7 +502,10 @@ extern "C" int mmt_patchify(const float* img, void* out, int B, int Cin, int H, 
   const int grid = B * (H / P);
   const bool vec8 = out_bf16 && (P % 8 == 0) && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool vec4 = out_bf16 && (P % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
   if (vec8) patchify_bf16x8_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
+  else if (vec4) patchify_bf16x4_kernel<<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
   else if (out_bf16) patchify_kernel<bf16><<<grid, 256, 0, s>>>(img, reinterpret_cast<bf16*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
   else patchify_kernel<float><<<grid, 256, 0, s>>>(img, reinterpret_cast<float*>(out), B, Cin, H, W, P, tok_off, tok_per_seq);
   MMT_RETURN_LAST_ERROR();
