@@ -120,12 +120,18 @@ def main_online(sharpen, yaml_name=None, batch=BATCH, variant="mixformer_vit_onl
 
 
 EXTRA = [("mixformer_vit_rgbt_shared", "baseline_attention_lasher_newfusion_2layer"),   # Attention_Fusion_Bimodal
-         ("asymmetric_shared", "attention_lasher_cat_3layer")]                           # RGBT_Fusion_Cat
+         ("asymmetric_shared", "attention_lasher_cat_3layer"),                           # RGBT_Fusion_Cat
+         ("mixformer_vit", "baseline_large")]                                            # MixViT-L RGB-only, 384 / 192
+
+
+ONLY = []      # restrict main_extra to these (variant, yaml) pairs (command line: extra:<variant>:<yaml>)
 
 
 def main_extra():
     """The two remaining fusion classes of the shipped YAMLs (sharpened weights, batch 2)."""
     for variant, yaml_name in EXTRA:
+        if ONLY and (variant, yaml_name) not in ONLY:
+            continue
         model, cfg = synthetic.make_model(variant, WEIGHT_SEED, yaml_name=yaml_name)
         sd = model.state_dict()
         inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
@@ -145,7 +151,7 @@ def main_extra():
         ora = O.forward(variant, sd, cfg, *inputs)
         d_box = (out["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
         d_map = (cap["maps"] - ora["score_maps"]).abs().max().item()
-        print(f"{variant}/{yaml_name} ({cfg.MODEL.FUSION_CLASS}): oracle vs reference boxes {d_box:.3e} maps {d_map:.3e}")
+        print(f"{variant}/{yaml_name} ({cfg.MODEL.get('FUSION_CLASS')}): oracle vs reference boxes {d_box:.3e} maps {d_map:.3e}")
         assert d_box <= 1e-5 and d_map <= 2e-4
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}__{yaml_name}_b{BATCH}.npz"),
                             pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy())
@@ -153,6 +159,9 @@ def main_extra():
 
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for v in [v for v in variants if v.startswith("extra:")]:
+        ONLY.append(tuple(v.split(":")[1:3]))
+        variants = [x for x in variants if x != v] + (["extra"] if "extra" not in variants else [])
     if "extra" in variants:
         torch.set_num_threads(8)
         main_extra()

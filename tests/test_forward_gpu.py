@@ -280,11 +280,13 @@ def test_template_cache_refused_for_cross_modal(built_lib):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("variant,yaml_name", [("mixformer_vit_rgbt_shared", "baseline_attention_lasher_newfusion_2layer"),
-                                               ("asymmetric_shared", "attention_lasher_cat_3layer")])
+                                               ("asymmetric_shared", "attention_lasher_cat_3layer"),
+                                               ("mixformer_vit", "baseline_large")])
 def test_other_fusion_classes(built_lib, variant, yaml_name, precision):
     """The remaining fusion classes of the shipped YAMLs: Attention_Fusion_Bimodal (one LayerNorm for both modalities,
     deformable_encoder.py:111-158) and RGBT_Fusion_Cat (3 x conv3x3 + BN + ReLU on the channel concat,
-    fusion_utils.py:86-110), against the reference's golden outputs."""
+    fusion_utils.py:86-110), against the reference's golden outputs; and MixViT-L RGB-only (experiments/mixformer_vit/
+    baseline_large.yaml: 24 blocks x 1024, 384^2 search / 192^2 templates)."""
     from mmt_b200 import synthetic
     model, cfg = synthetic.make_model(variant, 0, yaml_name=yaml_name)
     model = model.cuda().set_precision(precision)
@@ -294,7 +296,7 @@ def test_other_fusion_classes(built_lib, variant, yaml_name, precision):
     g = np.load(os.path.join(GOLDEN, f"{variant}__{yaml_name}_b2.npz"))
     d_box = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * cfg.DATA.SEARCH.SIZE
     d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
-    print(f"{variant}/{yaml_name} {cfg.MODEL.FUSION_CLASS} {precision}: boxes {d_box:.3e} px  maps {d_map:.3e}")
+    print(f"{variant}/{yaml_name} {cfg.MODEL.get('FUSION_CLASS')} {precision}: boxes {d_box:.3e} px  maps {d_map:.3e}")
     if precision == "fp32":
         assert d_box <= 1e-4 * cfg.DATA.SEARCH.SIZE and d_map <= 2e-4
     else:
