@@ -393,6 +393,8 @@ class _EngineModule(nn.Module):
             from .engine_online import OnlineEngine as ForwardEngine
         elif self.variant == "mixformer_convmae_online":
             from .engine_online import ConvMAEOnlineEngine as ForwardEngine
+        elif self.variant == "asymmetric_shared_online":
+            from .engine_online import AsymOnlineEngine as ForwardEngine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
@@ -592,6 +594,36 @@ def build_asymmetric_shared_ce(cfg, train=False) -> MixFormer_RGBT:
     return _build_stacked("asymmetric_shared_ce", cfg, train, True)
 
 
+class MixFormer_RGBT_OnlineScore(MixFormer_RGBT):
+    """asymmetric_shared + the SPM score head (lib/models/mixformer_vit_rgbt/asymmetric_shared_online.py:337-413):
+    the score decoder reads the FUSED search map and the first-template tokens of both modalities."""
+
+    def __init__(self, backbone, box_head, fusion_vi, score_branch, cfg):
+        super().__init__("asymmetric_shared_online", backbone, box_head, fusion_vi, cfg)
+        self.score_branch = score_branch
+
+    @torch.no_grad()
+    def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None, return_features=False):
+        res = self.engine().forward(list(template), list(online_template), list(search), run_score_head=run_score_head,
+                                    gt_bboxes=gt_bboxes)
+        coords = res["pred_boxes"]
+        out = {"pred_boxes": coords}
+        if run_score_head:
+            out["pred_scores"] = res["pred_scores"].view(-1)
+        if return_features:
+            eng, B = self._engine, coords.shape[0]
+            sv, si = res["search_rows"]
+            return out, coords, eng.rows_to_map(sv, B), eng.rows_to_map(si, B), eng.rows_to_map(res["feat_rows"], B)
+        return out, coords
+
+
+def build_asymmetric_shared_online_score(cfg, train=False) -> MixFormer_RGBT_OnlineScore:
+    _require_inference(train)
+    bb = _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE, per_modality_ln=True)
+    score_branch = _ScoreDecoder(num_heads=cfg.MODEL.HIDDEN_DIM // 64, hidden_dim=cfg.MODEL.HIDDEN_DIM, pool_size=4)
+    return MixFormer_RGBT_OnlineScore(bb, build_box_head(cfg), _fusion(cfg), score_branch, cfg).eval()
+
+
 def build_mixformer_vit_online_score(cfg, settings=None, train=False) -> MixFormerOnlineScore:
     _require_inference(train)
     backbone = _Backbone(cfg.MODEL.VIT_TYPE, cfg.DATA.SEARCH.SIZE, cfg.DATA.TEMPLATE.SIZE, timm_leftovers=True)
@@ -621,4 +653,5 @@ BUILDERS = {
     "mixformer_vit_rgbt_unibackbone": build_mixformer_vit_rgbt_uni,
     "asymmetric_shared": build_asymmetric_shared,
     "asymmetric_shared_ce": build_asymmetric_shared_ce,
+    "asymmetric_shared_online": build_asymmetric_shared_online_score,
 }

@@ -93,7 +93,10 @@ _VARIANTS = {
     "asymmetric_shared_ce": ([_RGBT, {"MODEL": {"BACKBONE": {"STRIDE": 16, "CE_LOC": [3, 6, 9],
                                                                "CE_KEEP_RATIO": [0.7, 0.7, 0.7],
                                                                "CE_TEMPLATE_RANGE": "CTR_POINT"}}}], []),
-    "asymmetric_shared_online": ([_RGBT, _ONLINE], []),
+    # lib/config/asymmetric_shared_online/config.py: the RGB-T tree with TRACKER_/SCORE_PRETRAINED_PATH instead of
+    # RGBT_PRETRAINED_PATH (no ONLINE_SIZES: the tracker class falls back to online_size 3 / its own defaults)
+    "asymmetric_shared_online": ([_RGBT, {"MODEL": {"TRACKER_PRETRAINED_PATH": "", "SCORE_PRETRAINED_PATH": ""}}],
+                                 [("MODEL", "RGBT_PRETRAINED_PATH")]),
     "mixformer_vit_online": ([_ONLINE], [("MODEL", "FUSION_LAYERS"), ("TEST", "LOAD_FROME_TRAIN_RESULT")]),
     "mixformer_convmae_online": ([_ONLINE, {"MODEL": {"VIT_TYPE": "convmae_base"}}],
                                  [("MODEL", "FUSION_LAYERS"), ("TEST", "LOAD_FROME_TRAIN_RESULT")]),

@@ -26,9 +26,10 @@ VIT_DIMS = {"base_patch16": dict(dim=768, depth=12, heads=12), "large_patch16": 
             # ConvMAE (lib/models/mixformer_convmae/mixformer_online.py:395-410): conv stem (4,2,2) then MixViT blocks
             "convmae_base": dict(dim=768, depth=11, heads=12, stem=(256, 384)),
             "convmae_large": dict(dim=1024, depth=20, heads=16, stem=(384, 768))}
-STACKED = ("mixformer_vit_rgbt_shared", "mixformer_vit_rgbt_unibackbone", "asymmetric_shared", "asymmetric_shared_ce")
-CROSS_MODAL = ("asymmetric_shared", "asymmetric_shared_ce")
-PER_MODALITY_LN = ("mixformer_vit_rgbt_shared", "asymmetric_shared", "asymmetric_shared_ce")
+STACKED = ("mixformer_vit_rgbt_shared", "mixformer_vit_rgbt_unibackbone", "asymmetric_shared", "asymmetric_shared_ce",
+           "asymmetric_shared_online")
+CROSS_MODAL = ("asymmetric_shared", "asymmetric_shared_ce", "asymmetric_shared_online")
+PER_MODALITY_LN = ("mixformer_vit_rgbt_shared", "asymmetric_shared", "asymmetric_shared_ce", "asymmetric_shared_online")
 
 
 def _f32(t, dev):

@@ -262,3 +262,57 @@ class ConvMAEOnlineEngine(OnlineEngine):
         ops.gemm(p3, st["pe3_w"], st["pe3_b"], out=y3)
         # LN + GELU of patch_embed3, written straight into the token order of the embedding GEMM (patch_embed4)
         self._ln_act(y3, st["pe3_ln"], True, buf, seg_rows=H3 * H3, out_seq_rows=tok_per_seq, out_row_off=tok_off)
+
+
+class AsymOnlineEngine(OnlineEngine):
+    """asymmetric_shared backbone + fusion + corner head (engine.ForwardEngine, batch-stacked modalities, cross-modal
+    attention) with the SPM score head on top (lib/models/mixformer_vit_rgbt/asymmetric_shared_online.py:352-401): the
+    score decoder pools the FUSED search map at the predicted box and attends the first-template tokens of BOTH
+    modalities (`torch.cat(torch.split(template, [N, N], dim=0), dim=2)`: RGB tokens first, then infrared)."""
+
+    def _spm_tiles(self, B, T):
+        """One query row per sequence; keys = the sequence's 16 pooled tokens (T = 16) or its two template segments
+        (T = 2 * gt^2: rows [b*Tm, +Tm) of the RGB half and of the infrared half of the stacked template buffer)."""
+        Tm = self.gt * self.gt
+        if T != 2 * Tm:
+            return super()._spm_tiles(B, T)
+        key = ("spm2", B, T)
+        hit = self._tiles.get(key)
+        if hit is None:
+            recs = [[b, 1, b, 2, b * Tm, (B + b) * Tm, 0, Tm, Tm, 0, 1, 1, 0, 0, 0, 0] for b in range(B)]
+            hit = (torch.from_numpy(np.asarray(recs, dtype=np.int32)).to(self.dev), T)
+            self._tiles[key] = hit
+        return hit
+
+    def forward(self, template, online_template, search, want_maps=True, run_score_head=False, gt_bboxes=None):
+        res = ForwardEngine.forward(self, template, online_template, search, want_maps=want_maps)
+        if not run_score_head:
+            return res
+        B = res["pred_boxes"].shape[0]
+        HW, C, Tm = self.Ls0, self.dim, self.gt * self.gt
+        tag = ("spm", B)
+        # fused search map as fp32 rows: the GroupNorm of fusion_vi's output conv once more, from its fp32 pre-activation
+        # (bf16 mode keeps only a bf16 copy of the fused map; PrRoIPool integrates fp32 like the reference)
+        F_ = self.fusion
+        if "cat_convs" in F_:
+            raise NotImplementedError("asymmetric_shared_online with RGBT_Fusion_Cat: no shipped YAML uses it")
+        pre = self._buf((("fus", B), "o"), "gn_pre", (B * HW, 768), torch.float32)
+        feat32 = self._buf(tag, "feat32", (B * HW, C), torch.float32)
+        ops.groupnorm(pre, B, HW, 32, F_["out"]["gn_w"], F_["out"]["gn_b"], 1e-5, out_f32=feat32)
+        # first-template rows of both modalities out of the residual stream: [RGB x B | infrared x B] blocks of Tm rows
+        x, N = self._last_x
+        templ = self._buf(tag, "templ2", (2 * B * Tm, C), self.act)
+        ops.copy_rows(x, N, 0, Tm, 2 * B, templ)
+        if gt_bboxes is not None:
+            xyxy = gt_bboxes.detach().to(device=self.dev, dtype=torch.float32).reshape(B, 4).contiguous()
+        else:
+            xyxy = self._last_xyxy
+        res["pred_scores"] = self._run_spm(feat32, templ, xyxy, B)
+        return res
+
+    def set_online(self, *a, **k):
+        # the reference's own set_online of this class references attributes that do not exist (backbone_v / backbone_i,
+        # asymmetric_shared_online.py:386-387): the RGB-T models support the full forward only (SURVEY 8b)
+        raise NotImplementedError("asymmetric_shared_online supports the full forward only (as in the reference)")
+
+    forward_test = set_online

@@ -26,6 +26,7 @@ DEFAULT_YAML = {
     "mixformer_vit_rgbt_unibackbone": "attention_lasher_newfusion_2layer",
     "asymmetric_shared": "attention_lasher_newfusion_2layer",
     "asymmetric_shared_ce": "attention_lasher_newfusion_2layer",
+    "asymmetric_shared_online": "attention_lasher_newfusion_2layer",
     "mixformer_vit_online": "baseline",
     "mixformer_convmae_online": "baseline",
 }

@@ -124,6 +124,41 @@ EXTRA = [("mixformer_vit_rgbt_shared", "baseline_attention_lasher_newfusion_2lay
          ("mixformer_vit", "baseline_large")]                                            # MixViT-L RGB-only, 384 / 192
 
 
+def main_asym_online():
+    """asymmetric_shared_online (asymmetric_shared + SPM on the fused map, asymmetric_shared_online.py:337-413): the
+    reference module with run_score_head=True against the oracle; sharpened and plain weight sets, batch 2."""
+    variant = "asymmetric_shared_online"
+    for sharpen in (True, False):
+        model, cfg = synthetic.make_model(variant, WEIGHT_SEED, sharpen=sharpen)
+        sd = model.state_dict()
+        inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+        ref_model, _ = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant])
+        missing, unexpected = ref_model.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        ref_model.score_branch.search_prroipool = _cpu_prroi_module()
+        cap = {}
+        orig = ref_model.box_head.get_score_map
+
+        def hooked(x, orig=orig, cap=cap):
+            tl, br = orig(x)
+            cap["maps"] = torch.stack([tl.flatten(1), br.flatten(1)], dim=1)
+            return tl, br
+        ref_model.box_head.get_score_map = hooked
+        with torch.no_grad():
+            out, _ = ref_model(*inputs, run_score_head=True)
+        ora = O.forward(variant, sd, cfg, *inputs)
+        d_box = (out["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
+        d_map = (cap["maps"] - ora["score_maps"]).abs().max().item()
+        d_sc = (out["pred_scores"] - ora["pred_scores"]).abs().max().item()
+        print(f"{variant} ({'sharpened' if sharpen else 'plain'}): oracle vs reference boxes {d_box:.3e} maps {d_map:.3e} "
+              f"scores {d_sc:.3e}   scores {out['pred_scores'].tolist()}")
+        assert d_box <= 1e-5 and d_map <= 2e-4 and d_sc <= 1e-4
+        tag = "" if sharpen else "_plain"
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}__spm{tag}_b{BATCH}.npz"),
+                            pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy(),
+                            pred_scores=out["pred_scores"].numpy())
+
+
 ONLY = []      # restrict main_extra to these (variant, yaml) pairs (command line: extra:<variant>:<yaml>)
 
 
@@ -162,6 +197,10 @@ def main(variants):
     for v in [v for v in variants if v.startswith("extra:")]:
         ONLY.append(tuple(v.split(":")[1:3]))
         variants = [x for x in variants if x != v] + (["extra"] if "extra" not in variants else [])
+    if "asymmetric_shared_online" in variants:
+        torch.set_num_threads(8)
+        main_asym_online()
+        variants = [v for v in variants if v != "asymmetric_shared_online"]
     if "extra" in variants:
         torch.set_num_threads(8)
         main_extra()

@@ -281,6 +281,7 @@ def backbone_asymmetric(sd, x_t, x_ot, x_s, heads, depth, ce_loc=None, ce_keep=N
     x_v = recover(x_v, removed_v, gidx_v)
     x_i = recover(x_i, removed_i, gidx_i)
     x = torch.cat([x_v, x_i], dim=0)
+    aux["template_tokens"] = x[:, :n_t // 2]            # first template's tokens (asymmetric_shared_online.py:263-269)
     return x[:, n_t:], aux
 
 
@@ -645,7 +646,7 @@ def forward(variant, sd, cfg, template, online_template, search):
                 s, _ = backbone_plain(bsd, t, ot, sr, d["heads"], d["depth"], per_modality_ln=True)
             elif variant == "mixformer_vit_rgbt_unibackbone":
                 s, _ = backbone_plain(bsd, t, ot, sr, d["heads"], d["depth"])
-            elif variant == "asymmetric_shared":
+            elif variant in ("asymmetric_shared", "asymmetric_shared_online"):
                 s, aux = backbone_asymmetric(bsd, t, ot, sr, d["heads"], d["depth"])
             elif variant == "asymmetric_shared_ce":
                 s, aux = backbone_asymmetric(bsd, t, ot, sr, d["heads"], d["depth"], mc["ce_loc"], mc["ce_keep"])
@@ -656,5 +657,15 @@ def forward(variant, sd, cfg, template, online_template, search):
         fv, fi = _tokens_to_map(sv, g).contiguous(), _tokens_to_map(si, g).contiguous()
         feat = fusion_vi(_sub(sd, "fusion_vi."), fv, fi, mc["fusion_class"])
         aux["search_v"], aux["search_i"] = fv, fi
+    templ_tok = aux.pop("template_tokens", None)
+    if variant == "asymmetric_shared_online":
+        # MixFormer_RGBT_OnlineScore.forward lib/models/mixformer_vit_rgbt/asymmetric_shared_online.py:352-373: the SPM sees
+        # the FUSED search map and both modalities' first-template maps stacked along H (cat(split(template), dim=2))
+        gt = mc["template_size"] // 16
+        n = templ_tok.shape[0] // 2
+        tmap = torch.cat([_tokens_to_map(templ_tok[:n], gt), _tokens_to_map(templ_tok[n:], gt)], dim=2)
+        out = forward_head_online(sd, feat, tmap, mc, d["heads"])
+        out.update(aux)
+        return out
     boxes, maps = box_head(_sub(sd, "box_head."), feat, mc)
     return dict(pred_boxes=boxes, score_maps=maps, feat=feat, **aux)

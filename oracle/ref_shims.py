@@ -160,6 +160,9 @@ VARIANTS = {
                                        "build_mixformer_vit_rgbt_uni", "mixformer_vit_rgbt_unibackbone"),
     "asymmetric_shared": ("lib.config.asymmetric_shared.config", "lib.models.mixformer_vit_rgbt.asymmetric_shared",
                           "build_asymmetric_shared", "asymmetric_shared"),
+    "asymmetric_shared_online": ("lib.config.asymmetric_shared_online.config",
+                                 "lib.models.mixformer_vit_rgbt.asymmetric_shared_online",
+                                 "build_asymmetric_shared_online_score", "asymmetric_shared_online"),
     "asymmetric_shared_ce": ("lib.config.asymmetric_shared_ce.config",
                              "lib.models.mixformer_vit_rgbt.asymmetric_shared_ce",
                              "build_asymmetric_shared_ce", "asymmetric_shared_ce"),

@@ -75,7 +75,7 @@ def test_online_score_state_dict_layout():
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("variant", ["mixformer_vit", "asymmetric_shared_ce", "mixformer_vit_online",
-                                     "mixformer_convmae_online"])
+                                     "mixformer_convmae_online", "asymmetric_shared_online"])
 def test_reference_builder_accepts_our_state_dict(variant):
     """strict=True load of our state_dict INTO the unmodified reference module (and the reverse)."""
     import mmt_b200  # noqa: F401

@@ -323,3 +323,35 @@ def test_full_size_batch_independence(built_lib, variant, batch):
     b = full.view(-1, 4)
     assert bool(torch.isfinite(b).all()) and bool(((b[:, :2] >= 0) & (b[:, :2] <= 1)).all())
     assert b[:, :2].std().item() > 1e-3            # boxes differ between sequences (not a constant output)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("weights", ["", "_plain"])
+def test_asymmetric_shared_online(built_lib, weights, precision):
+    """asymmetric_shared + SPM score head on the fused map (lib/models/mixformer_vit_rgbt/asymmetric_shared_online.py:
+    337-413, run_score_head=True) against the reference's golden boxes, corner maps and score logits."""
+    from mmt_b200 import synthetic
+    variant = "asymmetric_shared_online"
+    model, cfg = synthetic.make_model(variant, 0, sharpen=(weights == ""))
+    model = model.cuda().set_precision(precision)
+    inputs = synthetic.make_inputs(variant, cfg, 2, 1, device="cuda")
+    res = model.engine().forward(*inputs, run_score_head=True)
+    out, coords = model(*inputs, run_score_head=True)
+    torch.cuda.synchronize()
+    g = np.load(os.path.join(GOLDEN, f"{variant}__spm{weights}_b2.npz"))
+    d_box = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * cfg.DATA.SEARCH.SIZE
+    d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
+    d_sc = np.abs(out["pred_scores"].cpu().numpy() - g["pred_scores"]).max()
+    print(f"{variant}{weights} {precision}: boxes {d_box:.3e} px  maps {d_map:.3e}  scores {d_sc:.3e}")
+    assert torch.equal(out["pred_boxes"], res["pred_boxes"]) and out["pred_scores"].shape == (2,)
+    if precision == "fp32":
+        assert d_box <= 1e-4 * cfg.DATA.SEARCH.SIZE and d_map <= 2e-4 and d_sc <= 1e-4
+    elif weights == "_plain":
+        assert d_box <= 0.5 and d_map <= 1e-2 and d_sc <= 1e-2            # north-star bf16 bounds on random-init weights
+    else:
+        assert d_box <= 2.0 and d_map <= 2e-2 * np.abs(g["score_maps"]).max() and d_sc <= 2e-2
+    # without the score head the reference returns boxes only (run_score_head defaults to False, :352)
+    out2, _ = model(*inputs)
+    assert "pred_scores" not in out2 and torch.equal(out2["pred_boxes"], out["pred_boxes"])
+    with pytest.raises(NotImplementedError):
+        model.engine().set_online(None, None)

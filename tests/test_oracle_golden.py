@@ -29,6 +29,22 @@ def test_oracle_matches_reference_vectors(variant):
             assert out["ce_keep_v"][j].shape[1] == (227, 159, 112)[j]     # 324 -> 227 -> 159 -> 112
 
 
+def test_asymmetric_shared_online_oracle_matches_reference_vectors():
+    """asymmetric_shared + SPM on the fused map (asymmetric_shared_online.py:337-413): boxes, maps and score logits the
+    UNMODIFIED reference module produced (oracle/gen_golden.py main_asym_online)."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    variant = "asymmetric_shared_online"
+    model, cfg = synthetic.make_model(variant, 0)
+    inputs = synthetic.make_inputs(variant, cfg, 2, 1)
+    out = O.forward(variant, model.state_dict(), cfg, *inputs)
+    g = np.load(os.path.join(GOLDEN, f"{variant}__spm_b2.npz"))
+    assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
+    assert np.abs(out["score_maps"].numpy() - g["score_maps"]).max() <= 2e-4
+    assert np.abs(out["pred_scores"].numpy() - g["pred_scores"]).max() <= 1e-5
+
+
 @pytest.mark.parametrize("variant", ["mixformer_vit_online", "mixformer_convmae_online"])
 def test_online_oracle_matches_reference_vectors(variant):
     """Online trackers: full forward with the SPM score, and set_online + forward_test on seeded crops."""
