@@ -281,8 +281,11 @@ class OnlineBatchedTracker(BatchedTracker):
     cache of the reference, which assumes batch 1 - mixformer_vit/mixformer.py:238) is served per sequence by the
     model's own `set_online`/`forward_test` and is not batched here."""
 
-    def __init__(self, network, params, update_interval=200, max_score_decay=1.0, capacity=1024):
-        super().__init__(network, params, update_intervals=(), n_mod=1, use_template_cache=False, capacity=capacity)
+    def __init__(self, network, params, update_interval=200, max_score_decay=1.0, capacity=1024, n_mod=1, jet_mask=None):
+        # n_mod = 2: the RGB-T online tracker (lib/test/tracker/asymmetric_shared_online.py:62-119: the same bookkeeping
+        # on [v, i] crop pairs, Preprocessor_Multimodal, no score decay)
+        super().__init__(network, params, update_intervals=(), n_mod=n_mod, use_template_cache=False, capacity=capacity,
+                         jet_mask=jet_mask)
         self.update_interval = int(update_interval)
         self.max_score_decay = float(max_score_decay)
 
@@ -308,13 +311,16 @@ class OnlineBatchedTracker(BatchedTracker):
         if active is not None:
             act_np = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
             act = torch.from_numpy(act_np).to(self.device)
-            skip = [not a for a in act_np]
+            skip = [not act_np[i % self.B] for i in range(self.n_mod * self.B)]
         live = np.ones(self.B, dtype=bool) if act_np is None else act_np.astype(bool)
         self.frame_ids[live] += 1
-        k = self.up.upload(self._flatten(frames), skip=skip)
+        imgs = self._flatten([f if f is not None else [None] * self.n_mod for f in frames]) if active is not None \
+            else self._flatten(frames)
+        k = self.up.upload(imgs, skip=skip)
         self._crop(k, float(p.search_factor), int(p.search_size), self.search, active=act, rf=self.rf)
         with torch.inference_mode():
-            out, coords = self.network(self.template[0], self.online_template[0], self.search[0], run_score_head=True)
+            out, coords = self.network(self._model_args(self.template), self._model_args(self.online_template),
+                                       self._model_args(self.search), run_score_head=True)
         logits = out["pred_scores"].reshape(-1).contiguous()
         self.scores[self.frame_id].copy_(logits)
         ops.track_update(coords.view(-1, 4), self.rf, self.up.dims, self.state, int(p.search_size), self.MARGIN,

@@ -24,7 +24,7 @@ from .frames import BatchedTracker, OnlineBatchedTracker
 # Preprocessor_Multimodal -> JET on the infrared crop (bit 1); Preprocessor_wo_mask -> none
 _JET_MASK = {"mixformer_vit": 0, "mixformer_vit_rgbt": 0, "mixformer_vit_rgbt_shared": 0b10,
              "mixformer_vit_rgbt_unibackbone": 0b10, "asymmetric_shared": 0b10, "asymmetric_shared_ce": 0b10}
-_ONLINE = ("mixformer_vit_online", "mixformer_convmae_online")
+_ONLINE = ("mixformer_vit_online", "mixformer_convmae_online", "asymmetric_shared_online")
 
 
 class _TrackerBase:
@@ -91,15 +91,18 @@ class _OnlineTracker(_TrackerBase):
                                       "model's own set_online()/forward_test(), not by this class")
 
     def initialize(self, image, info: dict):
+        rgbt = self.variant == "asymmetric_shared_online"       # lib/test/tracker/asymmetric_shared_online.py
+        box = info["init_bbox"][0] if rgbt else info["init_bbox"]
         self._trk = OnlineBatchedTracker(self.network, self.params, update_interval=self.update_interval,
-                                         max_score_decay=self.max_score_decay)
-        self._trk.initialize([image], [list(info["init_bbox"])])
-        self.state = [float(v) for v in info["init_bbox"]]
+                                         max_score_decay=self.max_score_decay, n_mod=2 if rgbt else 1,
+                                         jet_mask=0b10 if rgbt else 0)
+        self._trk.initialize([list(image) if rgbt else image], [list(box)])
+        self.state = [float(v) for v in box]
         self.frame_id = 0
 
     def track(self, image, info: dict = None):
         self.frame_id += 1
-        self._trk.track([image])
+        self._trk.track([list(image) if self.variant == "asymmetric_shared_online" else image])
         return self._result()
 
 

@@ -211,12 +211,18 @@ class OnlineTrackerOracle:
     callable (template, online_template, search) -> (pred_box_f32[4] cxcywh, logit)."""
 
     def __init__(self, network, template_factor, template_size, search_factor, search_size, update_interval,
-                 max_score_decay=1.0):
+                 max_score_decay=1.0, rgbt=False):
+        # rgbt: the RGB-T online class (lib/test/tracker/asymmetric_shared_online.py:62-119): images and crops are [v, i]
+        # pairs, Preprocessor_Multimodal (JET on the infrared crop), same bookkeeping
         self.net = network
         self.tf, self.ts, self.sf, self.ss = template_factor, template_size, search_factor, search_size
-        self.update_interval, self.decay = update_interval, max_score_decay
+        self.update_interval, self.decay, self.rgbt = update_interval, max_score_decay, rgbt
 
     def _crop(self, image, state, factor, size):
+        if self.rgbt:
+            cv_, rf = sample_target(image[0], state, factor, size)
+            ci_, _ = sample_target(image[1], state, factor, size)
+            return list(process_multimodal(cv_, ci_)), rf
         c, rf = sample_target(image, state, factor, size)
         return normalize(c), rf
 
@@ -229,7 +235,7 @@ class OnlineTrackerOracle:
         self.frame_id = 0
 
     def track(self, image):
-        H, W = image.shape[:2]
+        H, W = (image[0] if self.rgbt else image).shape[:2]
         self.frame_id += 1
         search, rf = self._crop(image, self.state, self.sf, self.ss)
         pred, logit = self.net(self.template, self.online_template, search)

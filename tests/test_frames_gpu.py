@@ -434,3 +434,32 @@ def test_batched_tracker_full_size_batch_independence(built_lib):
     assert full.shape == (T, B, 4) and np.isfinite(full).all()
     assert np.array_equal(full[:, pick], sub)
     assert len({tuple(r) for r in full[T - 1].round(3).tolist()}) > B // 2       # the sequences really differ
+
+
+def test_rgbt_online_tracker_class(built_lib):
+    """`get_tracker_class("asymmetric_shared_online")` (lib/test/tracker/asymmetric_shared_online.py: RGB-T crops, SPM
+    score on the fused map, score-driven online-template candidate) against the oracle loop with the same network."""
+    from mmt_b200 import synthetic, trackers
+    cfg = synthetic.load_variant_config("asymmetric_shared_online")
+    params = types.SimpleNamespace(cfg=cfg, template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE, checkpoint=None, save_all_boxes=False,
+                                   update_interval=2)
+    torch.manual_seed(0)
+    trk = trackers.get_tracker_class("asymmetric_shared_online")(params, "lasher")
+    synthetic.sharpen_(trk.network, torch.Generator().manual_seed(1000))
+    trk.network.load_state_dict(trk.network.state_dict())                 # re-pack the engine arena after the edit
+    T, H, W = 6, 170, 230
+    vid = [GG.seeded_video(61, H, W, T), GG.seeded_video(62, H, W, T)]
+    box = [60.0, 45.0, 70.0, 52.0]
+    trk.initialize([vid[0][0], vid[1][0]], {"init_bbox": (box, box)})
+    got = [trk.track([vid[0][t], vid[1][t]])["target_bbox"] for t in range(1, T)]
+
+    def net(template, online_template, search):
+        to = lambda pair: [torch.from_numpy(a[None]).cuda() for a in pair]
+        out, coords = trk.network(to(template), to(online_template), to(search), run_score_head=True)
+        return coords.view(-1, 4).cpu().numpy()[0], out["pred_scores"].reshape(-1).cpu().numpy()[0]
+
+    orc = FO.OnlineTrackerOracle(net, 2.0, params.template_size, 4.5, params.search_size, 2, rgbt=True)
+    orc.initialize([vid[0][0], vid[1][0]], box)
+    for t in range(1, T):
+        assert got[t - 1] == [float(v) for v in orc.track([vid[0][t], vid[1][t]])], t
