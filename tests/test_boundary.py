@@ -128,3 +128,23 @@ def test_training_and_cpu_are_refused():
     cfg2 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "Attention_Fusion_512"})
     with pytest.raises(KeyError):                   # a fusion class no shipped YAML names: refused loudly, no fallback
         builders.build_mixformer_vit_rgbt(cfg2)
+
+
+def test_attention_tile_order_is_heavy_first_and_stable(built_lib):
+    """ops.order_tiles: records sorted by key count (descending), siblings of equal cost keep their order - the
+    persistent attention kernel's stride walk relies on both (balance, and L2 reuse of a sequence's K/V)."""
+    import numpy as np
+    from mmt_b200 import ops
+    recs = []
+    for s in range(3):                                   # per sequence: template tile (128 keys), 3 search tiles (452 keys)
+        base = s * 452
+        recs.append([base, 128, base, 1, base, 0, 0, 128, 0, 0, 0, 0, 0, 0, 0, 0])
+        for o, q in ((0, 128), (128, 128), (256, 68)):
+            recs.append([base + 128 + o, q, base + 128 + o, 1, base, 0, 0, 452, 0, 0, 0, 0, 0, 0, 0, 0])
+    out = ops.order_tiles(recs)
+    assert out.dtype == np.int32 and out.shape == (12, 16)
+    keys = out[:, 7:10].sum(1)
+    assert list(keys) == [452] * 9 + [128] * 3
+    assert list(out[:9, 0]) == [128, 256, 384, 580, 708, 836, 1032, 1160, 1288]      # search tiles, sequence by sequence
+    assert list(out[9:, 0]) == [0, 452, 904]
+    assert sorted(map(tuple, out.tolist())) == sorted(map(tuple, recs))              # a permutation, nothing altered
