@@ -548,6 +548,17 @@ class MixFormerOnlineScore(_EngineModule):
         res = self.engine().forward_test(self._sq(search), run_score_head=run_score_head, gt_bboxes=gt_bboxes)
         return self._finish_online(res, run_score_head)
 
+    # Batched form of the cached path (an extension: the reference's set_online / forward_test hold ONE sequence):
+    # template [B,3,T,T], online_template [B,n,3,T,T], search [B,3,S,S]; per sequence bit-identical to the calls above.
+    @torch.no_grad()
+    def set_online_batch(self, template, online_template):
+        self.engine().set_online_batch(template, online_template)
+
+    @torch.no_grad()
+    def forward_test_batch(self, search, run_score_head=True, gt_bboxes=None):
+        res = self.engine().forward_test_batch(search, run_score_head=run_score_head, gt_bboxes=gt_bboxes)
+        return self._finish_online(res, run_score_head)
+
 
 def _require_inference(train):
     if train:

@@ -179,6 +179,65 @@ class OnlineEngine(ForwardEngine):
         return res
 
 
+    # ------------------------------------------------------------------------------------------ cached path, B sequences
+    # The reference's set_online / forward_test assume ONE sequence (x_ot.reshape(1, -1, C), mixformer_online.py:252).
+    # The same computation for B independent sequences at once: every sequence keeps its own (1 + n) * T cached template
+    # rows per layer, its search tokens read that block and their own rows.  Per sequence the result is bit-identical to
+    # the batch-1 path above (same 128-row tile boundaries inside a sequence, row-independent GEMMs).
+    def set_online_batch(self, template, online_template):
+        """template [B, 3, T, T]; online_template [B, n, 3, T, T] (n online templates per sequence)."""
+        t = self._check_img(template, self.template_size)
+        if online_template.dim() != 5 or online_template.shape[0] != t.shape[0]:
+            raise RuntimeError(f"online_template must be [B, n, 3, T, T] with B = {t.shape[0]}, got {tuple(online_template.shape)}")
+        B, n = online_template.shape[0], online_template.shape[1]
+        T = self.gt * self.gt
+        Tm = (1 + n) * T
+        bb = self.bbs[0]
+        tag = ("online_tb", B, Tm)
+        x = self._buf(tag, "x", (B * Tm, self.dim), torch.float32)
+        patches = self._embed_buf(B * Tm)
+        self._stage_tokens(bb, t, patches, 0, Tm)
+        for k in range(n):
+            self._stage_tokens(bb, self._check_img(online_template[:, k], self.template_size), patches, (1 + k) * T, Tm)
+        pos_t = self._ws.get("pos_t")
+        if pos_t is None:
+            pos_t = bb["pos"][:T].contiguous()
+            self._ws["pos_t"] = pos_t
+            self._ws["pos_s"] = bb["pos"][2 * T:].contiguous()
+        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, pos_t, out=x)
+        mem = [self._buf(tag, f"qkv_mem{i}", (B * Tm, 3 * self.dim), self.act) for i in range(self.depth)]
+        tiles = self._seq_tiles(f"set_online_b{Tm}", B, Tm, lambda sq: [(0, sq * Tm, Tm)])
+        for i, blk in enumerate(bb["blocks"]):
+            self._block(blk, x, B, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=mem[i])
+        templ = ops.copy_rows(x, Tm, 0, T, B, self._buf(tag, "templ_rows", (B * T, self.dim), self.act))
+        self._batch_cache = dict(B=B, Tm=Tm, mem=mem, templ=templ)
+
+    def forward_test_batch(self, search, want_maps=True, run_score_head=True, gt_bboxes=None):
+        """search [B, 3, S, S] against the cache of set_online_batch (same B)."""
+        c = getattr(self, "_batch_cache", None)
+        if c is None:
+            raise RuntimeError("forward_test_batch called before set_online_batch")
+        s = self._check_img(search, self.search_size)
+        B, Tm = c["B"], c["Tm"]
+        if s.shape[0] != B:
+            raise RuntimeError(f"cached templates are for {B} sequences, got {s.shape[0]} search crops")
+        Ls, bb = self.Ls0, self.bbs[0]
+        tag = ("online_sb", B, Tm)
+        x = self._buf(tag, "x", (B * Ls, self.dim), torch.float32)
+        patches = self._embed_buf(B * Ls)
+        self._stage_tokens(bb, s, patches, 0, Ls)
+        ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_s"], out=x)
+        tiles = self._seq_tiles(f"forward_test_b{Tm}", B, Ls, lambda sq: [(1, sq * Tm, Tm), (0, sq * Ls, Ls)])
+        for i, blk in enumerate(bb["blocks"]):
+            self._block(blk, x, B, Ls, 0, 0, False, tag, tiles=tiles, qkv1=c["mem"][i])
+        feat = ops.copy_rows(x, Ls, 0, Ls, B, self._buf(tag, "search_rows", (B * Ls, self.dim), self.act))
+        boxes, maps = self._run_head(feat, B, want_maps)
+        res = dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feat)
+        if run_score_head:
+            res["pred_scores"] = self._scores(x, Ls, 0, B, c["templ"], gt_bboxes)
+        return res
+
+
 class ConvMAEOnlineEngine(OnlineEngine):
     """mixformer_convmae_online: the same online engine behind the ConvMAE conv stem
     (lib/models/mixformer_convmae/mixformer_online.py:266-392): per crop, Conv 4x4/4 + LN + GELU, 2 CBlocks,

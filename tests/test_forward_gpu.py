@@ -355,3 +355,30 @@ def test_asymmetric_shared_online(built_lib, weights, precision):
     assert "pred_scores" not in out2 and torch.equal(out2["pred_boxes"], out["pred_boxes"])
     with pytest.raises(NotImplementedError):
         model.engine().set_online(None, None)
+
+
+@pytest.mark.parametrize("variant,B,n", [("mixformer_vit_online", 3, 2), ("mixformer_convmae_online", 2, 3)])
+def test_batched_cached_template_path(built_lib, variant, B, n):
+    """set_online_batch / forward_test_batch (B sequences, n online templates each) against the reference-shaped batch-1
+    set_online / forward_test run per sequence: boxes, corner maps and score logits bit-identical."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model(variant, 0)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(5)
+    ts, ss = cfg.DATA.TEMPLATE.SIZE, cfg.DATA.SEARCH.SIZE
+    t = torch.randn(B, 3, ts, ts, generator=g).cuda()
+    ot = torch.randn(B, n, 3, ts, ts, generator=g).cuda()
+    s = torch.randn(B, 3, ss, ss, generator=g).cuda()
+    model.set_online_batch(t, ot)
+    out, coords = model.forward_test_batch(s, run_score_head=True)
+    maps = model.engine().forward_test_batch(s)["score_maps"].clone()
+    assert coords.shape == (B, 1, 4) and out["pred_scores"].shape == (B,)
+    for b in range(B):
+        model.set_online(t[b:b + 1], ot[b])
+        o1, c1 = model.forward_test(s[b:b + 1], run_score_head=True)
+        m1 = model.engine().forward_test(s[b:b + 1])["score_maps"]
+        assert torch.equal(c1[0], coords[b]), (b, (c1[0] - coords[b]).abs().max().item())
+        assert torch.equal(o1["pred_scores"][0], out["pred_scores"][b])
+        assert torch.equal(m1[0], maps[b])
+    with pytest.raises(RuntimeError):
+        model.forward_test_batch(s[:1])
