@@ -277,17 +277,26 @@ class OnlineBatchedTracker(BatchedTracker):
     with `online_size == 1`: every frame runs the full forward with the SPM score head; the crop at the new box becomes
     the online-template CANDIDATE when its score beats 0.5 and the running maximum (`mmt_online_score_update` + a masked
     `mmt_frame_crop`, no score read-back); every `update_interval` frames the candidate replaces the online template and
-    the bookkeeping restarts from the first template.  `online_size > 1` (the per-sequence `set_online`/`forward_test`
-    cache of the reference, which assumes batch 1 - mixformer_vit/mixformer.py:238) is served per sequence by the
-    model's own `set_online`/`forward_test` and is not batched here."""
+    the bookkeeping restarts from the first template.  `online_size > 1`: the candidate is appended to (then cycled
+    through) a list of online templates and every frame runs `forward_test` against the cached templates - the
+    reference does this for ONE sequence (mixformer_vit/mixformer.py:238); here `set_online_batch` /
+    `forward_test_batch` carry B lock-step sequences."""
 
-    def __init__(self, network, params, update_interval=200, max_score_decay=1.0, capacity=1024, n_mod=1, jet_mask=None):
+    def __init__(self, network, params, update_interval=200, max_score_decay=1.0, capacity=1024, n_mod=1, jet_mask=None,
+                 online_size=1):
         # n_mod = 2: the RGB-T online tracker (lib/test/tracker/asymmetric_shared_online.py:62-119: the same bookkeeping
         # on [v, i] crop pairs, Preprocessor_Multimodal, no score decay)
         super().__init__(network, params, update_intervals=(), n_mod=n_mod, use_template_cache=False, capacity=capacity,
                          jet_mask=jet_mask)
         self.update_interval = int(update_interval)
         self.max_score_decay = float(max_score_decay)
+        # online_size > 1 (mixformer_convmae_online.py:66-68,94-97,115-124): the online templates form a list that grows
+        # to online_size and is then overwritten round-robin; every frame runs the search tokens only against the cached
+        # templates (`set_online_batch` at every list change, `forward_test_batch` per frame).  Lock-step batches only.
+        self.online_size = int(online_size)
+        if self.online_size > 1 and n_mod != 1:
+            raise NotImplementedError("online_size > 1 exists for the RGB-only online trackers (the reference's RGB-T "
+                                      "set_online is broken, asymmetric_shared_online.py:386-387)")
 
     def initialize(self, frames, init_boxes, capacity_hw=None):
         super().initialize(frames, init_boxes, capacity_hw)
@@ -295,8 +304,14 @@ class OnlineBatchedTracker(BatchedTracker):
         self.take = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
         self.online_max_template = self.template.clone()
         self.scores = torch.zeros((self.log.shape[0], self.B), dtype=torch.float32, device=self.device)
+        if self.online_size > 1:
+            self.online_stack = self.template[0].unsqueeze(1).clone()        # [B, 1, 3, T, T]: online_template = template
+            self.online_forget_id = 0
+            self.network.set_online_batch(self.template[0], self.online_stack)
 
     def reset_slot(self, b, frames_b, init_box):
+        if self.online_size > 1:
+            raise NotImplementedError("online_size > 1 runs lock-step batches (one online-template list length for all slots)")
         super().reset_slot(b, frames_b, init_box)
         self.max_score[b:b + 1].fill_(-1.0)
         self.online_max_template[:, b].copy_(self.template[:, b])
@@ -318,9 +333,14 @@ class OnlineBatchedTracker(BatchedTracker):
             else self._flatten(frames)
         k = self.up.upload(imgs, skip=skip)
         self._crop(k, float(p.search_factor), int(p.search_size), self.search, active=act, rf=self.rf)
+        if self.online_size > 1 and active is not None:
+            raise NotImplementedError("online_size > 1 runs lock-step batches")
         with torch.inference_mode():
-            out, coords = self.network(self._model_args(self.template), self._model_args(self.online_template),
-                                       self._model_args(self.search), run_score_head=True)
+            if self.online_size > 1:
+                out, coords = self.network.forward_test_batch(self.search[0], run_score_head=True)
+            else:
+                out, coords = self.network(self._model_args(self.template), self._model_args(self.online_template),
+                                           self._model_args(self.search), run_score_head=True)
         logits = out["pred_scores"].reshape(-1).contiguous()
         self.scores[self.frame_id].copy_(logits)
         ops.track_update(coords.view(-1, 4), self.rf, self.up.dims, self.state, int(p.search_size), self.MARGIN,
@@ -329,7 +349,17 @@ class OnlineBatchedTracker(BatchedTracker):
         self._crop(k, float(p.template_factor), int(p.template_size), self.online_max_template, active=self.take)
         self.up.release(k)
         due = live & (self.frame_ids % self.update_interval == 0)
-        if due.all():
+        if due.all() and self.online_size > 1:
+            cand = self.online_max_template[0]
+            if self.online_stack.shape[1] < self.online_size:
+                self.online_stack = torch.cat([self.online_stack, cand.unsqueeze(1)], dim=1)
+            else:
+                self.online_stack[:, self.online_forget_id].copy_(cand)
+                self.online_forget_id = (self.online_forget_id + 1) % self.online_size
+            self.network.set_online_batch(self.template[0], self.online_stack)
+            self.online_max_template.copy_(self.template)
+            self.max_score.fill_(-1.0)
+        elif due.all():
             self.online_template.copy_(self.online_max_template)
             self.online_max_template.copy_(self.template)
             self.max_score.fill_(-1.0)

@@ -79,23 +79,21 @@ class _FullForwardTracker(_TrackerBase):
 
 
 class _OnlineTracker(_TrackerBase):
-    """lib/test/tracker/mixformer_convmae_online.py:12-145 / mixformer_vit_online.py with online_size == 1."""
+    """lib/test/tracker/mixformer_convmae_online.py:12-145 / mixformer_vit_online.py (params.online_sizes = 1: full
+    forward per frame; > 1: cached templates, list of online templates) and asymmetric_shared_online.py."""
 
     def __init__(self, params, dataset_name):
         super().__init__(params, dataset_name)
         self.update_interval = getattr(params, "update_interval", self.update_intervals[0])
         self.max_score_decay = getattr(params, "max_score_decay", 1.0)
-        online_size = getattr(params, "online_sizes", 1)
-        if online_size != 1:
-            raise NotImplementedError("online_size > 1 (the batch-1 set_online / forward_test cache) is served by the "
-                                      "model's own set_online()/forward_test(), not by this class")
+        self.online_size = int(getattr(params, "online_sizes", 1))        # mixformer_convmae_online.py:45-46
 
     def initialize(self, image, info: dict):
         rgbt = self.variant == "asymmetric_shared_online"       # lib/test/tracker/asymmetric_shared_online.py
         box = info["init_bbox"][0] if rgbt else info["init_bbox"]
         self._trk = OnlineBatchedTracker(self.network, self.params, update_interval=self.update_interval,
                                          max_score_decay=self.max_score_decay, n_mod=2 if rgbt else 1,
-                                         jet_mask=0b10 if rgbt else 0)
+                                         jet_mask=0b10 if rgbt else 0, online_size=1 if rgbt else self.online_size)
         self._trk.initialize([list(image) if rgbt else image], [list(box)])
         self.state = [float(v) for v in box]
         self.frame_id = 0

@@ -211,12 +211,15 @@ class OnlineTrackerOracle:
     callable (template, online_template, search) -> (pred_box_f32[4] cxcywh, logit)."""
 
     def __init__(self, network, template_factor, template_size, search_factor, search_size, update_interval,
-                 max_score_decay=1.0, rgbt=False):
+                 max_score_decay=1.0, rgbt=False, online_size=1):
         # rgbt: the RGB-T online class (lib/test/tracker/asymmetric_shared_online.py:62-119): images and crops are [v, i]
         # pairs, Preprocessor_Multimodal (JET on the infrared crop), same bookkeeping
         self.net = network
         self.tf, self.ts, self.sf, self.ss = template_factor, template_size, search_factor, search_size
         self.update_interval, self.decay, self.rgbt = update_interval, max_score_decay, rgbt
+        # online_size > 1 (mixformer_convmae_online.py:66-68,94-97,115-124): the online templates form a list that grows to
+        # online_size and is then overwritten round-robin; `network` receives the stacked list [n, 3, T, T]
+        self.online_size = online_size
 
     def _crop(self, image, state, factor, size):
         if self.rgbt:
@@ -228,7 +231,8 @@ class OnlineTrackerOracle:
 
     def initialize(self, image, init_box):
         self.template, _ = self._crop(image, list(init_box), self.tf, self.ts)
-        self.online_template = self.template
+        self.online_template = self.template if self.online_size == 1 else np.stack([self.template])
+        self.online_forget_id = 0
         self.online_max_template = self.template
         self.max_pred_score = -1.0
         self.state = [float(v) for v in init_box]
@@ -244,7 +248,14 @@ class OnlineTrackerOracle:
         if take:
             self.online_max_template, _ = self._crop(image, self.state, self.tf, self.ts)
         if self.frame_id % self.update_interval == 0:
-            self.online_template = self.online_max_template
+            if self.online_size == 1:
+                self.online_template = self.online_max_template
+            elif self.online_template.shape[0] < self.online_size:
+                self.online_template = np.concatenate([self.online_template, self.online_max_template[None]])
+            else:
+                self.online_template = self.online_template.copy()
+                self.online_template[self.online_forget_id] = self.online_max_template
+                self.online_forget_id = (self.online_forget_id + 1) % self.online_size
             self.max_pred_score = -1
             self.online_max_template = self.template
         return self.state

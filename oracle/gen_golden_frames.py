@@ -141,6 +141,56 @@ def main_online(out):
     print("online tracker case: ok,", len({s[1] for s in seen}), "distinct online templates")
 
 
+def main_online3(out):
+    """online_size = 3 (the shipped ONLINE_SIZES): UNMODIFIED MixFormerOnline with a stub network whose set_online /
+    forward_test record what they are given; OnlineTrackerOracle(online_size=3) must see the same template stacks."""
+    from lib.test.tracker import mixformer_convmae_online as trk
+    from lib.test.tracker.tracker_utils import Preprocessor_wo_mask
+    o = ONLINE
+    T = o["T"]
+    vid = seeded_video(o["seed"], o["H"], o["W"], T)
+    preds, logits = online_script(T)
+    logits = logits + np.float32(1.0)                    # more frames above 0.5: the list fills up and wraps
+    stub = types.SimpleNamespace()
+    stub.params = types.SimpleNamespace(search_factor=o["search_factor"], search_size=o["search_size"],
+                                        template_factor=o["template_factor"], template_size=o["template_size"], vis_attn=0)
+    stub.preprocessor = Preprocessor_wo_mask()
+    stub.online_size, stub.update_interval, stub.max_score_decay = 3, 2, 1.0
+    stub.save_all_boxes, stub.debug, stub.cfg = False, False, None
+    seen, cur = [], {}
+
+    class Net:
+        def set_online(self, template, online_template):
+            cur["t"], cur["ot"] = sha(template[0].numpy()), sha(online_template.numpy())
+
+        def forward_test(self, search, run_score_head=True):
+            t = stub.frame_id
+            seen.append((cur["t"], cur["ot"], sha(search[0].numpy())))
+            return {"pred_boxes": torch.from_numpy(preds[t]).view(1, 1, 4), "pred_scores": torch.tensor([logits[t]])}, None
+
+    stub.network = Net()
+    stub.map_box_back = types.MethodType(trk.MixFormerOnline.map_box_back, stub)
+    trk.MixFormerOnline.initialize(stub, vid[0], {"init_bbox": list(o["box"])})
+    states = [list(o["box"])]
+    for t in range(1, T):
+        states.append([float(v) for v in trk.MixFormerOnline.track(stub, vid[t])["target_bbox"]])
+    seen_o = []
+
+    def net_o(template, online_template, search):
+        seen_o.append((sha(template), sha(online_template), sha(search)))
+        return preds[orc.frame_id], logits[orc.frame_id]
+
+    orc = FO.OnlineTrackerOracle(net_o, o["template_factor"], o["template_size"], o["search_factor"], o["search_size"], 2,
+                                 online_size=3)
+    orc.initialize(vid[0], o["box"])
+    for t in range(1, T):
+        assert [float(v) for v in orc.track(vid[t])] == states[t], t
+    assert seen_o == seen
+    out["online3_states"] = np.array(states, dtype=np.float64)
+    out["online3_inputs_sha"] = np.array(seen)
+    print("online_size 3 case: ok,", len({s[1] for s in seen}), "distinct online-template stacks")
+
+
 FULL_CASES = (0, 2)        # cases whose uint8 crops are stored in full; the others are stored as SHA-256 digests
 
 
@@ -212,6 +262,7 @@ def main():
             out[f"c{ci}_{k}"] = v
         print(f"case {ci} ({note}): ok, search rf {rec['search_rf']:.6f}")
     main_online(out)
+    main_online3(out)
     out["n_cases"] = np.int64(len(CASES))
     out["params"] = np.array([template_factor, template_size, search_factor, search_size], dtype=np.float64)
     path = os.path.join(GOLDEN, "frames_rgbt.npz")

@@ -463,3 +463,77 @@ def test_rgbt_online_tracker_class(built_lib):
     orc.initialize([vid[0][0], vid[1][0]], box)
     for t in range(1, T):
         assert got[t - 1] == [float(v) for v in orc.track([vid[0][t], vid[1][t]])], t
+
+
+class _ScriptedCachedNet(torch.nn.Module):
+    """Stub with the batched cached-template API: records what set_online_batch / forward_test_batch are given."""
+
+    def __init__(self, preds, logits, B):
+        super().__init__()
+        self.anchor = torch.nn.Parameter(torch.zeros(1))
+        self.preds, self.logits, self.B, self.t = preds, logits, B, 0
+        self.seen, self.cur = [], None
+
+    def set_online_batch(self, template, online_template):
+        torch.cuda.synchronize()
+        self.cur = [(GG.sha(template[b].cpu().numpy()), GG.sha(online_template[b].cpu().numpy())) for b in range(self.B)]
+
+    def forward_test_batch(self, search, run_score_head=True):
+        self.t += 1
+        torch.cuda.synchronize()
+        self.seen.append([self.cur[b] + (GG.sha(search[b].cpu().numpy()),) for b in range(self.B)])
+        boxes = torch.tensor(np.stack([self.preds[self.t]] * self.B), device="cuda").view(-1, 1, 4)
+        return {"pred_boxes": boxes, "pred_scores": torch.full((self.B,), float(self.logits[self.t]), device="cuda")}, boxes
+
+
+def test_online_batched_tracker_online_size_3_matches_reference_fixture(built_lib):
+    """OnlineBatchedTracker(online_size=3): growing / wrapping list of online templates, cached-template calls - states
+    and the digests of every (template, online-template stack, search) handed to the network equal the run of the
+    UNMODIFIED MixFormerOnline class (fixture), for both sequences of the batch."""
+    from mmt_b200 import frames
+    o = GG.ONLINE
+    vid = GG.seeded_video(o["seed"], o["H"], o["W"], o["T"])
+    preds, logits = GG.online_script(o["T"])
+    logits = logits + np.float32(1.0)
+    net = _ScriptedCachedNet(preds, logits, 2).cuda()
+    params = types.SimpleNamespace(template_factor=o["template_factor"], template_size=o["template_size"],
+                                   search_factor=o["search_factor"], search_size=o["search_size"])
+    trk = frames.OnlineBatchedTracker(net, params, update_interval=2, online_size=3)
+    trk.initialize([vid[0], vid[0]], [o["box"], o["box"]])
+    for t in range(1, o["T"]):
+        trk.track([vid[t], vid[t]])
+    got = trk.results()
+    for slot in (0, 1):
+        assert np.array_equal(got[:, slot], GOLD["online3_states"])
+        assert np.array_equal(np.array([s[slot] for s in net.seen]), GOLD["online3_inputs_sha"])
+    with pytest.raises(NotImplementedError):
+        trk.reset_slot(0, vid[0], o["box"])
+
+
+def test_online_tracker_class_with_cached_templates(built_lib):
+    """`get_tracker_class("mixformer_vit_online")` with params.online_sizes = 3 (the real model, cached templates):
+    per-frame boxes equal the oracle loop whose network call is set_online + forward_test on the same model."""
+    from mmt_b200 import synthetic, trackers
+    cfg = synthetic.load_variant_config("mixformer_vit_online")
+    params = types.SimpleNamespace(cfg=cfg, template_factor=2.0, template_size=cfg.DATA.TEMPLATE.SIZE, search_factor=4.5,
+                                   search_size=cfg.DATA.SEARCH.SIZE, checkpoint=None, save_all_boxes=False,
+                                   update_interval=2, online_sizes=3)
+    torch.manual_seed(0)
+    trk = trackers.get_tracker_class("mixformer_vit_online")(params, "lasot")
+    synthetic.sharpen_(trk.network, torch.Generator().manual_seed(1000))
+    trk.network.load_state_dict(trk.network.state_dict())
+    T = 8
+    vid = GG.seeded_video(71, 180, 240, T)
+    box = [80.0, 60.0, 50.0, 40.0]
+    trk.initialize(vid[0], {"init_bbox": box})
+    got = [trk.track(vid[t])["target_bbox"] for t in range(1, T)]
+
+    def net(template, online_template, search):
+        trk.network.set_online(torch.from_numpy(template[None]).cuda(), torch.from_numpy(online_template).cuda())
+        out, coords = trk.network.forward_test(torch.from_numpy(search[None]).cuda(), run_score_head=True)
+        return coords.view(-1, 4).cpu().numpy()[0], out["pred_scores"].reshape(-1).cpu().numpy()[0]
+
+    orc = FO.OnlineTrackerOracle(net, 2.0, params.template_size, 4.5, params.search_size, 2, online_size=3)
+    orc.initialize(vid[0], box)
+    for t in range(1, T):
+        assert got[t - 1] == [float(v) for v in orc.track(vid[t])], t

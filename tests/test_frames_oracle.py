@@ -223,3 +223,25 @@ def test_run_sequences_slot_scheduler(built_lib, tmp_path):
     # sharding: rank 1 of 2 owns s1 and s3 only
     out1 = evaluation.run_sequences(None, None, seqs, batch=2, rank=1, world_size=2, tracker_factory=_RecordingTracker)
     assert sorted(out1) == ["s1", "s3"]
+
+
+def test_online_tracker_oracle_online_size_3_matches_reference_fixture():
+    """online_size = 3: the list of online templates grows, then wraps (mixformer_convmae_online.py:115-124); states and the
+    digests of (template, stacked online templates, search) per frame from the UNMODIFIED reference class."""
+    o = GG.ONLINE
+    vid = GG.seeded_video(o["seed"], o["H"], o["W"], o["T"])
+    preds, logits = GG.online_script(o["T"])
+    logits = logits + np.float32(1.0)
+    seen = []
+
+    def net(template, online_template, search):
+        seen.append((GG.sha(template), GG.sha(online_template), GG.sha(search)))
+        return preds[orc.frame_id], logits[orc.frame_id]
+
+    orc = FO.OnlineTrackerOracle(net, o["template_factor"], o["template_size"], o["search_factor"], o["search_size"], 2,
+                                 online_size=3)
+    orc.initialize(vid[0], o["box"])
+    for t in range(1, o["T"]):
+        assert [float(v) for v in orc.track(vid[t])] == GOLD["online3_states"][t].tolist()
+    assert np.array_equal(np.array(seen), GOLD["online3_inputs_sha"])
+    assert len({s[1] for s in seen}) >= 5
