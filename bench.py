@@ -107,25 +107,48 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_frames_per_s(variant, budget_s, batch=2, threads=None):
-    """Time oracle.forward (the CPU port of the reference forward) on `threads` host threads for about `budget_s`."""
-    import mmt_b200  # noqa: F401
-    from mmt_b200 import synthetic
-    from oracle import mixformer_oracle as O
+def cpu_baseline_frames_per_s(variant, yaml_name, budget_s, batch=8, threads=None):
+    """Time the reference forward on `threads` host threads for about `budget_s`: the UNMODIFIED reference modules
+    when a reference tree is present (build container, or baseline/_ref on the GPU box) - kind "reference" - else
+    oracle.forward, the pinned CPU port - kind "port".  The CPU run happens in a CHILD process (the .cuda() calls in the
+    reference head's constructor must be neutralised for a CPU model, which cannot be done in the bench process)."""
     threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    model, cfg = synthetic.make_model(variant, 0)
-    sd = model.state_dict()
-    inputs = synthetic.make_inputs(variant, cfg, batch, 1)
-    O.forward(variant, sd, cfg, *inputs)            # warm-up
-    times = []
-    t_end = time.perf_counter() + budget_s
-    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
-        t0 = time.perf_counter()
-        O.forward(variant, sd, cfg, *inputs)
-        times.append(time.perf_counter() - t0)
-    med = statistics.median(times)
-    return batch / med, threads, f"{len(times)} forwards of {batch} sequence-frames (fp32, torch CPU, {threads} threads), median"
+    code = (
+        "import sys, os, time, json, statistics, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "import mmt_b200\n"
+        "from mmt_b200 import synthetic\n"
+        f"variant, yaml_name, batch, budget, threads = {variant!r}, {yaml_name!r}, {batch}, {budget_s}, {threads}\n"
+        "torch.set_num_threads(threads)\n"
+        "model, cfg = synthetic.make_model(variant, 0, yaml_name=yaml_name)\n"
+        "sd = model.state_dict()\n"
+        "ref, where = bench.build_reference(variant, yaml_name, sd, cpu_model=True)\n"
+        "if ref is not None:\n"
+        "    kind = 'reference'\n"
+        "    def fwd(i):\n"
+        "        with torch.no_grad():\n"
+        "            return ref(*i)\n"
+        "else:\n"
+        "    from oracle import mixformer_oracle as O\n"
+        "    kind, where = 'port', 'oracle/mixformer_oracle.py'\n"
+        "    fwd = lambda i: O.forward(variant, sd, cfg, *i)\n"
+        "inputs = synthetic.make_inputs(variant, cfg, batch, 1)\n"
+        "fwd(inputs)\n"
+        "times, t_end = [], time.perf_counter() + budget\n"
+        "while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):\n"
+        "    t0 = time.perf_counter(); fwd(inputs); times.append(time.perf_counter() - t0)\n"
+        "print('CPUBASE ' + json.dumps({'value': batch / statistics.median(times), 'kind': kind, 'where': where, 'n': len(times)}))\n")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("CPUBASE ")]
+    if r.returncode != 0 or not line:
+        raise RuntimeError("cpu baseline child failed: " + r.stderr[-2000:])
+    d = json.loads(line[-1][8:])
+    impl = (f"UNMODIFIED reference modules ({d['where']})" if d["kind"] == "reference"
+            else "CPU port of the reference forward (oracle/mixformer_oracle.py)")
+    return d["value"], threads, d["kind"], (f"{d['n']} forwards of {batch} sequence-frames of the bench workload, {impl}, fp32, "
+                                            f"torch CPU, {threads} threads, median")
 
 
 def frame_path_bench(model, cfg, variant, B, steps, dev, cpu_budget):
@@ -203,42 +226,203 @@ def frame_path_bench(model, cfg, variant, B, steps, dev, cpu_budget):
     return out
 
 
+def workload_config(variant, yaml_name, cfg, B, world, rgbt):
+    """The `config` object of the JSON line - identical in the b200 arm and the reference arm."""
+    from mmt_b200 import synthetic
+    return {"workload": f"{variant} ({yaml_name or synthetic.DEFAULT_YAML[variant]}.yaml) "
+                        f"{'RGB-T two-modality' if rgbt else 'RGB'} full forward "
+                        f"({cfg.DATA.TEMPLATE.SIZE}^2 template + online template, {cfg.DATA.SEARCH.SIZE}^2 search), "
+                        f"bs={B} sequences per GPU, seeded random-init weights, N(0,1) crops",
+            "batch_per_gpu": B, "sequences": B * max(1, world), "parallelism": f"sequence-sharded x{max(1, world)}",
+            "l2": "working set per step (weights 2x209 MB + >1 GB activations) exceeds the 126 MB L2; no flush needed"}
+
+
+def build_reference(variant, yaml_name, sd, cpu_model):
+    """The UNMODIFIED reference module for `variant` (imported from /root/reference or the shipped copy baseline/_ref
+    through oracle/ref_shims.py) carrying the state_dict `sd`; None when no reference tree is available."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        return None, None
+    import io
+    import contextlib
+    import warnings
+    from mmt_b200 import synthetic
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        model, _ = ref_shims.build_reference_model(variant, yaml_name or synthetic.DEFAULT_YAML[variant], cpu_model=cpu_model)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return model, ref_shims.reference_kind()
+
+
 def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores - the UNMODIFIED
+    reference modules when a reference tree is present (/root/reference, or the copy oracle/ship_ref.py ships under
+    baseline/_ref), else the pinned CPU port (oracle/).  Each step = one forward of a bounded sample of the bs=64
+    workload (sized from a calibration forward so that the whole run stays within a few minutes)."""
     if rank != 0:
         return
-    # each "step" = one bounded sample (2 sequence-frames) of the bs=64 workload on the host cores
     import mmt_b200  # noqa: F401
     from mmt_b200 import synthetic
-    from oracle import mixformer_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sample = 2
-    model, cfg = synthetic.make_model(VARIANT, 0)
+    variant, B = args.variant, args.batch
+    model, cfg = synthetic.make_model(variant, 0, yaml_name=args.yaml)
     sd = model.state_dict()
-    inputs = synthetic.make_inputs(VARIANT, cfg, sample, 1)
-    steps, warmup = min(args.steps, 20), min(args.warmup, 3)
-    for _ in range(max(1, warmup)):
-        O.forward(VARIANT, sd, cfg, *inputs)
+    rgbt = variant not in ("mixformer_vit", "mixformer_vit_online", "mixformer_convmae_online")
+    ref, where = build_reference(variant, args.yaml, sd, cpu_model=True)
+    if ref is not None:
+        kind = "reference"
+
+        def fwd(inputs):
+            with torch.no_grad():
+                return ref(*inputs)[1]
+        what = f"UNMODIFIED reference modules ({where}) through oracle/ref_shims.py, fp32, torch CPU"
+    else:
+        from oracle import mixformer_oracle as O
+        kind = "port"
+        fwd = lambda inputs: O.forward(variant, sd, cfg, *inputs)["pred_boxes"]
+        what = "CPU port of the reference forward (oracle/mixformer_oracle.py, pinned against the unmodified reference)"
+    steps, warmup = args.steps, max(1, args.warmup)
+    # calibration: one forward of 4 sequence-frames -> sample size such that (steps + warmup) forwards take ~120 s
+    cal = synthetic.make_inputs(variant, cfg, 4, 1)
+    fwd(cal)
+    t0 = time.perf_counter()
+    fwd(cal)
+    per_frame = (time.perf_counter() - t0) / 4
+    sample = int(max(2, min(B, 120.0 / ((steps + warmup) * per_frame))))
+    inputs = synthetic.make_inputs(variant, cfg, sample, 1)
+    for _ in range(warmup):
+        fwd(inputs)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.forward(VARIANT, sd, cfg, *inputs)
+        boxes = fwd(inputs)
     dt = (time.perf_counter() - t0) / steps
+    assert bool(torch.isfinite(boxes).all())
     v = sample / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(1, warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{VARIANT} ({synthetic.DEFAULT_YAML[VARIANT]}.yaml) RGB-T two-modality full forward "
-                               f"({cfg.DATA.TEMPLATE.SIZE}^2 template + online template, {cfg.DATA.SEARCH.SIZE}^2 search), "
-                               f"bs={BATCH} sequences per GPU, seeded random-init weights, N(0,1) crops",
-                   "batch_per_gpu": BATCH, "sequences": BATCH * max(1, args.gpus),
-                   "parallelism": f"sequence-sharded x{max(1, args.gpus)}",
-                   "sample": f"each step = a {sample}-sequence-frame sample of the bs={BATCH} workload on the host cores"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps x {sample} sequence-frames, CPU port of the reference forward "
-                                   "(oracle/mixformer_oracle.py, pinned against the unmodified reference)"},
+        "config": workload_config(variant, args.yaml, cfg, B, args.gpus, rgbt),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{steps} steps x {sample} sequence-frames of the bs={B} workload per step; {what}, "
+                                   f"{threads} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def gpu_eager_baseline(variant, yaml_name, sd, dev, dev_inputs, dev1, steps):
+    """The UNMODIFIED reference modules in eager mode on this B200 (SURVEY 2b / BASELINE.md section 3 "GPU reference
+    beside it"): fp32 as the reference runs it (its trackers never enable autocast or TF32), fp32 with TF32 matmuls
+    allowed, and under torch.autocast(bfloat16); at the bench batch and at bs=1.  Deformable attention runs through the
+    reference's own CUDA kernel compiled from its sources (oracle/_ref/libmsda_ref.so), else its pure-PyTorch core.
+    CUDA-event timing after warm-up; None when no reference tree travelled."""
+    ref, where = build_reference(variant, yaml_name, sd, cpu_model=False)
+    if ref is None:
+        return {"unavailable": "no reference tree on this box (baseline/_ref not shipped)"}
+    from oracle import ref_shims
+    ref = ref.to(dev)
+    out = {"what": f"UNMODIFIED reference modules ({where}), PyTorch eager on the same GPU, same weights and inputs",
+           "modes": {}}
+    tf32_0 = torch.backends.cuda.matmul.allow_tf32
+
+    def timed(inputs, n, ctx):
+        with torch.no_grad(), ctx():
+            for _ in range(2):
+                ref(*inputs)
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                boxes = ref(*inputs)[1]
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in evs), boxes
+
+    import contextlib
+    B = (dev_inputs[2][0] if isinstance(dev_inputs[2], list) else dev_inputs[2]).shape[0]
+    try:
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+            ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if mode == "bf16_autocast" else contextlib.nullcontext
+            ms, boxes = timed(dev_inputs, max(3, min(steps, 8)), ctx)
+            rec = {"frames_per_s": B * 1e3 / ms[len(ms) // 2], "ms_per_step": ms[len(ms) // 2], "batch": B}
+            if dev1 is not None:
+                ms1, _ = timed(dev1, 30, ctx)
+                rec["latency_bs1_p50_ms"] = ms1[len(ms1) // 2]
+            rec["boxes"] = boxes.detach().float().view(-1, 4)
+            out["modes"][mode] = rec
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32_0
+    out["msda"] = ref_shims.MSDA_BACKEND["last"]
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
+# The other BASELINE.json configurations as short lines under `configs` of the default run (config 2 is the headline):
+# (key, variant, yaml, sequences per GPU, mode, GFLOP per sequence-frame - SURVEY.md section 8d / BASELINE.md section 2)
+CONFIG_LINES = [
+    ("config3_shared_backbone", "mixformer_vit_rgbt_shared", None, 64, "full", 183.79),
+    ("config3_unibackbone", "mixformer_vit_rgbt_unibackbone", None, 64, "full", 183.79),
+    ("config4_candidate_elimination_bs128", "asymmetric_shared_ce", None, 128, "full", 143.65),
+    ("config5_convmae_large_spm_full", "mixformer_convmae_online", "baseline_large", 32, "full", 681.93),
+    ("config5_convmae_large_spm_cached_1p3", "mixformer_convmae_online", "baseline_large", 32, "cached", 483.85),
+    ("config5_mixvit_large_spm_full", "mixformer_vit_online", "baseline_large", 32, "full", 600.00),
+    ("config5_mixvit_large_spm_cached_1p3", "mixformer_vit_online", "baseline_large", 32, "cached", 433.75),
+]
+
+
+def config_lines(dev, steps, precision, peaks):
+    """5-step lines of BASELINE.json configs 3, 4 and 5 on this GPU (same timing rules as the headline: >= 3 warm-up
+    steps, CUDA events, inputs resident, working sets far beyond L2).  "cached" = the online trackers' real per-frame
+    path: set_online_batch() once (1 template + 3 online templates per sequence), forward_test_batch() per frame."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    out = {}
+    model, last = None, None
+    for key, variant, yaml_name, B, mode, gf in CONFIG_LINES:
+        try:
+            if last != (variant, yaml_name):
+                del model
+                torch.cuda.empty_cache()
+                model, cfg = synthetic.make_model(variant, 0, yaml_name=yaml_name)
+                model = model.to(dev).set_precision(precision)
+                last = (variant, yaml_name)
+            to_dev = lambda a: [x.to(dev) for x in a] if isinstance(a, (list, tuple)) else a.to(dev)
+            t, ot, s_ = [to_dev(a) for a in synthetic.make_inputs(variant, cfg, B, 1)]
+            if mode == "cached":
+                g = torch.Generator().manual_seed(3)
+                ots = torch.randn(B, 3, 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.TEMPLATE.SIZE, generator=g).to(dev)
+                model.set_online_batch(t, ots)
+                fn = lambda: model.forward_test_batch(s_)[1]
+            else:
+                fn = lambda: model(t, ot, s_)[1]
+            for _ in range(3):
+                boxes = fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                boxes = fn()
+            b.record()
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(boxes).all())
+            ms = a.elapsed_time(b) / steps
+            fps = B * 1e3 / ms
+            out[key] = {"variant": variant, "yaml": yaml_name or synthetic.DEFAULT_YAML[variant], "batch": B, "mode": mode,
+                        "value": fps, "unit": UNIT, "ms_per_step": ms, "steps": steps, "gflop_per_frame": gf,
+                        "step_tensor_tflops": gf * fps / 1e3,
+                        "frac_of_measured_peak": gf * fps / 1e3 / peaks["bf16_tflops"],
+                        "frac_of_nominal_2250": gf * fps / 1e3 / 2250.0}
+        except Exception as e:      # a failing side line must not take the headline down; it is reported as such
+            out[key] = {"error": f"{type(e).__name__}: {e}"}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -257,6 +441,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="developer A/B: replay the bs=B forward as one CUDA graph in the "
                                                         "resident-input region")
     ap.add_argument("--no-frame-path", action="store_true", help="skip the BatchedTracker (uint8 frames in) measurement")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-GPU run of the unmodified reference modules")
+    ap.add_argument("--no-variants", action="store_true", help="skip the short lines of BASELINE.json configs 3, 4, 5")
     ap.add_argument("--breakdown", action="store_true",
                     help="developer aid: after the timed regions, run 3 more steps with EVERY op bracketed by CUDA "
                          "events and print the per-class table to stderr")
@@ -275,6 +461,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the forward has no CPU fallback")
 
     import torch.distributed as dist
+    if world > 1:
+        # one slice of the host cores per rank: the launch threads of the ranks do not migrate onto each other
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -305,9 +499,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    # boxes of every step stay on the device in a [K, B, 4] log; ONE all-gather at the end of the timed region brings
+    # the ranks' logs together (the design's only collective: never inside the forward, and not once per step)
+    box_log = torch.empty((max(args.steps, 8), B, 4), device=dev, dtype=torch.float32)
+
+    def step_resident(k=0):
         out, coords = model(*dev_inputs)
-        return runner.gather_boxes(coords.view(-1, 4))
+        box_log[k].copy_(coords.view(-1, 4))
+        return coords
 
     if args.graph:
         model.enable_cuda_graph(True)
@@ -321,11 +520,13 @@ def main():
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            gathered = step_resident()
+        for k in range(args.steps):
+            step_resident(k)
+        gathered_log = runner.gather_boxes(box_log[:args.steps].reshape(-1, 4))      # [world, K*B, 4]
         e1.record()
         barrier()
     launches = ops.LAUNCHES
+    gathered = gathered_log.view(gathered_log.shape[0], args.steps, B, 4)[:, -1]
     if args.graph:
         model.enable_cuda_graph(False)
     # ---- roofline pass: the same K steps again with every tensor-core GEMM launch bracketed by CUDA events on its
@@ -344,8 +545,8 @@ def main():
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         p0.record()
-        for _ in range(args.steps):
-            step_resident()
+        for k in range(args.steps):
+            step_resident(k)
         p1.record()
         barrier()
         ops.PROFILER = None
@@ -408,9 +609,10 @@ def main():
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        for _ in range(args.steps):
+        for k in range(args.steps):
             _, cb = model.forward_search(dev_inputs[2])
-            runner.gather_boxes(cb.view(-1, 4))
+            box_log[k].copy_(cb.view(-1, 4))
+        runner.gather_boxes(box_log[:args.steps].reshape(-1, 4))
         c1.record()
         barrier()
         tc = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
@@ -451,6 +653,20 @@ def main():
                "e2e_host_p50_ms": wall[100], "e2e_host_p99_ms": wall[197],
                "note": "device = CUDA events around model(crops on device); e2e_host = wall clock of FrameStep.step "
                        "(pinned host crops -> H2D -> graph replay -> D2H box -> sync)"}
+
+    eager = None
+    if world == 1 and rank == 0 and not args.no_eager:
+        try:
+            eager = gpu_eager_baseline(variant, args.yaml, model.state_dict(), dev, dev_inputs,
+                                       [to_dev(a) for a in synthetic.make_inputs(variant, cfg, 1, 99)], args.steps)
+            mine = model(*dev_inputs)[1].view(-1, 4).float()
+            for rec in eager.get("modes", {}).values():       # same-run parity: our bf16 boxes vs the reference's on this GPU
+                rec["max_box_diff_px_vs_b200_path"] = float((rec.pop("boxes") - mine).abs().max()) * int(cfg.DATA.SEARCH.SIZE)
+        except Exception as e:
+            eager = {"error": f"{type(e).__name__}: {e}"}
+    configs = None
+    if world == 1 and rank == 0 and not args.no_variants and variant == VARIANT and args.yaml is None:
+        configs = config_lines(dev, 5, args.precision, _peaks())
 
     frame_path = None
     if world == 1 and not args.no_frame_path and variant not in ("mixformer_vit_online", "mixformer_convmae_online"):
@@ -510,13 +726,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-        "config": {"workload": f"{variant} ({args.yaml or synthetic.DEFAULT_YAML[variant]}.yaml) "
-                               f"{'RGB-T two-modality' if isinstance(dev_inputs[2], list) else 'RGB'} full forward "
-                               f"({cfg.DATA.TEMPLATE.SIZE}^2 template + online template, {cfg.DATA.SEARCH.SIZE}^2 search), "
-                               f"bs={B} sequences per GPU, "
-                               "seeded random-init weights, N(0,1) crops",
-                   "batch_per_gpu": B, "sequences": n_seq_total, "parallelism": f"sequence-sharded x{world}",
-                   "l2": "working set per step (weights 2x209 MB + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
+        "config": workload_config(variant, args.yaml, cfg, B, world, isinstance(dev_inputs[2], list)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fs_h2d, "d2h_bytes_per_step": fs_d2h,
                 "note": "FrameStep.step(None, None, search): templates resident on the device (as in the reference tracker "
                         "loop), per step pinned uint8 search crops -> H2D -> device Preprocessor -> FULL forward -> boxes "
@@ -528,14 +738,17 @@ def main():
         "roofline": roof,
         "step_tensor_tflops_per_gpu": step_tflops,
         "step_tensor_frac_of_measured_peak": step_tflops / peaks["bf16_tflops"],
+        "step_tensor_frac_of_nominal_2250": step_tflops / 2250.0,
         "clocks": clocks.summary(),
         "latency_bs1": lat,
         "cached_template": cached,
         "frame_path": frame_path,
+        "gpu_eager_baseline": eager,
+        "configs": configs,
     }
-    if world == 1 and args.cpu_budget > 0 and args.yaml is None:
-        v, cores, sample = cpu_port_frames_per_s(variant, args.cpu_budget)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if world == 1 and args.cpu_budget > 0:
+        v, cores, kind, sample = cpu_baseline_frames_per_s(variant, args.yaml, args.cpu_budget)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -614,9 +614,11 @@ class MixFormer_RGBT_OnlineScore(MixFormer_RGBT):
         self.score_branch = score_branch
 
     @torch.no_grad()
-    def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None, return_features=False):
+    def forward(self, template, online_template, search, run_score_head=False, gt_bboxes=None, return_features=False,
+                ready_events=None):
+        """ready_events: see ForwardEngine.forward (runner.FrameStep passes the per-modality upload events)."""
         res = self.engine().forward(list(template), list(online_template), list(search), run_score_head=run_score_head,
-                                    gt_bboxes=gt_bboxes)
+                                    gt_bboxes=gt_bboxes, ready_events=ready_events)
         coords = res["pred_boxes"]
         out = {"pred_boxes": coords}
         if run_score_head:

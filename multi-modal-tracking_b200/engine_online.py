@@ -343,8 +343,10 @@ class AsymOnlineEngine(OnlineEngine):
             self._tiles[key] = hit
         return hit
 
-    def forward(self, template, online_template, search, want_maps=True, run_score_head=False, gt_bboxes=None):
-        res = ForwardEngine.forward(self, template, online_template, search, want_maps=want_maps)
+    def forward(self, template, online_template, search, want_maps=True, run_score_head=False, gt_bboxes=None,
+                ready_events=None):
+        res = ForwardEngine.forward(self, template, online_template, search, want_maps=want_maps,
+                                    ready_events=ready_events)
         if not run_score_head:
             return res
         B = res["pred_boxes"].shape[0]

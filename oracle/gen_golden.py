@@ -121,7 +121,11 @@ def main_online(sharpen, yaml_name=None, batch=BATCH, variant="mixformer_vit_onl
 
 EXTRA = [("mixformer_vit_rgbt_shared", "baseline_attention_lasher_newfusion_2layer"),   # Attention_Fusion_Bimodal
          ("asymmetric_shared", "attention_lasher_cat_3layer"),                           # RGBT_Fusion_Cat
-         ("mixformer_vit", "baseline_large")]                                            # MixViT-L RGB-only, 384 / 192
+         ("mixformer_vit", "baseline_large"),                                            # MixViT-L RGB-only, 384 / 192
+         # Attention_Fusion_Bimodal_LNSpecific_Sum / _2 (fusion_utils.py:282-353), the fusion classes of three shipped YAMLs
+         ("asymmetric_shared", "attention-lasher-cross_deform_fusion_sum_2layer"),
+         ("asymmetric_shared", "attention_lasher_newfusionAdd_2layer"),
+         ("asymmetric_shared_ce", "attention_lasher_newfusionAdd_2layer")]
 
 
 def main_asym_online():

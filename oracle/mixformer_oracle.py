@@ -207,17 +207,39 @@ def backbone_plain(sd, x_t, x_ot, x_s, heads, depth, per_modality_ln=False):
     return x[:, n_t:], x
 
 
-def candidate_elimination(attn, tokens_v, tokens_i, keep_ratio, gidx_v, gidx_i, n_t):
+def _forced_order(gi, forced):
+    """Local positions (in the current global-index table `gi` [B, Ls]) of the tokens whose GLOBAL indices are listed
+    in `forced` [B, keep], in the listed order, followed by the remaining local positions (ascending)."""
+    B, Ls = forced.shape[0], gi.shape[1]     # gi may carry more rows than sequences (first stage: full-batch table)
+    idx = torch.empty((B, Ls), dtype=torch.int64)
+    for b in range(B):
+        pos = {int(g): i for i, g in enumerate(gi[b].tolist())}
+        top = [pos[int(g)] for g in forced[b].tolist()]      # KeyError: the forced token was removed at an earlier stage
+        assert len(set(top)) == len(top), "forced keep list names a token twice"
+        rest = sorted(set(range(Ls)) - set(top))
+        idx[b] = torch.tensor(top + rest, dtype=torch.int64)
+    return idx
+
+
+def candidate_elimination(attn, tokens_v, tokens_i, keep_ratio, gidx_v, gidx_i, n_t, forced=None):
     """asymmetric_shared_ce.py:49-101 with box_mask_z=None (the test-time call,
-    lib/test/tracker/asymmetric_shared_ce.py:96-98); get_token_from_attn :22-46."""
+    lib/test/tracker/asymmetric_shared_ce.py:96-98); get_token_from_attn :22-46.
+    forced = (keep_v, keep_i) global indices [B, keep]: TEST AID ("forced-keep" mode) - the scores are computed as
+    the reference does, but the kept set is the given one instead of the top-k of the scores, so that an
+    implementation whose low-precision scores flipped near-ties across the keep boundary can be compared stage by
+    stage on the SAME token population (tests/test_forward_gpu.py)."""
     lens_s = attn.shape[-1] // 2
     lens_keep = math.ceil(keep_ratio * lens_s)
     if lens_keep == lens_s:
         return tokens_v, tokens_i, gidx_v, gidx_i, None, None, None
     score = attn.mean(dim=2).mean(dim=1)
     outs = []
-    for sc, tok, gi in ((score[:, :lens_s], tokens_v, gidx_v), (score[:, lens_s:], tokens_i, gidx_i)):
-        _, idx = torch.sort(sc, dim=1, descending=True)
+    for m, (sc, tok, gi) in enumerate(((score[:, :lens_s], tokens_v, gidx_v), (score[:, lens_s:], tokens_i, gidx_i))):
+        if forced is None:
+            _, idx = torch.sort(sc, dim=1, descending=True)
+        else:
+            assert forced[m].shape == (sc.shape[0], lens_keep), (forced[m].shape, lens_keep)
+            idx = _forced_order(gi, forced[m])
         top, non = idx[:, :lens_keep], idx[:, lens_keep:]
         keep_i = gi.gather(1, top)
         rem_i = gi.gather(1, non)
@@ -227,7 +249,7 @@ def candidate_elimination(attn, tokens_v, tokens_i, keep_ratio, gidx_v, gidx_i, 
     return outs[0][0], outs[1][0], outs[0][1], outs[1][1], outs[0][2], outs[1][2], score
 
 
-def backbone_asymmetric(sd, x_t, x_ot, x_s, heads, depth, ce_loc=None, ce_keep=None):
+def backbone_asymmetric(sd, x_t, x_ot, x_s, heads, depth, ce_loc=None, ce_keep=None, forced_keep=None):
     """asymmetric_shared.py:137-154 blocks / asymmetric_shared_ce.py CE_Block_Shared.forward :247-282,
     VisionTransformer.forward :377-425, _recover_search :427-447.  Inputs are batch-stacked [RGB x B, TIR x B].
     Returns (search tokens [2B, n_s, C] in original positions, aux dict with CE scores / kept indices)."""
@@ -253,7 +275,11 @@ def backbone_asymmetric(sd, x_t, x_ot, x_s, heads, depth, ce_loc=None, ce_keep=N
         av, ai, attn_t2s = cross_modal_attention(hv, hi, _sub(p, "attn."), heads, n_t, n_s, exe_ce)
         x_v, x_i = x_v + av, x_i + ai
         if exe_ce:
-            x_v, x_i, gidx_v, gidx_i, rv, ri, score = candidate_elimination(attn_t2s, x_v, x_i, keep, gidx_v, gidx_i, n_t)
+            forced = None if forced_keep is None else forced_keep[len(aux["ce_scores"])]
+            aux.setdefault("ce_gidx_in_v", []).append(gidx_v)       # token population the stage scored (global indices)
+            aux.setdefault("ce_gidx_in_i", []).append(gidx_i)
+            x_v, x_i, gidx_v, gidx_i, rv, ri, score = candidate_elimination(attn_t2s, x_v, x_i, keep, gidx_v, gidx_i, n_t,
+                                                                            forced)
             aux["ce_scores"].append(score)
             aux["ce_keep_v"].append(gidx_v)
             aux["ce_keep_i"].append(gidx_i)
@@ -619,9 +645,11 @@ def _tokens_to_map(tok, g):
 
 
 @torch.no_grad()
-def forward(variant, sd, cfg, template, online_template, search):
+def forward(variant, sd, cfg, template, online_template, search, forced_keep=None):
     """The reference `model(template, online_template, search)` for the non-online variants.
-    RGB-T inputs are 2-lists [v, i].  Returns dict(pred_boxes [B,1,4], score_maps [B,2,S*S], + aux)."""
+    RGB-T inputs are 2-lists [v, i].  Returns dict(pred_boxes [B,1,4], score_maps [B,2,S*S], + aux).
+    forced_keep (asymmetric_shared_ce only, test aid): per CE stage a (keep_v, keep_i) pair of global-index tensors
+    [B, keep] that replaces the stage's top-k selection (see candidate_elimination)."""
     mc = cfg if "variant" in cfg else model_cfg(variant, cfg)
     d = vit_dims(mc["vit_type"])
     g = mc["search_size"] // 16
@@ -649,7 +677,8 @@ def forward(variant, sd, cfg, template, online_template, search):
             elif variant in ("asymmetric_shared", "asymmetric_shared_online"):
                 s, aux = backbone_asymmetric(bsd, t, ot, sr, d["heads"], d["depth"])
             elif variant == "asymmetric_shared_ce":
-                s, aux = backbone_asymmetric(bsd, t, ot, sr, d["heads"], d["depth"], mc["ce_loc"], mc["ce_keep"])
+                s, aux = backbone_asymmetric(bsd, t, ot, sr, d["heads"], d["depth"], mc["ce_loc"], mc["ce_keep"],
+                                             forced_keep)
             else:
                 raise KeyError(variant)
             n = s.shape[0] // 2

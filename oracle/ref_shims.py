@@ -1,18 +1,20 @@
-"""TEST INFRASTRUCTURE - import shims that let the UNMODIFIED reference (/root/reference, read-only,
-only present in the build container) be imported and run on CPU, so that the oracle restatement in
-oracle/mixformer_oracle.py can be pinned against it and golden vectors can be generated
-(oracle/gen_golden.py).  Nothing here is used by the product path, by `-m gpu` tests, by smoke() or
-by bench.py: /root/reference does not exist on the GPU box.
+"""TEST / BASELINE INFRASTRUCTURE - import shims that let the UNMODIFIED reference be imported and run, so that
+  * the oracle restatement in oracle/mixformer_oracle.py can be pinned against it and golden vectors can be
+    generated (oracle/gen_golden.py; build container, /root/reference), and
+  * bench.py can time the reference itself on the GPU box, on the host cores (`--impl reference`) and in eager mode on
+    the B200 (`gpu_eager_baseline`), from the unmodified copy oracle/ship_ref.py puts under baseline/_ref.
+Nothing here is used by the product path, by `-m gpu` parity tests or by smoke().
 
-Shims:
+Shims for packages the image lacks - the reference's own files are imported as they are:
   * timm.models.vision_transformer.VisionTransformer - a stand-in base class exposing the attributes
     the reference subclasses touch (cls_token, pos_embed, pos_drop, norm, head, init_weights);
     timm.models.layers.{Mlp, DropPath, trunc_normal_} (fc1 -> act -> fc2; identity in eval).
   * easydict.EasyDict, empty mmcv.ops classes, empty matplotlib.pyplot.
-  * MultiScaleDeformableAttention.ms_deform_attn_forward -> the reference's own pure-PyTorch
-    ms_deform_attn_core_pytorch (lib/models/mixformer_vit_rgbt/deformable_attention/ops/functions/
-    ms_deform_attn_func.py:41-61).
-  * torch.Tensor.cuda -> identity (the corner head calls .cuda() in __init__, head.py:142-145).
+  * MultiScaleDeformableAttention.ms_deform_attn_forward (the reference's pybind extension, which does not build
+    against torch 2.11): CUDA tensors -> the reference's OWN kernel compiled by oracle/build_ref.py
+    (oracle/_ref/libmsda_ref.so); CPU tensors (or library absent) -> the reference's own pure-PyTorch
+    ms_deform_attn_core_pytorch (deformable_attention/ops/functions/ms_deform_attn_func.py:41-61).
+  * torch.Tensor.cuda -> identity for CPU runs (the corner head calls .cuda() in __init__, head.py:142-145).
 """
 from __future__ import annotations
 
@@ -23,11 +25,28 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("MMT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """/root/reference in the build container; on the GPU box the unmodified copy that oracle/ship_ref.py put under
+    baseline/_ref (git-ignored, travels with the gpurun snapshot)."""
+    env = os.environ.get("MMT_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_REPO, "baseline", "_ref")]:
+        if os.path.isdir(os.path.join(cand, "lib", "models")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "models"))
+
+
+def reference_kind() -> str:
+    return "shipped copy (baseline/_ref)" if REFERENCE_ROOT.startswith(_REPO) else REFERENCE_ROOT
 
 
 class _EasyDict(dict):
@@ -104,8 +123,32 @@ class _TimmViT(nn.Module):
 _installed = False
 
 
-def install() -> None:
-    """Install the shims into sys.modules and put the reference root on sys.path."""
+_MSDA_LIB = None
+
+
+def _msda_ref_lib():
+    """The reference's OWN deformable-attention forward kernel, compiled by oracle/build_ref.py (None if not built)."""
+    global _MSDA_LIB
+    if _MSDA_LIB is None:
+        import ctypes
+        path = os.path.join(_REPO, "oracle", "_ref", "libmsda_ref.so")
+        _MSDA_LIB = False
+        if os.path.exists(path):
+            try:
+                _MSDA_LIB = ctypes.CDLL(path)
+                _MSDA_LIB.msda_ref_forward.restype = ctypes.c_int
+            except OSError:
+                _MSDA_LIB = False
+    return _MSDA_LIB or None
+
+
+MSDA_BACKEND = {"last": None}      # which implementation served the last MSDA call (reported by bench.py)
+
+
+def install(cpu_model: bool | None = None) -> None:
+    """Install the shims into sys.modules and put the reference root on sys.path.
+    cpu_model: the reference model will run on the CPU (neutralise the `.cuda()` calls of the head's constructor,
+    head.py:142-145); default = True exactly when no GPU is visible.  Pass True for a CPU run on a GPU box."""
     global _installed
     if _installed:
         return
@@ -131,13 +174,38 @@ def install() -> None:
     mpl.pyplot = mod("matplotlib.pyplot")
 
     def _msda_forward(value, shapes, level_start, loc, weights, im2col_step):
+        lib = _msda_ref_lib() if value.is_cuda else None
+        if lib is not None:
+            # CUDA tensors: the reference's own kernel (ms_deform_im2col_cuda.cuh) behind oracle/msda_ref_wrapper.cu,
+            # called the way ms_deform_attn_cuda.cu:20-80 calls it.  The kernel is fp32 (the reference dispatches
+            # float/double only): under autocast the operands are cast up, what custom_fwd(cast_inputs=float32) does.
+            import ctypes
+            odt = value.dtype
+            v, l, w = value.float().contiguous(), loc.float().contiguous(), weights.float().contiguous()
+            ss, ls = shapes.to(torch.int64).contiguous(), level_start.to(torch.int64).contiguous()
+            N, S, M, D = v.shape
+            Lq, L, P = l.shape[1], l.shape[3], l.shape[4]
+            out = torch.zeros((N, Lq, M * D), device=v.device, dtype=torch.float32)
+            step = min(int(im2col_step), N)
+            while N % step:
+                step -= 1
+            p = lambda t: ctypes.c_void_p(t.data_ptr())
+            st = lib.msda_ref_forward(p(v), p(ss), p(ls), p(l), p(w), p(out), N, S, M, D, L, Lq, P, step,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if st != 0:
+                raise RuntimeError(f"msda_ref_forward failed: {st}")
+            MSDA_BACKEND["last"] = "reference CUDA kernel (oracle/_ref/libmsda_ref.so)"
+            return out.to(odt)
         from lib.models.mixformer_vit_rgbt.deformable_attention.ops.functions.ms_deform_attn_func import \
             ms_deform_attn_core_pytorch
+        MSDA_BACKEND["last"] = "reference pure-PyTorch core (ms_deform_attn_core_pytorch)"
         return ms_deform_attn_core_pytorch(value, [(int(h), int(w)) for h, w in shapes.tolist()], loc, weights)
 
     mod("MultiScaleDeformableAttention", ms_deform_attn_forward=_msda_forward, ms_deform_attn_backward=None)
 
-    if not torch.cuda.is_available():
+    if cpu_model is None:
+        cpu_model = not torch.cuda.is_available()
+    if cpu_model:
         torch.Tensor.cuda = lambda self, *a, **k: self   # head.py:142-145 / tracker_utils.py:26-27
         torch.cuda.current_device = lambda: 0
 
@@ -174,10 +242,11 @@ VARIANTS = {
 }
 
 
-def build_reference_model(variant: str, yaml_name: str):
-    """Construct the reference nn.Module for `variant` from its shipped YAML, in eval mode, on CPU."""
+def build_reference_model(variant: str, yaml_name: str, cpu_model: bool | None = None):
+    """Construct the reference nn.Module for `variant` from its shipped YAML, in eval mode, on CPU (call .cuda() on the
+    result for the eager-GPU baseline; pass cpu_model=True when it will RUN on the CPU of a GPU box)."""
     import importlib
-    install()
+    install(cpu_model)
     cfg_mod, model_mod, fn, exp_dir = VARIANTS[variant]
     cm = importlib.import_module(cfg_mod)
     cm.update_config_from_file(os.path.join(REFERENCE_ROOT, "experiments", exp_dir, yaml_name + ".yaml"))

@@ -309,14 +309,15 @@ def test_preprocess_u8_matches_oracle(built_lib):
         assert np.array_equal(got[i], want), i
 
 
-@pytest.mark.parametrize("variant", ["mixformer_vit_rgbt_shared", "mixformer_vit"])
+@pytest.mark.parametrize("variant", ["mixformer_vit_rgbt_shared", "mixformer_vit", "asymmetric_shared_online",
+                                     "mixformer_vit_rgbt", "asymmetric_shared_ce", "mixformer_vit_online"])
 def test_framestep_uint8_crops_and_resident_templates(built_lib, variant):
     """FrameStep with uint8 HWC crops (uploaded as bytes, normalised on the device) gives the boxes of the model called
     on oracle-normalised fp32 crops; resident templates + step(None, None, search) gives the same boxes again."""
     from mmt_b200 import synthetic, runner
     model, cfg = synthetic.make_model(variant, 0, sharpen=True)
     model = model.cuda()
-    rgbt = variant != "mixformer_vit"
+    rgbt = variant not in ("mixformer_vit", "mixformer_vit_online")
     B, ts, ss = 3, cfg.DATA.TEMPLATE.SIZE, cfg.DATA.SEARCH.SIZE
     rng = np.random.default_rng(23)
     u8 = lambda size: rng.integers(0, 256, (B, size, size, 3), dtype=np.uint8)

@@ -105,3 +105,45 @@ def test_msda_core_matches_grid_sample_kat():
     aw = attn.transpose(1, 2).reshape(N * M, 1, Lq, L * P)
     ref = (torch.stack(vals, dim=-2).flatten(-2) * aw).sum(-1).view(N, M * D, Lq).transpose(1, 2)
     assert torch.allclose(out, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_forced_keep_mode_reproduces_the_free_run():
+    """The oracle's forced-keep test aid (candidate_elimination(..., forced=...)): forcing the kept sets the free run
+    chose itself must reproduce it exactly; forcing a different (swapped) token must change the population the next
+    stage scores."""
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    variant = "asymmetric_shared_ce"
+    model, cfg = synthetic.make_model(variant, 0, sharpen=False)
+    sd = model.state_dict()
+    inputs = synthetic.make_inputs(variant, cfg, 1, 4)
+    free = O.forward(variant, sd, cfg, *inputs)
+    forced = [(kv.clone(), ki.clone()) for kv, ki in zip(free["ce_keep_v"], free["ce_keep_i"])]
+    again = O.forward(variant, sd, cfg, *inputs, forced_keep=forced)
+    assert torch.equal(free["pred_boxes"], again["pred_boxes"]) and torch.equal(free["score_maps"], again["score_maps"])
+    for a, b in zip(free["ce_scores"], again["ce_scores"]):
+        assert torch.equal(a, b)
+    # swap a stage-0 RGB token that the free run prunes at stage 1 for one it removed at stage 0: stage 1 then scores a
+    # different population (and the later forced lists stay valid)
+    keep0, keep1 = forced[0][0][0].tolist(), set(free["ce_keep_v"][1][0].tolist())
+    pos = next(i for i, t in enumerate(keep0) if t not in keep1)
+    other = next(float(t) for t in range(324) if float(t) not in set(keep0))
+    forced[0][0][0, pos] = other
+    diff = O.forward(variant, sd, cfg, *inputs, forced_keep=forced)
+    assert other in set(diff["ce_gidx_in_v"][1][0].tolist())
+    assert not torch.equal(diff["ce_scores"][1], free["ce_scores"][1])
+
+
+@pytest.mark.parametrize("yaml_name", ["attention-lasher-cross_deform_fusion_sum_2layer", "attention_lasher_newfusionAdd_2layer"])
+def test_oracle_matches_reference_vectors_sum_fusion_classes(yaml_name):
+    """Attention_Fusion_Bimodal_LNSpecific_Sum / _2 (fusion_utils.py:282-353): oracle against the reference's outputs."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    variant = "asymmetric_shared"
+    model, cfg = synthetic.make_model(variant, 0, yaml_name=yaml_name)
+    inputs = synthetic.make_inputs(variant, cfg, 2, 1)
+    out = O.forward(variant, model.state_dict(), cfg, *inputs)
+    g = np.load(os.path.join(GOLDEN, f"{variant}__{yaml_name}_b2.npz"))
+    assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
+    assert np.abs(out["score_maps"].numpy() - g["score_maps"]).max() <= 2e-4
