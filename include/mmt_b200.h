@@ -48,6 +48,30 @@ int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
                   const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out, int ldo,
                   int out_fp32, int max_ctas, void* stream);
 
+/*
+ * mmt_gemm_bf16 with the transformer block's LayerNorm folded into the two GEMMs around it, so that the normalised
+ * rows never exist in HBM (Block.forward lib/models/mixformer_vit/mixformer.py:126-129: x + attn(norm1(x)),
+ * x + mlp(norm2(x)); modality-specific norms mixformer_shared.py:143-159 = one call per modality's row range).
+ * With LN(x) = (x - mu) * rs * gamma + beta, Linear(LN(x)) = rs * (x W'^T - mu * colsum) + bias' where
+ * W' = W * diag(gamma), colsum[n] = sum_k W'[n,k], bias' = bias + W beta are prepared once on the host:
+ *   consumer side (ln_stats != NULL; bf16 output): A holds the RAW residual rows in bf16, W / bias are W' / bias';
+ *     ln_stats [M, ln_slots, 2] fp32 = per-row partial (sum, sum of squares) over the K columns, summed here in slot
+ *     order (deterministic); the epilogue computes out = rs * (acc - mu * colsum[n]) + bias[n], then `act`.
+ *   producer side (xb_out, stats_out != NULL; fp32 output, N % 128 == 0, ldo == N): besides out (= act(AW^T + bias) +
+ *     resid) the call leaves xb_out [M, ld_xb] = bf16(out) and stats_out [M, N/128, 2] = partial (sum, sum of squares)
+ *     of the out rows, i.e. what the next consumer needs.  Fused into the epilogue of the CTA-pair kernel; for launch
+ *     shapes that take another kernel the same outputs are produced by mmt_rowstats_cast after the GEMM.
+ * Everything else as mmt_gemm_bf16 (which is this function with the four extra pointers NULL).
+ */
+int mmt_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
+                     const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out, int ldo,
+                     int out_fp32, int max_ctas, const float* ln_stats, int ln_slots, float ln_eps,
+                     const float* colsum, void* xb_out, int ld_xb, float* stats_out, void* stream);
+
+/* Stand-alone producer of the folded LayerNorm: xb [rows, ld_xb] = bf16(x), stats [rows, slots, 2] = (sum, sum of
+ * squares) of the fp32 row in slot 0, zeros in the other slots. */
+int mmt_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, void* stream);
+
 /* Same contract, fp32 operands and fp32 FMA accumulation (parity mode; SIMT kernel). */
 int mmt_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias, int act,
                  const float* resid, int ldr, const float* rowadd, int rowadd_period, float* out, int ldo,

@@ -10,7 +10,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmmt_b200.so")
+# MMT_B200_DEV_LIB=1 (tools/ only): the developer build with the GEMM experiment switches (build.py --dev)
+LIB_PATH = os.path.join(_HERE, "csrc", "libmmt_b200_dev.so" if os.environ.get("MMT_B200_DEV_LIB") == "1" else "libmmt_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mmt_b200.h")
 
 

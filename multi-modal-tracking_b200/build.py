@@ -67,17 +67,33 @@ def is_fresh() -> bool:
         return f.read().strip() == source_digest()
 
 
-def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) -> str:
-    """Compile every csrc/*.cu for sm_100a and link csrc/libmmt_b200.so. Returns the library path."""
+def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False, dev: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a and link csrc/libmmt_b200.so. Returns the library path.
+    dev=True builds the DEVELOPER library csrc/libmmt_b200_dev.so instead: the same sources with -DMMT_GEMM_DEV (epilogue
+    isolation switches, cycle counters, A/B environment switches) plus csrc/dev/*.cu; selected at import time by
+    MMT_B200_DEV_LIB=1 (tools/ only - the product, the tests and bench.py use the shipped library)."""
+    if dev:
+        return _build_dev(verbose, force, ptxas_info)
     if not force and is_fresh():
         return LIB
-    os.makedirs(OBJ, exist_ok=True)
+    return _compile_and_link(_sources(), list(NVCC_FLAGS), OBJ, LIB, verbose, force, ptxas_info, stamp=True)
+
+
+def _build_dev(verbose, force, ptxas_info):
+    dev_dir = os.path.join(CSRC, "dev")
+    srcs = _sources() + sorted(os.path.join(dev_dir, f) for f in os.listdir(dev_dir) if f.endswith(".cu"))
+    return _compile_and_link(srcs, list(NVCC_FLAGS) + ["-DMMT_GEMM_DEV"], os.path.join(CSRC, "_obj", "dev"),
+                             os.path.join(CSRC, "libmmt_b200_dev.so"), verbose, force, ptxas_info, stamp=False)
+
+
+def _compile_and_link(sources, base_flags, obj_dir, lib_path, verbose, force, ptxas_info, stamp):
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
-    hdr_digest = _digest(_headers(), " ".join(NVCC_FLAGS))
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_info else [])
+    hdr_digest = _digest(_headers(), " ".join(base_flags))
+    flags = list(base_flags) + (["-Xptxas", "-v"] if ptxas_info else [])
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         tag = obj + ".digest"
         want = _digest([src], hdr_digest)
         if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read() == want:
@@ -93,16 +109,17 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
         return obj
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        objs = list(ex.map(compile_one, sources))
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-        raise RuntimeError("link of libmmt_b200.so failed")
-    with open(os.path.join(OBJ, "stamp.txt"), "w") as f:
-        f.write(source_digest())
-    return LIB
+        raise RuntimeError(f"link of {os.path.basename(lib_path)} failed")
+    if stamp:
+        with open(os.path.join(OBJ, "stamp.txt"), "w") as f:
+            f.write(source_digest())
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, ptxas_info="--ptxas" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, ptxas_info="--ptxas" in sys.argv, dev="--dev" in sys.argv))

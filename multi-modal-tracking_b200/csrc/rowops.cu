@@ -140,6 +140,52 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row statistics + bf16 cast: the stand-alone producer of the folded LayerNorm (mmt_gemm_bf16_ex).  For rows whose
+// producer is not a fused GEMM epilogue (the token embedding, the rows candidate elimination re-gathered, launch shapes
+// without the CTA-pair epilogue) this kernel leaves what that epilogue leaves: a bf16 copy of the fp32 row and its
+// (sum, sum of squares) in statistics slot 0, zeros in the other slots.  One warp per row, one pass over HBM.
+template <int MAXV>  // C <= MAXV * 128
+__global__ void rowstats_cast_kernel(const float* __restrict__ x, int rows, int C, bf16* __restrict__ xb, int ld_xb,
+                                     float* __restrict__ stats, int slots) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
+  const int nv = C >> 2;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float4 v = xr[idx];
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+      uint2 p;
+      p.x = pack_bf16x2(v.x, v.y);
+      p.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(xb + static_cast<size_t>(warp) * ld_xb)[idx] = p;
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  float2* so = reinterpret_cast<float2*>(stats) + static_cast<size_t>(warp) * slots;
+  if (lane < slots) so[lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
+int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, cudaStream_t s) {
+  if (!(x && xb && stats && rows > 0 && C > 0 && C % 4 == 0 && C <= 2048 && slots > 0 && slots <= 32 && ld_xb >= C &&
+        ld_xb % 4 == 0))
+    return MMT_ERR_BAD_ARG;
+  const int wpb = 8;
+  const int grid = cdiv(rows, wpb);
+  bf16* o = reinterpret_cast<bf16*>(xb);
+  if (C <= 512) rowstats_cast_kernel<4><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
+  else if (C <= 1024) rowstats_cast_kernel<8><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
+  else rowstats_cast_kernel<16><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
+  MMT_RETURN_LAST_ERROR();
+}
+
+// ------------------------------------------------------------------------------------------------
 // GroupNorm(G, C) on NHWC rows [B, HW, C] (nn.GroupNorm after the fusion 1x1 convs,
 // lib/models/mixformer_vit_rgbt/fusion_utils.py:252-268).  One CTA per (sample, 8 groups).
 // Output row of (b, r) is b*out_seq_rows + out_row_off + r, so a modality's map can be written straight into
@@ -525,6 +571,11 @@ extern "C" int mmt_layernorm(const float* x, int rows, int C, float eps, const f
   else if (C <= 1024) layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
   else layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
   MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots,
+                                void* stream) {
+  return mmt::launch_rowstats_cast(x, rows, C, xb, ld_xb, stats, slots, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float eps, const float* gamma,
