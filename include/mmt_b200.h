@@ -55,22 +55,25 @@ int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
  * With LN(x) = (x - mu) * rs * gamma + beta, Linear(LN(x)) = rs * (x W'^T - mu * colsum) + bias' where
  * W' = W * diag(gamma), colsum[n] = sum_k W'[n,k], bias' = bias + W beta are prepared once on the host:
  *   consumer side (ln_stats != NULL; bf16 output): A holds the RAW residual rows in bf16, W / bias are W' / bias';
- *     ln_stats [M, ln_slots, 2] fp32 = per-row partial (sum, sum of squares) over the K columns, summed here in slot
- *     order (deterministic); the epilogue computes out = rs * (acc - mu * colsum[n]) + bias[n], then `act`.
+ *     ln_stats [ln_slots][ln_stride][2] fp32 (slot-major; ln_stride >= M rows between slots, row 0 = first row of A) =
+ *     per-row partial (sum, sum of squares) over the K columns, summed here in slot order (deterministic); the epilogue
+ *     computes out = rs * (acc - mu * colsum[n]) + bias[n], then `act`.
  *   producer side (xb_out, stats_out != NULL; fp32 output, N % 128 == 0, ldo == N): besides out (= act(AW^T + bias) +
- *     resid) the call leaves xb_out [M, ld_xb] = bf16(out) and stats_out [M, N/128, 2] = partial (sum, sum of squares)
- *     of the out rows, i.e. what the next consumer needs.  Fused into the epilogue of the CTA-pair kernel; for launch
+ *     resid) the call leaves xb_out [M, ld_xb] = bf16(out) and stats_out [N/128][stats_stride][2] = partial (sum, sum of
+ *     squares) of the out rows (one slot per 128 columns, same slot-major layout), i.e. what the next consumer needs.  Fused into the epilogue of the CTA-pair kernel; for launch
  *     shapes that take another kernel the same outputs are produced by mmt_rowstats_cast after the GEMM.
  * Everything else as mmt_gemm_bf16 (which is this function with the four extra pointers NULL).
  */
 int mmt_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
                      const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out, int ldo,
-                     int out_fp32, int max_ctas, const float* ln_stats, int ln_slots, float ln_eps,
-                     const float* colsum, void* xb_out, int ld_xb, float* stats_out, void* stream);
+                     int out_fp32, int max_ctas, const float* ln_stats, int ln_slots, int ln_stride, float ln_eps,
+                     const float* colsum, void* xb_out, int ld_xb, float* stats_out, int stats_stride, void* stream);
 
-/* Stand-alone producer of the folded LayerNorm: xb [rows, ld_xb] = bf16(x), stats [rows, slots, 2] = (sum, sum of
- * squares) of the fp32 row in slot 0, zeros in the other slots. */
-int mmt_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, void* stream);
+/* Stand-alone producer of the folded LayerNorm: xb [rows, ld_xb] = bf16(x), stats [slots = C/128][slot_stride][2] = the
+ * partial (sum, sum of squares) of the fp32 row per 128-column slot, accumulated in the same order as the fused GEMM
+ * epilogue accumulates them (bit-identical statistics whichever producer ran). */
+int mmt_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, int slot_stride,
+                      void* stream);
 
 /* Same contract, fp32 operands and fp32 FMA accumulation (parity mode; SIMT kernel). */
 int mmt_gemm_f32(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const float* bias, int act,
@@ -174,7 +177,8 @@ int mmt_upsample_add(const void* src1, int ld1, int s1, const void* src2, int ld
 
 /*
  * Corner decode for both corners: score = conv5_1x1(x4) + up4(a3) + up2(a4), softmax over S*S, soft-argmax,
- * xyxy / img_sz and box_xyxy_to_cxcywh.  score_maps (fp32 [B,2,S*S], raw logits) may be NULL.
+ * xyxy / img_sz and box_xyxy_to_cxcywh.  score_maps (fp32 [B,2,S*S], raw logits) may be NULL.  a3_* / a4_* NULL: the
+ * plain Corner_Predictor (score = conv5_1x1(x4) only, head.py:23-94).
  * Reference: head.py:181,198-212 (coords :138-145), lib/utils/box_ops.py:27-31, forward_box_head mixformer.py:325-338.
  */
 int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x, int C4, const float* w5_tl, const float* w5_br,
@@ -204,6 +208,17 @@ int mmt_mixattn_fwd(const void* qkv0, int rows0, const void* qkv1, int rows1, in
  */
 int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
                   float* partial_ws, float* scores, int is_bf16, void* stream);
+
+/*
+ * The same scores with the template rows (queries) and the search rows (keys) in two buffers of the same row stride:
+ * qbuf [2B, q_seq_rows, 3C] holds every sequence-modality's template rows first in its block, qkv [2B, n_tok, 3C] the
+ * search rows from row k_row_off of its block.  mmt_ce_scores is the call with one buffer (q_seq_rows = n_tok,
+ * k_row_off = Lt); the cached-template path (template q/k/v computed once per template update, search tokens only per
+ * frame) passes the template cache and the search-only buffer (k_row_off = 0).  Same kernels, same summation order.
+ */
+int mmt_ce_scores_split(const void* qbuf, int q_seq_rows, const void* qkv, int n_tok, int k_row_off, int ld, int C,
+                        int heads, int B, int Lt, int Ls, float scale, float* partial_ws, float* scores, int is_bf16,
+                        void* stream);
 
 /*
  * Per (sequence, modality) descending sort of the Ls scores; order int32 [2B, Ls] (sorted local indices),

@@ -138,8 +138,12 @@ attn_f32_kernel(const float* __restrict__ qkv0, const float* __restrict__ qkv1, 
 // 2*Lt rows first, then over heads, like the reference), so the result is run-to-run deterministic.
 template <typename T>
 __global__ void __launch_bounds__(256)
-ce_score_partial_kernel(const T* __restrict__ qkv, int ld, int C, int B, int n_tok, int Lt, int Ls,
-                        float scale, int kt_pad, float* __restrict__ partial) {
+ce_score_partial_kernel(const T* __restrict__ qbuf, int q_seq_rows, const T* __restrict__ qkv, int n_tok, int k_row_off,
+                        int ld, int C, int B, int Lt, int Ls, float scale, int kt_pad, float* __restrict__ partial) {
+  // qbuf / q_seq_rows: buffer and rows per sequence-modality of the TEMPLATE rows (queries, row 0 of each sequence block);
+  // qkv / n_tok / k_row_off: buffer, rows per sequence-modality and first search row of the SEARCH rows (keys).  The full
+  // forward passes the same packed buffer twice (q_seq_rows = n_tok, k_row_off = Lt); the cached-template path reads the
+  // queries from the template cache and the keys from the search-only buffer (k_row_off = 0).
   extern __shared__ float sm[];
   float* sQ = sm;                 // [32][64]
   float* sKV = sQ + 32 * HD;      // [64][65]
@@ -150,14 +154,14 @@ ce_score_partial_kernel(const T* __restrict__ qkv, int ld, int C, int B, int n_t
   // query rows: tile qt covers template rows [qt*32, qt*32+32) of the stacked [V templates; I templates]
   const int qg = qt * 32;
   const int qmod = qg >= Lt;                       // 0: RGB templates, 1: TIR templates
-  const size_t qrow0 = (static_cast<size_t>(qmod) * B + b) * n_tok + (qg - qmod * Lt);
+  const size_t qrow0 = (static_cast<size_t>(qmod) * B + b) * q_seq_rows + (qg - qmod * Lt);
   for (int i = tid; i < 32 * HD; i += 256) {
     const int r = i / HD, d = i % HD;
-    sQ[i] = to_f<T>(qkv[(qrow0 + r) * ld + h * HD + d]);
+    sQ[i] = to_f<T>(qbuf[(qrow0 + r) * ld + h * HD + d]);
   }
   const int ktot = 2 * Ls;
   for (int mod = 0; mod < 2; ++mod) {
-    const size_t krow0 = (static_cast<size_t>(mod) * B + b) * n_tok + Lt;
+    const size_t krow0 = (static_cast<size_t>(mod) * B + b) * n_tok + k_row_off;
     for (int k0 = 0; k0 < Ls; k0 += 64) {
       const int len = min(64, Ls - k0);
       __syncthreads();
@@ -255,14 +259,15 @@ extern "C" int mmt_mixattn_fwd(const void* qkv0, int rows0, const void* qkv1, in
 }
 
 namespace mmt {
-int launch_ce_scores_tc(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
-                        float* partial, int* nqt_out, cudaStream_t stream);
+int launch_ce_scores_tc(const void* qbuf, int q_seq_rows, const void* qkv, int n_tok, int k_row_off, int ld, int C, int heads,
+                        int B, int Lt, int Ls, float scale, float* partial, int* nqt_out, cudaStream_t stream);
 }
 
-extern "C" int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
-                             float* partial_ws, float* scores, int is_bf16, void* stream) {
-  MMT_CHECK_ARG(qkv && partial_ws && scores && B > 0 && heads > 0 && C == heads * HD && ld >= 3 * C);
-  MMT_CHECK_ARG(Lt > 0 && Lt % 32 == 0 && Ls > 0 && n_tok == Lt + Ls);
+extern "C" int mmt_ce_scores_split(const void* qbuf, int q_seq_rows, const void* qkv, int n_tok, int k_row_off, int ld, int C,
+                                   int heads, int B, int Lt, int Ls, float scale, float* partial_ws, float* scores,
+                                   int is_bf16, void* stream) {
+  MMT_CHECK_ARG(qbuf && qkv && partial_ws && scores && B > 0 && heads > 0 && C == heads * HD && ld >= 3 * C);
+  MMT_CHECK_ARG(Lt > 0 && Lt % 32 == 0 && Ls > 0 && q_seq_rows >= Lt && k_row_off >= 0 && n_tok >= k_row_off + Ls);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int ktot = 2 * Ls, kt_pad = ktot + 1, nqt = (2 * Lt) / 32;
   const size_t smem = (32 * HD + 64 * 65 + static_cast<size_t>(32) * kt_pad) * sizeof(float);
@@ -271,19 +276,28 @@ extern "C" int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, i
   cudaError_t e;
   if (is_bf16) {
     // bf16 mode: tensor-core kernel (ce_scores_tc.cu); fewer, larger query tiles -> its own nqt
-    MMT_CHECK_ARG(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0);
+    MMT_CHECK_ARG(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(qbuf) & 15) == 0);
     int nqt_tc = 0;
-    const int rc = launch_ce_scores_tc(qkv, ld, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, &nqt_tc, s);
+    const int rc = launch_ce_scores_tc(qbuf, q_seq_rows, qkv, n_tok, k_row_off, ld, C, heads, B, Lt, Ls, scale, partial_ws,
+                                       &nqt_tc, s);
     if (rc) return rc;
     ce_score_reduce_kernel<<<cdiv(B * ktot, 256), 256, 0, s>>>(partial_ws, B, heads, nqt_tc, ktot, 2 * Lt, scores);
     MMT_RETURN_LAST_ERROR();
   } else {
     e = cudaFuncSetAttribute(ce_score_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    ce_score_partial_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(qkv), ld, C, B, n_tok, Lt, Ls, scale, kt_pad, partial_ws);
+    ce_score_partial_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(qbuf), q_seq_rows,
+                                                           reinterpret_cast<const float*>(qkv), n_tok, k_row_off, ld, C, B, Lt,
+                                                           Ls, scale, kt_pad, partial_ws);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   ce_score_reduce_kernel<<<cdiv(B * ktot, 256), 256, 0, s>>>(partial_ws, B, heads, nqt, ktot, 2 * Lt, scores);
   MMT_RETURN_LAST_ERROR();
+}
+
+extern "C" int mmt_ce_scores(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
+                             float* partial_ws, float* scores, int is_bf16, void* stream) {
+  MMT_CHECK_ARG(n_tok == Lt + Ls);
+  return mmt_ce_scores_split(qkv, n_tok, qkv, n_tok, Lt, ld, C, heads, B, Lt, Ls, scale, partial_ws, scores, is_bf16, stream);
 }

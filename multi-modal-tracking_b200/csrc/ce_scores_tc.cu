@@ -44,8 +44,10 @@ __device__ __forceinline__ float cet_ex2(float x) {
 }
 
 __global__ void __launch_bounds__(CET_THREADS, 2)
-ce_scores_tc_kernel(const __grid_constant__ CUtensorMap tm, int C, int B, int n_tok, int Lt, int Ls, int nqt_per_mod,
-                    float scale_log2e, float* __restrict__ partial) {
+ce_scores_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tm, int C, int B,
+                    int q_seq_rows, int n_tok, int k_row_off, int Lt, int Ls, int nqt_per_mod, float scale_log2e,
+                    float* __restrict__ partial) {
+  // tmq / q_seq_rows: template rows (queries); tm / n_tok / k_row_off: search rows (keys) - see mmt_ce_scores_split
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = smem_base;
@@ -70,7 +72,7 @@ ce_scores_tc_kernel(const __grid_constant__ CUtensorMap tm, int C, int B, int n_
   const int qmod = qt / nqt_per_mod, qchunk = qt % nqt_per_mod;
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_row0 = (qmod * B + b) * n_tok + qchunk * 128;
+  const int q_row0 = (qmod * B + b) * q_seq_rows + qchunk * 128;
   const int q_rows = min(128, Lt - qchunk * 128);
   // keys: two segments (search rows of the RGB and of the TIR stream of sequence b), 64-row boxes
   const int nbs = (Ls + CET_KB - 1) / CET_KB;     // boxes per segment
@@ -80,13 +82,14 @@ ce_scores_tc_kernel(const __grid_constant__ CUtensorMap tm, int C, int B, int n_
     const bool ghost = blk >= nb;
     if (ghost) blk = nb - 1;
     const int s = blk >= nbs ? 1 : 0, k = blk - s * nbs;
-    row0 = (s * B + b) * n_tok + Lt + k * CET_KB;
+    row0 = (s * B + b) * n_tok + k_row_off + k * CET_KB;
     len = ghost ? 0 : min(CET_KB, Ls - k * CET_KB);
     col0 = s * Ls + k * CET_KB;
   };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm);
+    prefetch_tmap(&tmq);
     for (int s = 0; s < CET_STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     mbar_init(q_full, 1);
     mbar_init(s_full, 1);
@@ -116,8 +119,8 @@ ce_scores_tc_kernel(const __grid_constant__ CUtensorMap tm, int C, int B, int n_
     // ------------------------------------------------------------------ TMA producer: Q, then every K pair twice
     if (lane == 0) {
       mbar_expect_tx(q_full, CET_Q_BYTES);
-      tma_load_2d(q_smem, &tm, q_full, h * CET_HD, q_row0);
-      tma_load_2d(q_smem + CET_Q_BYTES / 2, &tm, q_full, h * CET_HD, q_row0 + 64);
+      tma_load_2d(q_smem, &tmq, q_full, h * CET_HD, q_row0);
+      tma_load_2d(q_smem + CET_Q_BYTES / 2, &tmq, q_full, h * CET_HD, q_row0 + 64);
       int stage = 0;
       uint32_t phase = 0;
       for (int pass = 0; pass < 2; ++pass)
@@ -299,19 +302,21 @@ static PFN_cuTensorMapEncodeTiled_v12000 cet_encode_fn() {
 }
 
 // partial: fp32 [B, heads, nqt, 2*Ls] with nqt = 2 * ceil(Lt / 128); returns nqt through *nqt_out
-int launch_ce_scores_tc(const void* qkv, int ld, int C, int heads, int B, int n_tok, int Lt, int Ls, float scale,
-                        float* partial, int* nqt_out, cudaStream_t stream) {
+int launch_ce_scores_tc(const void* qbuf, int q_seq_rows, const void* qkv, int n_tok, int k_row_off, int ld, int C, int heads,
+                        int B, int Lt, int Ls, float scale, float* partial, int* nqt_out, cudaStream_t stream) {
   auto fn = cet_encode_fn();
   if (!fn) return MMT_ERR_UNSUPPORTED;
-  CUtensorMap tm;
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(3 * C), static_cast<cuuint64_t>(2) * B * n_tok};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64, 64};
-  cuuint32_t estr[2] = {1, 1};
-  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), gdim, gstr, box, estr,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return MMT_ERR_BAD_ARG;
+  CUtensorMap tm, tmq;
+  auto encode = [&](CUtensorMap* m, const void* ptr, int rows) {
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(3 * C), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!encode(&tm, qkv, 2 * B * n_tok) || !encode(&tmq, qbuf, 2 * B * q_seq_rows)) return MMT_ERR_BAD_ARG;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ce_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CET_SMEM);
@@ -321,7 +326,7 @@ int launch_ce_scores_tc(const void* qkv, int ld, int C, int heads, int B, int n_
   const int nqt_per_mod = (Lt + 127) / 128;
   *nqt_out = 2 * nqt_per_mod;
   dim3 grid(B * 2 * nqt_per_mod, heads);
-  ce_scores_tc_kernel<<<grid, CET_THREADS, CET_SMEM, stream>>>(tm, C, B, n_tok, Lt, Ls, nqt_per_mod,
+  ce_scores_tc_kernel<<<grid, CET_THREADS, CET_SMEM, stream>>>(tmq, tm, C, B, q_seq_rows, n_tok, k_row_off, Lt, Ls, nqt_per_mod,
                                                               scale * 1.4426950408889634f, partial);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MMT_OK : (int)e;

@@ -68,14 +68,17 @@ struct GemmEpi {
   // ---- LayerNorm folded into the GEMMs around it (mmt_gemm_bf16_ex):
   // consumer side (bf16 output): A holds RAW residual rows, W / bias carry gamma / beta, and the epilogue finishes the
   // normalisation per row: out = rs * (acc - mu * colsum[n]) + bias[n], mu / rs from the row's partial sums
-  const float* ln_stats;  // [M, ln_slots, 2] (sum, sum of squares) partials of the A rows, or nullptr
+  const float* ln_stats;  // [ln_slots][ln_stride rows][2] (sum, sum of squares) partials of the A rows (slot-major: the 32
+                          // rows of a warp read / write 256 contiguous bytes per slot), or nullptr
   const float* colsum;    // [N] fp32: sum over k of the (bf16-rounded) folded weight row
   int ln_slots;
+  int ln_stride;          // rows between two slots of ln_stats
   float ln_inv_k;         // 1 / K
   float ln_eps;
   // producer side (fp32 residual output): also emit a bf16 copy of the output rows and their partial sums
   bf16* xb_out;           // [M, ld_xb] or nullptr
-  float* stats_out;       // [M, N / 128, 2] or nullptr (one slot per (256-column tile, epilogue half))
+  float* stats_out;       // [N / 128][stats_stride rows][2] or nullptr: slot = (256-column tile, epilogue half)
+  int stats_stride;
   int ld_xb;
   int dbg_flags;          // MMT_GEMM_DEV builds only (MMT_GEMM_DBG): 1 = epilogue without global traffic, 2 = every tile
                           // loads the operands of tile 0 (pure L2 hits), ...
@@ -95,7 +98,7 @@ struct GemmConv {
 
 // PAIR: two CTAs of a cluster compute one 256 x BN tile with cta_group::2 MMAs - each loads its own 128 A rows and
 // HALF of the W rows, so a k-slice costs 32 KB of L2->SM traffic and smem per SM instead of 48 KB (BN = 256):
-// 6 pipeline stages instead of 4 and 1/3 less operand traffic for the same MMA work.
+// 4 pipeline stages of 32 KB (the per-warp epilogue tiles take the rest) and 1/3 less operand traffic for the same MMA work.
 template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -103,7 +106,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue shared memory per warp: one 4 KB staging tile; PAIR: two 4 KB tiles (fp32 residual / output tiles of the
   // TMA epilogue, double-buffered; the bf16 epilogue uses 2 KB of it for the packed rows + 512 B for its bias slices)
-  static constexpr int EPI_TILE_BYTES = PAIR ? 8192 : GEMM_STAGING_WORDS * 4;
+  // (+ 2 KB: the bf16 shadow tile of the folded-LayerNorm producer, mmt_gemm_bf16_ex)
+  static constexpr int EPI_TILE_BYTES = PAIR ? 8192 + 2048 : GEMM_STAGING_WORDS * 4;
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_TILE_BYTES;
   static constexpr int BAR_BYTES = 512;
   // the dynamic shared memory is declared __align__(1024) (checked at kernel start): no alignment slack is reserved
@@ -115,11 +119,15 @@ struct GemmCfg {
                                         : (2 * BN <= 256) ? 256 : 512;
 };
 
+// 320 threads are allocated as 384 (warps come in groups of four), so a thread may hold 65 536 / 384 = 170 -> 168 registers:
+// that is what __launch_bounds__(320, 1) makes ptxas target; a higher cap (__maxnreg__) compiles but the launch is refused
+// (cudaErrorLaunchOutOfResources).  The few spilled words are the epilogue's one-tile-ahead prefetch registers (written and
+// read once per tile, L1-resident).
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N,
-                         int K, GemmEpi ep, GemmConv cv) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                         const __grid_constant__ CUtensorMap tmX, int M, int N, int K, GemmEpi ep, GemmConv cv) {
   using Cfg = GemmCfg<BN, PAIR>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
@@ -298,6 +306,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   warp * (Cfg::EPI_TILE_BYTES / 16);
     const uint32_t rbar0 = bar_base + 256u + 16u * warp;          // this warp's two residual-tile barriers (PAIR)
     uint32_t rk = 0;                                               // running chunk counter of the TMA fp32 epilogue
+    uint32_t bk = 0;                                               // running chunk counter of the TMA bf16 epilogue
     constexpr int CH = Cfg::CH;
     constexpr int NCH = BN / CH;
     constexpr int VPR = CH / 4;                 // 16-byte fp32 vectors per staged row (8 or 4)
@@ -306,6 +315,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int LPR_H = CH / 8;               // bf16 out: lanes per row (8 columns each)
     constexpr int IT_H = LPR_H;
     auto key_of = [](int r) { return (r / KEYDIV) & (VPR - 1); };
+    // folded LayerNorm, consumer side: the partial sums of this thread's row are fetched ONE TILE AHEAD (raw values parked in
+    // registers, reduced when the tile starts), so their L2 latency never sits on the epilogue's critical path
+    const bool ln_active = !ep.out_fp32 && ep.vec_ok && ep.bias != nullptr && ep.ln_stats != nullptr && !cv.enabled;
+    constexpr int LN_MAX_SLOTS = 8;
+    float2 ln_raw[LN_MAX_SLOTS];
+    auto ln_fetch = [&](int t) {
+      const int g = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + (warp & 3) * 32 + lane;
+      const float2* sp = reinterpret_cast<const float2*>(ep.ln_stats) + g;
+#pragma unroll
+      for (int q = 0; q < LN_MAX_SLOTS; ++q)
+        ln_raw[q] = (q < ep.ln_slots && g < M && !(dbg_flags & 64)) ? __ldg(sp + static_cast<size_t>(q) * ep.ln_stride)
+                                                                    : make_float2(0.f, 0.f);
+    };
+    if (ln_active && worker < num_tiles) ln_fetch(worker);
+    // (Measured and dropped: requesting a warp's residual tiles into L2 one tile ahead with cp.async.bulk.prefetch made proj
+    // 50 -> 56 us and fc2 120 -> 130 us at M = 28 928 - like the A-operand prefetch of round 1, profiles/r2_gemm_epilogue.md.)
     int local = 0;
     for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
       const int as = local & 1;
@@ -368,7 +393,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const bool bias_smem = !ep.out_fp32 && ep.vec_ok && ep.bias != nullptr;
       // folded LayerNorm (consumer side): column sums of the folded weight beside the bias slices, and this thread's row
       // statistics from the partial sums its producer left (fixed summation order -> deterministic)
-      const bool ln_in = bias_smem && ep.ln_stats != nullptr && !cv.enabled;
+      const bool ln_in = ln_active;
       float* csum_s = bias_s + MAXC * CH;
       float ln_mu = 0.f, ln_rs = 1.f;
       if (bias_smem) {
@@ -386,21 +411,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
-      if (ln_in) {
-        const int grow = grow_of(lrow0 + lane);
-        if (grow >= 0) {
-          const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(grow) * ep.ln_slots * 2);
-          float s1 = 0.f, s2 = 0.f;
-          for (int q = 0; q < ep.ln_slots / 2; ++q) {       // slots come in pairs: (sum, sumsq, sum, sumsq)
-            const float4 t = __ldg(sp + q);
-            s1 += t.x; s2 += t.y; s1 += t.z; s2 += t.w;
-          }
-          ln_mu = s1 * ep.ln_inv_k;
-          ln_rs = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * ep.ln_inv_k), 0.f) + ep.ln_eps);
-        }
-      }
       // folded LayerNorm (producer side): running partial sums of this thread's output row over the chunks it owns
       float st_s1 = 0.f, st_s2 = 0.f;
+      if (ln_in) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < LN_MAX_SLOTS; ++q) { s1 += ln_raw[q].x; s2 += ln_raw[q].y; }      // fixed slot order: deterministic
+        ln_mu = s1 * ep.ln_inv_k;
+        ln_rs = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * ep.ln_inv_k), 0.f) + ep.ln_eps);
+        if (dbg_flags & 64) { ln_mu = 0.f; ln_rs = 1.f; }
+        if (tile + n_workers < num_tiles) ln_fetch(tile + n_workers);      // consumed at the start of the next tile
+      }
+
       const int grow_w = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0;   // first global row of this warp
       auto issue_resid = [&](int c, uint32_t k) {     // TMA load of the residual tile of chunk c into buffer k & 1
         if (lane == 0) {
@@ -469,17 +491,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               xbp[2 * j + 1] = pack_bf16x2(y2, y3);
             }
           }
-          if (ln_out && grow_w + lane < M) {
-            // thread == row: 32 consecutive bf16 (64 B = two full sectors) of this row, straight from registers
-            uint4* xo = reinterpret_cast<uint4*>(ep.xb_out + static_cast<size_t>(grow_w + lane) * ep.ld_xb + nb);
+          uint4* xtile = stg4 + 512;                     // bf16 shadow tile: 32 rows x 64 B, 64-byte swizzle (after the 2 x 4 KB)
+          if (ln_out) {
+            if (lane == 0) bulk_wait_read_all();         // the previous chunk's shadow-tile store has read it
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) xo[j] = make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              xtile[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
           }
           fence_proxy_async_shared();
           __syncwarp();
           if (lane == 0) {
             if (dbg_flags & 16) tma_store_2d_hint(&tmC, smem_u32(tile), nb, grow_w, l2_policy_evict_last());
             else tma_store_2d(&tmC, smem_u32(tile), nb, grow_w);
+            if (ln_out && !(dbg_flags & 256)) tma_store_2d(&tmX, smem_u32(xtile), nb, grow_w);
             bulk_commit_group();
           }
           continue;
@@ -530,7 +555,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 b = reinterpret_cast<const float4*>(bias_s + kc * CH)[j >> 2];   // broadcast reads
-              const float4 c = reinterpret_cast<const float4*>(csum_s + kc * CH)[j >> 2];
+              const float4 c = (dbg_flags & 128) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                 : reinterpret_cast<const float4*>(csum_s + kc * CH)[j >> 2];
               f[j] = fmaf(ln_rs, fmaf(nmu, c.x, f[j]), b.x);
               f[j + 1] = fmaf(ln_rs, fmaf(nmu, c.y, f[j + 1]), b.y);
               f[j + 2] = fmaf(ln_rs, fmaf(nmu, c.z, f[j + 2]), b.z);
@@ -581,8 +607,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             continue;
           }
           const bool tma_out = CH == 32 && ep.tma_store && !cv.enabled;
-          if (tma_out) {                       // the previous chunk's bulk store must have read the staging tile
-            if (lane == 0) bulk_wait_read_all();
+          uint4* stg = stg4;
+          if (tma_out) {
+            // the bulk store that last used this staging tile must have read it.  CTA-pair kernel: two tiles per warp (the
+            // second one in the area of the fp32 epilogue's buffers), so only the store of TWO chunks ago is waited for and
+            // packing chunk k overlaps the store of chunk k - 1; single-CTA kernel: one tile
+            if (PAIR && !(dbg_flags & 2048)) {
+              stg = stg4 + 256 * (bk++ & 1u);              // 4096 B apart (bias / column-sum slices sit at +2048 .. +3072)
+              if (lane == 0) bulk_wait_read_1();
+            } else if (lane == 0) {
+              bulk_wait_read_all();
+            }
             __syncwarp();
           }
 #pragma unroll
@@ -590,7 +625,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint4 w;
             w.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); w.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
             w.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); w.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            stg4[lane * LPR_H + (j ^ ((lane / KD_H) & (LPR_H - 1)))] = w;
+            stg[lane * LPR_H + (j ^ ((lane / KD_H) & (LPR_H - 1)))] = w;
           }
           if (tma_out) {
             // one bulk tensor store of the warp's 32 x 32 tile: no per-lane STG, rows beyond M are clipped by the TMA
@@ -598,8 +633,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             __syncwarp();
             if (lane == 0) {
               const int r0 = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0;
-              if (dbg_flags & 32) tma_store_2d_hint(&tmC, smem_u32(stg4), nb, r0, l2_policy_evict_first());
-              else tma_store_2d(&tmC, smem_u32(stg4), nb, r0);
+              if (dbg_flags & 32) tma_store_2d_hint(&tmC, smem_u32(stg), nb, r0, l2_policy_evict_first());
+              else tma_store_2d(&tmC, smem_u32(stg), nb, r0);
               bulk_commit_group();
             }
             continue;
@@ -635,11 +670,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       }
-      if (f32_tma && ep.stats_out != nullptr && grow_w + lane < M) {
-        // slot = (256-column tile, epilogue half): every (row, slot) is written by exactly one thread of the grid
-        float2* so = reinterpret_cast<float2*>(ep.stats_out) + static_cast<size_t>(grow_w + lane) * (N / 128) +
-                     (n0 / BN) * (BN / 128) + half;
-        *so = make_float2(st_s1, st_s2);
+      if (f32_tma && ep.stats_out != nullptr && grow_w + lane < M && !(dbg_flags & 512)) {
+        // slot = (256-column tile, epilogue half): every (slot, row) is written by exactly one thread of the grid, the 32
+        // rows of the warp as one 256-byte segment
+        const int slot = (n0 / BN) * (BN / 128) + half;
+        reinterpret_cast<float2*>(ep.stats_out)[static_cast<size_t>(slot) * ep.stats_stride + grow_w + lane] =
+            make_float2(st_s1, st_s2);
       }
       // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator
       tc_fence_before();
@@ -777,8 +813,8 @@ static int num_sms() {
 }
 
 // CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles
-static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const void* W, int ldw,
-                            int M, int N, int K, const GemmEpi& ep, cudaStream_t stream) {
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const CUtensorMap& tmX,
+                            const void* W, int ldw, int M, int N, int K, const GemmEpi& ep, cudaStream_t stream) {
   constexpr int BN = 256;
   using Cfg = GemmCfg<BN, true>;
   CUtensorMap tmB;
@@ -807,7 +843,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, cons
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GemmConv cv = {};
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, tmR, M, N, K, ep, cv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, tmR, tmX, M, N, K, ep, cv);
   if (e != cudaSuccess) return (int)e;
   MMT_RETURN_LAST_ERROR();
 }
@@ -830,7 +866,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const voi
   const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC, M, N, K, ep, cv);
+  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC, tmC, M, N, K, ep, cv);
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -896,9 +932,11 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
         make_tmap_f32_tile(&tmC, ep.out, M, N, ep.ldo) == MMT_OK &&
         make_tmap_f32_tile(&tmR, ep.resid, M, N, ep.ldr) == MMT_OK)
       ep.tma_f32 = 1;
+    CUtensorMap tmX = tmA;
+    if (ep.tma_f32 && ep.xb_out && make_tmap_out(&tmX, ep.xb_out, M, N, ep.ld_xb) != MMT_OK) ep.tma_f32 = 0;
     if (!ep.tma_f32) { ep.xb_out = nullptr; ep.stats_out = nullptr; }
     else if (ln_produced && ep.xb_out) *ln_produced = 1;
-    return launch_gemm_pair(tmA, tmC, tmR, W, ldw, M, N, K, ep, s);
+    return launch_gemm_pair(tmA, tmC, tmR, tmX, W, ldw, M, N, K, ep, s);
   }
   ep.xb_out = nullptr;
   ep.stats_out = nullptr;
@@ -959,7 +997,8 @@ static void pick_conv_box(int H, int W, int* BW, int* BH) {
 }  // namespace mmt
 
 namespace mmt {
-int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, cudaStream_t s);
+int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, int slot_stride,
+                         cudaStream_t s);
 
 static void init_epi(GemmEpi& ep) {
   std::memset(&ep, 0, sizeof(ep));
@@ -975,8 +1014,9 @@ static void init_epi(GemmEpi& ep) {
 
 extern "C" int mmt_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                                 int act, const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out,
-                                int ldo, int out_fp32, int max_ctas, const float* ln_stats, int ln_slots, float ln_eps,
-                                const float* colsum, void* xb_out, int ld_xb, float* stats_out, void* stream) {
+                                int ldo, int out_fp32, int max_ctas, const float* ln_stats, int ln_slots, int ln_stride,
+                                float ln_eps, const float* colsum, void* xb_out, int ld_xb, float* stats_out,
+                                int stats_stride, void* stream) {
   using namespace mmt;
   MMT_CHECK_ARG(A && W && out && M > 0 && N > 0 && K > 0);
   MMT_CHECK_ARG(lda >= K && ldw >= K && ldo >= N);
@@ -996,15 +1036,17 @@ extern "C" int mmt_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, 
   if (ln_stats) {
     // folded LayerNorm, consumer side: bf16 output, per-column (bias, colsum) vectors, every column chunk complete
     MMT_CHECK_ARG(colsum && bias && !out_fp32 && !rowadd && ep.vec_ok && (N % 32) == 0);
-    MMT_CHECK_ARG(ln_slots > 0 && (ln_slots % 2) == 0 && al16(ln_stats) && al16(colsum));
-    ep.ln_stats = ln_stats; ep.colsum = colsum; ep.ln_slots = ln_slots; ep.ln_inv_k = 1.0f / static_cast<float>(K);
+    MMT_CHECK_ARG(ln_slots > 0 && ln_slots <= 8 && ln_stride >= M && (reinterpret_cast<uintptr_t>(ln_stats) & 7) == 0 &&
+                  al16(colsum));
+    ep.ln_stats = ln_stats; ep.colsum = colsum; ep.ln_slots = ln_slots; ep.ln_stride = ln_stride;
+    ep.ln_inv_k = 1.0f / static_cast<float>(K);
     ep.ln_eps = ln_eps;
   }
   if (xb_out || stats_out) {
     // producer side: fp32 output rows (N a multiple of 128: one statistics slot per 128 columns) + bf16 copy + partial sums
     MMT_CHECK_ARG(xb_out && stats_out && out_fp32 && (N % 128) == 0 && ld_xb >= N && (ld_xb % 8) == 0 && al16(xb_out) &&
-                  (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0 && ldo == N);
-    ep.xb_out = static_cast<bf16*>(xb_out); ep.stats_out = stats_out; ep.ld_xb = ld_xb;
+                  (reinterpret_cast<uintptr_t>(stats_out) & 7) == 0 && ldo == N && stats_stride >= M);
+    ep.xb_out = static_cast<bf16*>(xb_out); ep.stats_out = stats_out; ep.ld_xb = ld_xb; ep.stats_stride = stats_stride;
   }
   CUtensorMap tmA;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
@@ -1015,7 +1057,7 @@ extern "C" int mmt_gemm_bf16_ex(const void* A, int lda, const void* W, int ldw, 
   rc = dispatch_gemm(tmA, W, ldw, M, N, K, ep, cv, max_ctas, s, &produced);
   if (rc) return rc;
   if (xb_out && !produced)      // launch shapes without the fused form: same outputs from the row-statistics kernel
-    return launch_rowstats_cast(static_cast<const float*>(out), M, N, xb_out, ld_xb, stats_out, N / 128, s);
+    return launch_rowstats_cast(static_cast<const float*>(out), M, N, xb_out, ld_xb, stats_out, N / 128, stats_stride, s);
   return MMT_OK;
 }
 
@@ -1023,7 +1065,7 @@ extern "C" int mmt_gemm_bf16(const void* A, int lda, const void* W, int ldw, int
                              int act, const float* resid, int ldr, const float* rowadd, int rowadd_period, void* out,
                              int ldo, int out_fp32, int max_ctas, void* stream) {
   return mmt_gemm_bf16_ex(A, lda, W, ldw, M, N, K, bias, act, resid, ldr, rowadd, rowadd_period, out, ldo, out_fp32,
-                          max_ctas, nullptr, 0, 0.f, nullptr, nullptr, 0, nullptr, stream);
+                          max_ctas, nullptr, 0, 0, 0.f, nullptr, nullptr, 0, nullptr, 0, stream);
 }
 
 extern "C" int mmt_conv3x3_bf16(const void* in, int ld_in, int B, int H, int W, int C, const void* Wt, int ldw, int N,

@@ -142,46 +142,77 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, f
 // ------------------------------------------------------------------------------------------------
 // Row statistics + bf16 cast: the stand-alone producer of the folded LayerNorm (mmt_gemm_bf16_ex).  For rows whose
 // producer is not a fused GEMM epilogue (the token embedding, the rows candidate elimination re-gathered, launch shapes
-// without the CTA-pair epilogue) this kernel leaves what that epilogue leaves: a bf16 copy of the fp32 row and its
-// (sum, sum of squares) in statistics slot 0, zeros in the other slots.  One warp per row, one pass over HBM.
+// without the CTA-pair epilogue) this kernel leaves EXACTLY what that epilogue leaves: a bf16 copy of the fp32 row and, per
+// 128-column statistics slot, the partial (sum, sum of squares) accumulated in the epilogue's own order - slot s covers the
+// 32-column chunks {h, h+2, h+4, h+6} (h = s & 1) of the 256-column tile s >> 1, columns ascending, four at a time
+// (gemm_tc.cu, TMA fp32 epilogue).  Equal partial sums mean equal mean / rstd bits downstream, so a sequence's boxes do not
+// depend on whether its batch was large enough for the CTA-pair kernel (tests: sub-batch bit-identity).
+// One warp per row, one pass over HBM; the row is parked in shared memory (33-word pitch) for the ordered slot sums.
 template <int MAXV>  // C <= MAXV * 128
 __global__ void rowstats_cast_kernel(const float* __restrict__ x, int rows, int C, bf16* __restrict__ xb, int ld_xb,
-                                     float* __restrict__ stats, int slots) {
+                                     float* __restrict__ stats, int slots, int slot_stride) {
+  extern __shared__ float rs_smem[];
+  const int wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
+  float* row = rs_smem + wib * (MAXV * 128 + MAXV * 4);
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * C);
   const int nv = C >> 2;
-  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nv) {
       const float4 v = xr[idx];
-      s1 += (v.x + v.y) + (v.z + v.w);
-      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
       uint2 p;
       p.x = pack_bf16x2(v.x, v.y);
       p.y = pack_bf16x2(v.z, v.w);
       reinterpret_cast<uint2*>(xb + static_cast<size_t>(warp) * ld_xb)[idx] = p;
+      const int c = idx * 4;
+      float* d = row + c + (c >> 5);                 // 33-word pitch per 32-column chunk: the slot lanes hit distinct banks
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
   }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  float2* so = reinterpret_cast<float2*>(stats) + static_cast<size_t>(warp) * slots;
-  if (lane < slots) so[lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+  __syncwarp();
+  if (lane < slots) {
+    const int tile = lane >> 1, h = lane & 1;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = tile * 256 + (h + 2 * k) * 32;
+      if (c0 >= C) break;
+      const float* d = row + c0 + (c0 >> 5);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y0 = d[4 * j], y1 = d[4 * j + 1], y2 = d[4 * j + 2], y3 = d[4 * j + 3];
+        s1 += (y0 + y1) + (y2 + y3);
+        s2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, s2))));
+      }
+    }
+    reinterpret_cast<float2*>(stats)[static_cast<size_t>(lane) * slot_stride + warp] = make_float2(s1, s2);
+  }
 }
 
-int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, cudaStream_t s) {
-  if (!(x && xb && stats && rows > 0 && C > 0 && C % 4 == 0 && C <= 2048 && slots > 0 && slots <= 32 && ld_xb >= C &&
-        ld_xb % 4 == 0))
+int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots, int slot_stride,
+                         cudaStream_t s) {
+  // slots = C / 128 (one per 128 columns), the layout the consumer epilogue sums: C a multiple of 128
+  if (!(x && xb && stats && rows > 0 && C > 0 && C % 128 == 0 && C <= 2048 && slots == C / 128 && ld_xb >= C &&
+        ld_xb % 4 == 0 && slot_stride >= rows))
     return MMT_ERR_BAD_ARG;
   const int wpb = 8;
   const int grid = cdiv(rows, wpb);
   bf16* o = reinterpret_cast<bf16*>(xb);
-  if (C <= 512) rowstats_cast_kernel<4><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
-  else if (C <= 1024) rowstats_cast_kernel<8><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
-  else rowstats_cast_kernel<16><<<grid, wpb * 32, 0, s>>>(x, rows, C, o, ld_xb, stats, slots);
+  auto smem = [&](int maxv) { return static_cast<size_t>(wpb) * (maxv * 128 + maxv * 4) * sizeof(float); };
+  if (C <= 512) rowstats_cast_kernel<4><<<grid, wpb * 32, smem(4), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
+  else if (C <= 1024) rowstats_cast_kernel<8><<<grid, wpb * 32, smem(8), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
+  else {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(rowstats_cast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(16));
+      if (e != cudaSuccess) return (int)e;
+      attr = true;
+    }
+    rowstats_cast_kernel<16><<<grid, wpb * 32, smem(16), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
+  }
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -450,8 +481,8 @@ __global__ void corner_decode_kernel(CornerArgs a, int S, int C4, float stride_p
     float acc = 0.f;
     for (int c = 0; c < C4; ++c) acc = fmaf(to_f<T>(row[c]), __ldg(w5 + c), acc);
     acc += a.b5[cor];
-    acc += to_f<T>(a3[(static_cast<size_t>(b) * S4 * S4 + (y / 4) * S4 + x / 4) * a.lda3]);
-    acc += to_f<T>(a4[(static_cast<size_t>(b) * S2 * S2 + (y / 2) * S2 + x / 2) * a.lda4]);
+    if (a3) acc += to_f<T>(a3[(static_cast<size_t>(b) * S4 * S4 + (y / 4) * S4 + x / 4) * a.lda3]);   // pyramid head only
+    if (a4) acc += to_f<T>(a4[(static_cast<size_t>(b) * S2 * S2 + (y / 2) * S2 + x / 2) * a.lda4]);
     logit[i] = acc;
     if (score_maps) score_maps[(static_cast<size_t>(b) * 2 + cor) * n + i] = acc;
     lmax = fmaxf(lmax, acc);
@@ -574,8 +605,8 @@ extern "C" int mmt_layernorm(const float* x, int rows, int C, float eps, const f
 }
 
 extern "C" int mmt_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, float* stats, int slots,
-                                void* stream) {
-  return mmt::launch_rowstats_cast(x, rows, C, xb, ld_xb, stats, slots, reinterpret_cast<cudaStream_t>(stream));
+                                int slot_stride, void* stream) {
+  return mmt::launch_rowstats_cast(x, rows, C, xb, ld_xb, stats, slots, slot_stride, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float eps, const float* gamma,
@@ -668,8 +699,10 @@ extern "C" int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x,
                                  int lda3, const void* a4_tl, const void* a4_br, int lda4, int B, int S,
                                  float stride_px, float img_sz, float* score_maps, float* xyxy, float* cxcywh,
                                  int is_bf16, void* stream) {
-  MMT_CHECK_ARG(x4_tl && x4_br && w5_tl && w5_br && a3_tl && a3_br && a4_tl && a4_br && xyxy && cxcywh);
-  MMT_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0 && S * S * 4 <= 96 * 1024 && C4 > 0 && img_sz > 0);
+  MMT_CHECK_ARG(x4_tl && x4_br && w5_tl && w5_br && xyxy && cxcywh);
+  // a3 / a4 (the pyramid head's side maps) come in pairs or not at all (plain Corner_Predictor, head.py:23-94)
+  MMT_CHECK_ARG((a3_tl != nullptr) == (a3_br != nullptr) && (a4_tl != nullptr) == (a4_br != nullptr));
+  MMT_CHECK_ARG(B > 0 && S > 0 && (S % 4 == 0 || (!a3_tl && !a4_tl)) && S * S * 4 <= 96 * 1024 && C4 > 0 && img_sz > 0);
   CornerArgs a;
   a.x4[0] = x4_tl; a.x4[1] = x4_br; a.a3[0] = a3_tl; a.a3[1] = a3_br; a.a4[0] = a4_tl; a.a4[1] = a4_br;
   a.w5[0] = w5_tl; a.w5[1] = w5_br; a.b5[0] = b5_tl; a.b5[1] = b5_br;

@@ -9,7 +9,9 @@ Data layout in HBM (B = sequences in the batched step, N = tokens per sequence-m
   * GEMM inputs are `act` dtype = bf16 (fast mode) or fp32 (parity mode); LayerNorm/GroupNorm statistics, the
     residual stream, softmax state, sampling offsets and the corner soft-argmax are always fp32;
   * feature maps are NHWC (== token rows); conv weights are packed [O, (ky, kx, c)] with eval-BatchNorm folded;
-  * all workspaces are allocated once per batch size and reused (no allocation inside a step).
+  * all workspaces are allocated once per batch size and reused (no allocation inside a step);
+  * bf16 mode: the blocks' LayerNorms are folded into the GEMMs around them (_block_folded) - the residual stream has a
+    bf16 shadow copy `xb` and per-row partial sums written by the proj / fc2 epilogues, the normalised rows never exist.
 
 No torch compute op is on the path: torch provides memory (torch.empty) and the stream only.
 """
@@ -54,15 +56,19 @@ class ForwardEngine:
         self.Ls0, self.Lt = self.gs * self.gs, 2 * self.gt * self.gt
         self.N0 = self.Lt + self.Ls0
         self.head_type = m["HEAD_TYPE"]
-        if self.head_type != "CORNER_UP":
-            raise NotImplementedError("only the CORNER_UP (pyramid) head - used by every shipped YAML - is on the "
-                                      "accelerated path")
+        if self.head_type not in ("CORNER_UP", "CORNER"):
+            raise NotImplementedError(f"HEAD_TYPE {self.head_type!r}: only the corner heads (CORNER_UP = pyramid, used by "
+                                      "every shipped MixViT / ConvMAE YAML, and the plain CORNER) are on the accelerated path")
         self.rgbt = variant not in ("mixformer_vit", "mixformer_vit_online", "mixformer_convmae_online")
         self.fusion_class = m.get("FUSION_CLASS") if self.rgbt else None
         bb = m.get("BACKBONE", {})
         self.ce_loc = list(bb["CE_LOC"]) if (variant == "asymmetric_shared_ce" and "CE_LOC" in bb) else []
         self.ce_keep = list(bb["CE_KEEP_RATIO"]) if self.ce_loc else []
         self.scale = (self.dim // self.heads) ** -0.5
+        # LayerNorm folded into the GEMMs around it (bf16 tensor-core path; _block): the normalised rows never exist in HBM.
+        # MMT_LN_FOLD=0 keeps the stand-alone LayerNorm kernel (A/B measurements); the fp32 parity mode always does.
+        import os
+        self.ln_fold = self.bf16 and os.environ.get("MMT_LN_FOLD", "1") != "0"
         self._ws = {}
         self._tiles = {}
         self.aux = {}
@@ -95,8 +101,22 @@ class ForwardEngine:
                 else:
                     b[f"ln{j}"] = (_f32(g(p + f"norm{j}.weight"), dev), _f32(g(p + f"norm{j}.bias"), dev), None, None)
             for name, key in (("qkv", "attn.qkv"), ("proj", "attn.proj"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2")):
-                b[name + "_w"] = self._w(g(p + key + ".weight"))
-                b[name + "_b"] = _f32(g(p + key + ".bias"), dev)
+                folded = self.ln_fold and name in ("qkv", "fc1")
+                if not folded:
+                    b[name + "_w"] = self._w(g(p + key + ".weight"))
+                    b[name + "_b"] = _f32(g(p + key + ".bias"), dev)
+                    continue
+                # Linear(LN(x)) = rs * (x W'^T - mu * colsum) + bias'  with  W' = W diag(gamma), colsum = rowsum(bf16 W'),
+                # bias' = bias + W beta (one set per modality-specific norm): include/mmt_b200.h, mmt_gemm_bf16_ex
+                W = g(p + key + ".weight").detach().float().cpu()
+                bias = g(p + key + ".bias").detach().float().cpu()
+                ln = b["ln1" if name == "qkv" else "ln2"]
+                sets = []
+                for s_ in range(2 if ln[2] is not None else 1):
+                    gam, bet = ln[2 * s_].float().cpu(), ln[2 * s_ + 1].float().cpu()
+                    Wf = (W * gam[None, :]).to(torch.bfloat16)
+                    sets.append((Wf.to(dev).contiguous(), _f32(bias + W @ bet, dev), _f32(Wf.float().sum(dim=1), dev)))
+                b[name + "_f"] = sets
             blocks.append(b)
         bb["blocks"] = blocks
         return bb
@@ -118,6 +138,23 @@ class ForwardEngine:
         fold = lambda n: self._fold_bn(sd, "box_head." + n)
         ws, bs, self.s1_cols = [], [], {}
         col = 0
+        self.head_ch = sd["box_head.conv1_tl.0.weight"].shape[0]
+        if self.head_type == "CORNER":       # Corner_Predictor head.py:23-94: conv1..conv4 (3x3 + BN + ReLU) + conv5 (1x1) at stride 16
+            for n in ("conv1_tl", "conv1_br"):
+                w, b = fold(n)
+                self.s1_cols[n] = (col, col + w.shape[0])
+                col += w.shape[0]
+                ws.append(w)
+                bs.append(b)
+            H["s1_w"], H["s1_b"] = self._w(torch.cat(ws, 0)), _f32(torch.cat(bs, 0), dev)
+            self.s1_width = col
+            for c in ("tl", "br"):
+                for n in (f"conv2_{c}", f"conv3_{c}", f"conv4_{c}"):
+                    w, b = fold(n)
+                    H[n + "_w"], H[n + "_b"] = self._w(w), _f32(b, dev)
+                H[f"w5_{c}"] = _f32(sd[f"box_head.conv5_{c}.weight"].reshape(-1), dev)
+                H[f"b5_{c}"] = float(sd[f"box_head.conv5_{c}.bias"].detach().float().reshape(-1)[0])
+            return H
         for n in ("conv1_tl", "conv1_br", "adjust1_tl", "adjust1_br", "adjust2_tl", "adjust2_br"):
             w, b = fold(n)
             self.s1_cols[n] = (col, col + w.shape[0])
@@ -133,7 +170,6 @@ class ForwardEngine:
                 H[n + "_w"], H[n + "_b"] = self._w(w), _f32(b, dev)
             H[f"w5_{c}"] = _f32(sd[f"box_head.conv5_{c}.weight"].reshape(-1), dev)
             H[f"b5_{c}"] = float(sd[f"box_head.conv5_{c}.bias"].detach().float().reshape(-1)[0])
-        self.head_ch = sd["box_head.conv1_tl.0.weight"].shape[0]
         return H
 
     def _pack_fusion(self, sd):
@@ -269,10 +305,15 @@ class ForwardEngine:
         ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos"], out=x)
 
     def _block(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep=None, gidx=None, tiles=None, qkv1=None,
-               qkv_out=None):
+               qkv_out=None, first=True, last=True):
         """One pre-LN block on x [nseq*N, dim] fp32 (in place).  Returns (x, N, Ls, gidx) - changed by CE.
         tiles / qkv1 / qkv_out: explicit attention tile table, second (cached) qkv buffer and the buffer that receives
-        this block's qkv (the cached-template paths of engine_online.py)."""
+        this block's qkv (the cached-template paths of engine_online.py).
+        first / last: position of the block in its chain of `_block` calls on the same x (folded LayerNorm: the first
+        block has no producing GEMM in front of it, the last one no consumer behind it)."""
+        if self.ln_fold:
+            return self._block_folded(blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep, gidx, tiles, qkv1, qkv_out,
+                                      first, last)
         M = nseq * N
         dim = self.dim
         h = self._buf(tag, "h", (M, dim), self.act)
@@ -285,7 +326,8 @@ class ForwardEngine:
         ops.mixattn(qkv, qkv1, dim, self.heads, tiles, max_keys, att, self.scale)
         ops.gemm(att, blk["proj_w"], blk["proj_b"], ops.ACT_NONE, x, None, out=x)
         if ce_keep is not None:
-            x, N, Ls, gidx = self._candidate_elimination(qkv, x, nseq, N, Ls, ce_keep, gidx, tag)
+            x, N, Ls, gidx = self._candidate_elimination(qkv, x, nseq, N, Ls, ce_keep, gidx, tag,
+                                                         q_src=qkv1 if N == Ls else None)
             M = nseq * N
             h = self._buf(tag, "h", (M, dim), self.act)
         g0, b0, g1, b1 = blk["ln2"]
@@ -295,29 +337,86 @@ class ForwardEngine:
         ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], ops.ACT_NONE, x, None, out=x)
         return x, N, Ls, gidx
 
+    # ---- the same block with both LayerNorms folded into the GEMMs around them (bf16 mode; mmt_gemm_bf16_ex):
+    #   proj / fc2 epilogue   : x += ... (fp32, as before) AND a bf16 copy xb of the new rows + their partial (sum, sumsq)
+    #   qkv / fc1 GEMM        : A = xb (raw rows), W' = W diag(gamma); epilogue = rs * (acc - mu * colsum) + bias', GELU
+    # so the normalised activations are never written to or read from HBM: 2 launches and ~270 MB of traffic per block
+    # and modality at 64 sequences.  Rows without a producing GEMM (first block of a chain, rows re-gathered by candidate
+    # elimination) get xb / sums from mmt_rowstats_cast.  Modality-specific norms = one consumer launch per row range.
+    def _ln_bufs(self, tag, M):
+        return (self._buf(tag, "xb", (M, self.dim), torch.bfloat16),
+                self._buf(tag, "ln_sums", (self.dim // 128, M, 2), torch.float32))       # slot-major partial sums
+
+    def _gemm_ln(self, xb, sums, sets, period, act, out):
+        M = xb.shape[0]
+        if period and len(sets) > 1:
+            for (w, b, cs), (r0, r1) in zip(sets, ((0, period), (period, M))):
+                ops.gemm(xb[r0:r1], w, b, act, out=out[r0:r1], ln_stats=sums[:, r0:r1], ln_eps=1e-6, colsum=cs)
+        else:
+            w, b, cs = sets[0]
+            ops.gemm(xb, w, b, act, out=out, ln_stats=sums, ln_eps=1e-6, colsum=cs)
+
+    def _block_folded(self, blk, x, nseq, N, Ls, ln_period, cross, tag, ce_keep, gidx, tiles, qkv1, qkv_out, first, last):
+        M = nseq * N
+        dim = self.dim
+        qkv = qkv_out if qkv_out is not None else self._buf(tag, "qkv", (M, 3 * dim), self.act)
+        att = self._buf(tag, "att", (M, dim), self.act)
+        xb, sums = self._ln_bufs(tag, M)
+        if first:
+            ops.rowstats_cast(x, xb, sums)
+        self._gemm_ln(xb, sums, blk["qkv_f"], ln_period, ops.ACT_NONE, qkv)
+        tiles, max_keys = tiles if tiles is not None else self._attn_tiles("cross" if cross else "sym", nseq, N, Ls)
+        ops.mixattn(qkv, qkv1, dim, self.heads, tiles, max_keys, att, self.scale)
+        if ce_keep is not None:
+            ops.gemm(att, blk["proj_w"], blk["proj_b"], ops.ACT_NONE, x, None, out=x)
+            x, N, Ls, gidx = self._candidate_elimination(qkv, x, nseq, N, Ls, ce_keep, gidx, tag,
+                                                         q_src=qkv1 if N == Ls else None)
+            M = nseq * N
+            xb, sums = self._ln_bufs(tag, M)
+            ops.rowstats_cast(x, xb, sums)
+        else:
+            ops.gemm(att, blk["proj_w"], blk["proj_b"], ops.ACT_NONE, x, None, out=x, xb_out=xb, stats_out=sums)
+        hid = self._buf(tag, "hid", (M, 4 * dim), self.act)
+        self._gemm_ln(xb, sums, blk["fc1_f"], nseq * N // 2 if ln_period else 0, ops.ACT_GELU, hid)
+        if last:
+            ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], ops.ACT_NONE, x, None, out=x)
+        else:
+            ops.gemm(hid, blk["fc2_w"], blk["fc2_b"], ops.ACT_NONE, x, None, out=x, xb_out=xb, stats_out=sums)
+        return x, N, Ls, gidx
+
     def _ln(self, x, g0, b0, g1, b1, period, eps, out):
         if self.bf16:
             ops.layernorm(x, g0, b0, g1, b1, period, eps, out_bf16=out)
         else:
             ops.layernorm(x, g0, b0, g1, b1, period, eps, out_f32=out)
 
-    def _candidate_elimination(self, qkv, x, nseq, N, Ls, keep_ratio, gidx, tag):
-        """asymmetric_shared_ce.py:49-101 (test-time branch: no template mask)."""
+    def _candidate_elimination(self, qkv, x, nseq, N, Ls, keep_ratio, gidx, tag, q_src=None):
+        """asymmetric_shared_ce.py:49-101 (test-time branch: no template mask).
+        q_src: the block's cached template q/k/v [nseq*Lt, 3*dim] when x / qkv hold the search rows only (forward_search);
+        the template rows of x (N - Ls of them per sequence: Lt or 0) are carried over unchanged."""
         keep = math.ceil(keep_ratio * Ls)
         if keep == Ls:
             return x, N, Ls, gidx
         B = nseq // 2
+        lt_x = N - Ls                       # template rows inside x: Lt (full forward) or 0 (search-only rows)
         nqt = 2 * self.Lt // 32
         partial = self._buf(tag, "ce_partial", (B * self.heads * nqt * 2 * Ls,), torch.float32)
-        scores = torch.empty((B, 2 * Ls), device=self.dev, dtype=torch.float32)
-        ops.ce_scores(qkv, self.dim, self.heads, B, N, self.Lt, Ls, self.scale, partial, scores)
-        g_keep = torch.empty((nseq, keep), device=self.dev, dtype=torch.float32)
-        g_rem = torch.empty((nseq, Ls - keep), device=self.dev, dtype=torch.float32)
-        order = torch.empty((nseq, Ls), device=self.dev, dtype=torch.int32)
+        # per-stage workspaces, allocated once per batch size (no allocation inside a step; the aux outputs below are
+        # views of them, valid until the next forward)
+        stage = len(self.aux["ce_scores"])
+        scores = self._buf(tag, f"ce_scores{stage}", (B, 2 * Ls), torch.float32)
+        if q_src is None:
+            ops.ce_scores(qkv, self.dim, self.heads, B, N, self.Lt, Ls, self.scale, partial, scores)
+        else:
+            ops.ce_scores(qkv, self.dim, self.heads, B, N, self.Lt, Ls, self.scale, partial, scores, q_src=q_src,
+                          q_seq_rows=self.Lt, k_row_off=lt_x)
+        g_keep = self._buf(tag, f"ce_keep{stage}", (nseq, keep), torch.float32)
+        g_rem = self._buf(tag, f"ce_rem{stage}", (nseq, Ls - keep), torch.float32)
+        order = self._buf(tag, f"ce_order{stage}", (nseq, Ls), torch.int32)
         ops.ce_topk(scores, B, Ls, keep, gidx, g_keep, g_rem, order)
-        n_new = self.Lt + keep
-        x_new = torch.empty((nseq * n_new, self.dim), device=self.dev, dtype=torch.float32)
-        ops.ce_gather_tokens(x, nseq, N, self.Lt, order, Ls, keep, x_new)
+        n_new = lt_x + keep
+        x_new = self._buf(tag, f"ce_x{stage}", (nseq * n_new, self.dim), torch.float32)
+        ops.ce_gather_tokens(x, nseq, N, lt_x, order, Ls, keep, x_new)
         self.aux["ce_scores"].append(scores)
         self.aux["ce_keep"].append(g_keep)
         self.aux["ce_removed"].append(g_rem)
@@ -353,7 +452,7 @@ class ForwardEngine:
                 ce_keep = None
         st["x"], st["N"], st["Ls"], st["gidx"] = self._block(
             bb["blocks"][i], st["x"], nseq, st["N"], st["Ls"], (nseq * st["N"] // 2) if st["per_ln"] else 0, st["cross"],
-            tag, ce_keep, st["gidx"])
+            tag, ce_keep, st["gidx"], first=(i == 0), last=(i == len(bb["blocks"]) - 1))
 
     def _backbone_end(self, st, nseq, tag):
         x, N, Ls, gidx = st["x"], st["N"], st["Ls"], st["gidx"]
@@ -506,7 +605,9 @@ class ForwardEngine:
         return ops.gemm(col, w, b, ops.ACT_RELU, out=out)
 
     def _run_head(self, feat, B, want_maps=True):
-        """Pyramid corner head on NHWC rows feat [B*gs*gs, C] -> boxes cxcywh [B,4] (+ raw score maps)."""
+        """Corner head on NHWC rows feat [B*gs*gs, C] -> boxes cxcywh [B,4] (+ raw score maps)."""
+        if self.head_type == "CORNER":
+            return self._run_head_plain(feat, B, want_maps)
         H = self.head
         gs = self.gs
         ch = self.head_ch                       # 384
@@ -561,6 +662,30 @@ class ForwardEngine:
         xyxy = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
         boxes = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
         ops.corner_decode(x4s, (H["w5_tl"], H["w5_br"]), (H["b5_tl"], H["b5_br"]), a3s, a4s, B, S, 4.0,
+                          float(self.search_size), xyxy, boxes, maps)
+        self._last_xyxy = xyxy
+        return boxes, maps
+
+    def _run_head_plain(self, feat, B, want_maps=True):
+        """Corner_Predictor (head.py:23-94): both corners' conv1 as one launch, then conv2..conv4 per corner at the
+        backbone resolution, conv5 (1x1) + softmax + soft-argmax (stride 16) in the decode kernel."""
+        H, gs, ch, C = self.head, self.gs, self.head_ch, feat.shape[1]
+        tag = ("headp", B)
+        n = B * gs * gs
+        s1 = self._buf(tag, "s1", (n, self.s1_width), self.act)
+        self._conv3x3(feat, B, gs, gs, C, H["s1_w"], H["s1_b"], s1, tag)
+        x4s = []
+        for c in ("tl", "br"):
+            a = s1[:, self.s1_cols[f"conv1_{c}"][0]: self.s1_cols[f"conv1_{c}"][1]]
+            for j, co in ((2, ch // 2), (3, ch // 4), (4, ch // 8)):
+                o = self._buf(tag, f"x{j}{c}", (n, co), self.act)
+                self._conv3x3(a, B, gs, gs, a.shape[1], H[f"conv{j}_{c}_w"], H[f"conv{j}_{c}_b"], o, (tag, c))
+                a = o
+            x4s.append(a)
+        maps = torch.empty((B, 2, gs * gs), device=self.dev, dtype=torch.float32) if want_maps else None
+        xyxy = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
+        boxes = torch.empty((B, 4), device=self.dev, dtype=torch.float32)
+        ops.corner_decode(x4s, (H["w5_tl"], H["w5_br"]), (H["b5_tl"], H["b5_br"]), None, None, B, gs, 16.0,
                           float(self.search_size), xyxy, boxes, maps)
         self._last_xyxy = xyxy
         return boxes, maps
@@ -633,9 +758,10 @@ class ForwardEngine:
         return hit
 
     def _check_cacheable(self):
-        if self.variant in CROSS_MODAL or self.ce_loc:
-            raise NotImplementedError("template caching is implemented for the symmetric variants (mixformer_vit, "
-                                      "mixformer_vit_rgbt, _shared, _unibackbone)")
+        """Every variant qualifies: template rows attend template keys of their own modality only - also in the cross-modal
+        blocks (asymmetric_shared.py:55-104: q_mt x k_mt per modality) and with candidate elimination, which prunes search
+        tokens only (asymmetric_shared_ce.py:49-101)."""
+        return None
 
     def cache_templates(self, template, online_template):
         self._check_cacheable()
@@ -661,17 +787,15 @@ class ForwardEngine:
                 sub = buf[m * B * Lt:(m + 1) * B * Lt]
                 self._stage_tokens(bb, ts[m], sub, 0, Lt)
                 self._stage_tokens(bb, ots[m], sub, T, Lt)
-            pos_tt = self._ws.get("pos_tt")
-            if pos_tt is None:
-                pos_tt = bb["pos"][:Lt].contiguous()
-                self._ws["pos_tt"] = pos_tt
-                self._ws["pos_ss"] = bb["pos"][Lt:].contiguous()
-            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, pos_tt, out=x)
+            if "pos_tt" not in bb:       # per backbone: backbone_v / backbone_i carry their own positional tables
+                bb["pos_tt"] = bb["pos"][:Lt].contiguous()
+                bb["pos_ss"] = bb["pos"][Lt:].contiguous()
+            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos_tt"], out=x)
             tiles = self._seq_tiles("tcache", nseq, Lt, lambda sq: [(0, sq * Lt, Lt)])
             cache = [self._buf(tag, f"qkv{i}", (nseq * Lt, 3 * self.dim), self.act) for i in range(self.depth)]
             for i, blk in enumerate(bb["blocks"]):
                 self._block(blk, x, nseq, Lt, 0, (nseq * Lt // 2) if per_ln else 0, False, tag, tiles=tiles,
-                            qkv_out=cache[i])
+                            qkv_out=cache[i], first=(i == 0), last=(i == self.depth - 1))
             self._tcache.append((cache, nseq, B))
 
     def forward_search(self, search, want_maps=True):
@@ -699,12 +823,39 @@ class ForwardEngine:
             buf = self._embed_buf(nseq * Ls)
             for m in range(len(imgs)):
                 self._stage_tokens(bb, imgs[m], buf[m * B * Ls:(m + 1) * B * Ls], 0, Ls)
-            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_ss"], out=x)
-            tiles = self._seq_tiles("scache", nseq, Ls, lambda sq: [(1, sq * Lt, Lt), (0, sq * Ls, Ls)])
+            ops.gemm(buf, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, bb["pos_ss"], out=x)
+            cross = self.variant in CROSS_MODAL
+            Bh = nseq // 2
+
+            def tiles_for(ls):
+                if not cross:      # keys: the sequence's cached template rows, then its own search rows
+                    return self._seq_tiles(("scache", ls), nseq, ls, lambda sq: [(1, sq * Lt, Lt), (0, sq * ls, ls)])
+                # cross-modal blocks: cached template rows of BOTH modalities (RGB first, as in _attn_tiles("cross")),
+                # then the own search rows
+                return self._seq_tiles(("scache_x", ls), nseq, ls,
+                                       lambda sq: [(1, (sq % Bh) * Lt, Lt), (1, (Bh + sq % Bh) * Lt, Lt), (0, sq * ls, ls)])
+
+            ls, gidx, ce_i = Ls, None, 0
+            if self.ce_loc:
+                gidx = self._ws.get(("gidx0", nseq, Ls))
+                if gidx is None:
+                    gidx = torch.arange(Ls, device=self.dev, dtype=torch.float32).repeat(nseq, 1).contiguous()
+                    self._ws[("gidx0", nseq, Ls)] = gidx
+                self.aux.update(ce_scores=[], ce_keep=[], ce_removed=[])
             for i, blk in enumerate(bb["blocks"]):
-                self._block(blk, x, nseq, Ls, 0, (nseq * Ls // 2) if per_ln else 0, False, tag, tiles=tiles,
-                            qkv1=cache[i])
-            feats.append(ops.copy_rows(x, Ls, 0, Ls, nseq, self._buf(tag, "search_rows", (nseq * Ls, self.dim), self.act)))
+                ce_keep = None
+                if i in self.ce_loc:
+                    ce_keep = self.ce_keep[ce_i] if self.ce_keep[ce_i] < 1 else None
+                    ce_i += 1
+                x, _, ls, gidx = self._block(blk, x, nseq, ls, ls, (nseq * ls // 2) if per_ln else 0, cross, tag, ce_keep,
+                                             gidx, tiles=tiles_for(ls), qkv1=cache[i], first=(i == 0),
+                                             last=(i == self.depth - 1))
+            rows = self._buf(tag, "search_rows", (nseq * Ls, self.dim), self.act)
+            if ls != Ls:
+                ops.ce_recover(x, nseq, ls, 0, gidx, ls, Ls, rows)
+            else:
+                ops.copy_rows(x, Ls, 0, Ls, nseq, rows)
+            feats.append(rows)
         if not self.rgbt:
             boxes, maps = self._run_head(feats[0], B, want_maps)
             return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feats[0])
@@ -714,7 +865,7 @@ class ForwardEngine:
             sv, si = feats[0][: B * Ls], feats[0][B * Ls:]
         fused = self._run_fusion(sv, si, B)
         boxes, maps = self._run_head(fused, B, want_maps)
-        return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=fused, search_rows=(sv, si))
+        return dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=fused, search_rows=(sv, si), **self.aux)
 
     def forward_head_only(self, search_feat):
         """Corner head on an NCHW feature map (forward_box_head, mixformer.py:325-338)."""

@@ -150,7 +150,8 @@ class OnlineEngine(ForwardEngine):
         self.qkv_mem = [self._buf(tag, f"qkv_mem{i}", (Tm, 3 * self.dim), self.act) for i in range(self.depth)]
         tiles = self._full_tiles(Tm, [(0, 0, Tm)], "set_online")
         for i, blk in enumerate(bb["blocks"]):
-            self._block(blk, x, 1, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=self.qkv_mem[i])
+            self._block(blk, x, 1, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=self.qkv_mem[i], first=(i == 0),
+                        last=(i == self.depth - 1))
         self.templ_rows = ops.copy_rows(x, Tm, 0, T, 1, self._buf(tag, "templ_rows", (T, self.dim), self.act))
         self.mem_rows = Tm
 
@@ -170,7 +171,8 @@ class OnlineEngine(ForwardEngine):
         ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_s"], out=x)
         tiles = self._full_tiles(Ls, [(1, 0, Tm), (0, 0, Ls)], "forward_test")
         for i, blk in enumerate(bb["blocks"]):
-            self._block(blk, x, 1, Ls, 0, 0, False, tag, tiles=tiles, qkv1=self.qkv_mem[i])
+            self._block(blk, x, 1, Ls, 0, 0, False, tag, tiles=tiles, qkv1=self.qkv_mem[i], first=(i == 0),
+                        last=(i == self.depth - 1))
         feat = ops.copy_rows(x, Ls, 0, Ls, 1, self._buf(tag, "search_rows", (Ls, self.dim), self.act))
         boxes, maps = self._run_head(feat, 1, want_maps)
         res = dict(pred_boxes=boxes.view(1, 1, 4), score_maps=maps, feat_rows=feat)
@@ -208,7 +210,7 @@ class OnlineEngine(ForwardEngine):
         mem = [self._buf(tag, f"qkv_mem{i}", (B * Tm, 3 * self.dim), self.act) for i in range(self.depth)]
         tiles = self._seq_tiles(f"set_online_b{Tm}", B, Tm, lambda sq: [(0, sq * Tm, Tm)])
         for i, blk in enumerate(bb["blocks"]):
-            self._block(blk, x, B, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=mem[i])
+            self._block(blk, x, B, Tm, 0, 0, False, tag, tiles=tiles, qkv_out=mem[i], first=(i == 0), last=(i == self.depth - 1))
         templ = ops.copy_rows(x, Tm, 0, T, B, self._buf(tag, "templ_rows", (B * T, self.dim), self.act))
         self._batch_cache = dict(B=B, Tm=Tm, mem=mem, templ=templ)
 
@@ -229,7 +231,8 @@ class OnlineEngine(ForwardEngine):
         ops.gemm(patches, bb["pe_w"], bb["pe_b"], ops.ACT_NONE, None, self._ws["pos_s"], out=x)
         tiles = self._seq_tiles(f"forward_test_b{Tm}", B, Ls, lambda sq: [(1, sq * Tm, Tm), (0, sq * Ls, Ls)])
         for i, blk in enumerate(bb["blocks"]):
-            self._block(blk, x, B, Ls, 0, 0, False, tag, tiles=tiles, qkv1=c["mem"][i])
+            self._block(blk, x, B, Ls, 0, 0, False, tag, tiles=tiles, qkv1=c["mem"][i], first=(i == 0),
+                        last=(i == self.depth - 1))
         feat = ops.copy_rows(x, Ls, 0, Ls, B, self._buf(tag, "search_rows", (B * Ls, self.dim), self.act))
         boxes, maps = self._run_head(feat, B, want_maps)
         res = dict(pred_boxes=boxes.view(B, 1, 4), score_maps=maps, feat_rows=feat)

@@ -67,12 +67,24 @@ def _load(frame, reader, n_mod):
     return [f if isinstance(f, np.ndarray) else reader(f) for f in frame]
 
 
+def results_exist(results_dir, seq):
+    """running.py:157-165 (`_results_exist`, single-object sequences): the box file of the sequence is already there."""
+    return results_dir is not None and os.path.exists(os.path.join(results_dir, seq.dataset, seq.name + ".txt"))
+
+
 def run_sequences(network, params, sequences, results_dir=None, batch=64, update_intervals=(), n_mod=2,
-                  reader=read_image_rgb, rank=0, world_size=1, capacity_hw=None, tracker_factory=None):
+                  reader=read_image_rgb, rank=0, world_size=1, capacity_hw=None, tracker_factory=None,
+                  skip_existing=True, prefetch_workers=8):
     """Track every sequence owned by `rank`; returns {name: [T, 4] float64 boxes} and writes the reference's result
-    files when results_dir is given.  `sequences`: SequenceSpec list (or reference Sequence objects)."""
+    files when results_dir is given.  `sequences`: SequenceSpec list (or reference Sequence objects).
+    skip_existing: resume like the reference (running.py:157-171): a sequence whose result file exists is not tracked
+    again (and is absent from the returned dict).  prefetch_workers: frames of the NEXT step are decoded by a thread pool
+    while the GPU runs the current one (the reference reads every frame synchronously inside its per-frame loop,
+    tracker_rgbt.py:144-179; `track()` here never synchronises, so decode and forward overlap); 0 = decode in the loop."""
     specs = [s if isinstance(s, SequenceSpec) else SequenceSpec.from_reference(s) for s in sequences]
     mine = [specs[i] for i in runner.shard_sequences(len(specs), world_size, rank)]
+    if skip_existing:
+        mine = [s for s in mine if not results_exist(results_dir, s)]
     out = {}
     if not mine:
         return out
@@ -96,6 +108,23 @@ def run_sequences(network, params, sequences, results_dir=None, batch=64, update
     start = [0] * B                                 # result-table row holding the slot's initial box
     times = [[init_t] for _ in range(B)]
     live = [True] * B
+    pool = None
+    if prefetch_workers and prefetch_workers > 0:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=int(prefetch_workers), thread_name_prefix="mmt-frames")
+    nxt = [None] * B                                # future of the slot's next frame (decoded ahead of the step)
+
+    def fetch(b):
+        nxt[b] = None
+        if pool is not None and pos[b] < len(slots[b].frames):
+            nxt[b] = pool.submit(_load, slots[b].frames[pos[b]], reader, n_mod)
+
+    def take(b):
+        f, nxt[b] = nxt[b], None
+        return f.result() if f is not None else _load(slots[b].frames[pos[b]], reader, n_mod)
+
+    for b in range(B):
+        fetch(b)
 
     def finish(b):
         s = slots[b]
@@ -115,6 +144,7 @@ def run_sequences(network, params, sequences, results_dir=None, batch=64, update
                     t0 = time.perf_counter()
                     trk.reset_slot(b, _load(slots[b].frames[0], reader, n_mod), slots[b].init_bbox)
                     pos[b], start[b], times[b] = 1, trk.frame_id, [time.perf_counter() - t0]
+                    fetch(b)
                 else:
                     live[b] = False
         # single-frame sequences end right after initialisation
@@ -123,11 +153,16 @@ def run_sequences(network, params, sequences, results_dir=None, batch=64, update
         if any(live[b] and pos[b] >= len(slots[b].frames) for b in range(B)):
             continue
         t0 = time.perf_counter()
-        frames = [_load(slots[b].frames[pos[b]], reader, n_mod) if live[b] else None for b in range(B)]
+        frames = [take(b) if live[b] else None for b in range(B)]
         trk.track(frames, active=None if all(live) else live)
-        dt = (time.perf_counter() - t0) / sum(live)
         for b in range(B):
             if live[b]:
                 pos[b] += 1
+                fetch(b)                            # decode the slot's next frame while the GPU runs this step
+        dt = (time.perf_counter() - t0) / sum(live)
+        for b in range(B):
+            if live[b]:
                 times[b].append(dt)
+    if pool is not None:
+        pool.shutdown(wait=True)
     return out

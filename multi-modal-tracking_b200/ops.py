@@ -57,8 +57,8 @@ def _pair_min_tiles():
     global _PAIR_MIN
     if _PAIR_MIN is None:
         import os
-        if os.environ.get("MMT_GEMM_PAIR", "1") == "0":
-            _PAIR_MIN = 1 << 60
+        if os.environ.get("MMT_B200_DEV_LIB") == "1" and os.environ.get("MMT_GEMM_PAIR", "1") == "0":
+            _PAIR_MIN = 1 << 60          # developer build with the CTA-pair kernel switched off (A/B)
         else:
             _PAIR_MIN = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2
     return _PAIR_MIN
@@ -91,17 +91,42 @@ def _need_cuda(*ts):
             raise NotImplementedError("mmt_b200 ops are CUDA-only (no CPU fallback)")
 
 
-_gemm_bf16 = _lib.fn("mmt_gemm_bf16")
+_gemm_bf16 = _lib.fn("mmt_gemm_bf16_ex")
 _gemm_f32 = _lib.fn("mmt_gemm_f32")
+_rowstats_cast = _lib.fn("mmt_rowstats_cast")
 
 
-def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_dtype=None, max_ctas=0):
+def _check_ln_sums(t, M):
+    """Statistics tensors of the folded LayerNorm are slot-major [slots, rows, 2] fp32 (row slices allowed)."""
+    assert t.dtype == torch.float32 and t.dim() == 3 and t.shape[1] == M and t.shape[2] == 2
+    assert t.stride(2) == 1 and t.stride(1) == 2 and t.stride(0) % 2 == 0 and t.stride(0) >= 2 * M
+    return t.shape[0], t.stride(0) // 2
+
+
+def rowstats_cast(x, xb, stats):
+    """xb = bf16(x), stats[0] = (sum, sum of squares) of every fp32 row, other slots zero (mmt_rowstats_cast): the
+    stand-alone producer of the folded LayerNorm.  stats: [slots, rows, 2]."""
+    _need_cuda(x, xb, stats)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    assert xb.dtype == torch.bfloat16 and xb.shape == x.shape and xb.stride(1) == 1
+    slots, stride = _check_ln_sums(stats, x.shape[0])
+    _ev = _begin()
+    _lib.check(_rowstats_cast(_ptr(x), c_int(x.shape[0]), c_int(x.shape[1]), _ptr(xb), c_int(xb.stride(0)), _ptr(stats),
+                              c_int(slots), c_int(stride), _stream()), "mmt_rowstats_cast")
+    _count(1, "rowstats_cast", _ev)
+
+
+def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_dtype=None, max_ctas=0,
+         ln_stats=None, ln_eps=0.0, colsum=None, xb_out=None, stats_out=None):
     """out = act(a @ w.T + bias) + rowadd[row % period] + resid.
 
     a: [M, K] (may be a row-strided view), w: [N, K]; both bf16 (tcgen05 kernel) or both fp32 (parity kernel).
     bias [N] / rowadd [period, N] / resid [M, N] are fp32.  `out` may be a column-slice view.
+    Folded LayerNorm (bf16 only, mmt_gemm_bf16_ex): ln_stats [slots, M, 2] + colsum [N] = `a` holds raw residual rows,
+    w / bias carry gamma / beta, the epilogue finishes the normalisation; xb_out [M, N] bf16 + stats_out [N/128, M, 2] =
+    also leave the bf16 copy and the partial sums of the fp32 output rows for the next consumer.
     """
-    _need_cuda(a, w, bias, resid, rowadd, out)
+    _need_cuda(a, w, bias, resid, rowadd, out, ln_stats, colsum, xb_out, stats_out)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -124,17 +149,27 @@ def gemm(a, w, bias=None, act=ACT_NONE, resid=None, rowadd=None, out=None, out_d
     if is_bf16:
         prof = PROFILER
         ev = prof.begin() if prof is not None else None
+        slots = ln_stride = out_stride = 0
+        if ln_stats is not None:
+            assert colsum is not None and colsum.dtype == torch.float32 and colsum.numel() == N
+            slots, ln_stride = _check_ln_sums(ln_stats, M)
+        if xb_out is not None:
+            assert stats_out is not None and xb_out.dtype == torch.bfloat16 and xb_out.shape == (M, N)
+            n_out, out_stride = _check_ln_sums(stats_out, M)
+            assert n_out == N // 128
         st = _gemm_bf16(_ptr(a), c_int(a.stride(0)), _ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
                         _ptr(bias), c_int(act), _ptr(resid), c_int(ldr), _ptr(rowadd), c_int(period), _ptr(out),
                         c_int(out.stride(0)), c_int(1 if out.dtype == torch.float32 else 0), c_int(max_ctas),
-                        _stream())
-        _lib.check(st, "mmt_gemm_bf16")
+                        _ptr(ln_stats), c_int(slots), c_int(ln_stride), c_float(ln_eps), _ptr(colsum), _ptr(xb_out),
+                        c_int(xb_out.stride(0) if xb_out is not None else 0), _ptr(stats_out), c_int(out_stride), _stream())
+        _lib.check(st, "mmt_gemm_bf16_ex")
         if ev is not None:
             # same dispatch rule as gemm_tc.cu::dispatch_gemm: the CTA-pair kernel takes the big N % 256 == 0 GEMMs
             pair = max_ctas <= 0 and N % 256 == 0 and ((M + 255) // 256) * (N // 256) >= _pair_min_tiles()
             prof.end(ev, 2.0 * M * N * K, "gemm_bf16_pair" if pair else "gemm_bf16_single")
     else:
         assert a.dtype == torch.float32 and out.dtype == torch.float32
+        assert ln_stats is None and xb_out is None, "the folded LayerNorm exists in the bf16 tcgen05 path only"
         st = _gemm_f32(_ptr(a), c_int(a.stride(0)), _ptr(w), c_int(w.stride(0)), c_int(M), c_int(N), c_int(K),
                        _ptr(bias), c_int(act), _ptr(resid), c_int(ldr), _ptr(rowadd), c_int(period), _ptr(out),
                        c_int(out.stride(0)), _stream())
@@ -154,6 +189,7 @@ _msda = _lib.fn("mmt_msda_fwd")
 _msda_bimodal = _lib.fn("mmt_msda_bimodal_fwd")
 _mixattn = _lib.fn("mmt_mixattn_fwd")
 _ce_scores = _lib.fn("mmt_ce_scores")
+_ce_scores_split = _lib.fn("mmt_ce_scores_split")
 _ce_topk = _lib.fn("mmt_ce_topk")
 _ce_gather = _lib.fn("mmt_ce_gather_tokens")
 _ce_recover = _lib.fn("mmt_ce_recover")
@@ -280,11 +316,17 @@ def corner_decode(x4, w5, b5, a3, a4, B, S, stride_px, img_sz, xyxy, cxcywh, sco
     """x4/a3/a4: (tl, br) pairs of row views; w5: (tl, br) fp32 [C4]; b5: (tl, br) floats."""
     _need_cuda(x4[0], xyxy, cxcywh)
     C4 = w5[0].numel()
-    assert x4[0].stride(0) == x4[1].stride(0) and a3[0].stride(0) == a3[1].stride(0) and a4[0].stride(0) == a4[1].stride(0)
+    if a3 is None:          # plain corner head: no side maps
+        a3 = a4 = (None, None)
+        lda3 = lda4 = 0
+    else:
+        assert a3[0].stride(0) == a3[1].stride(0) and a4[0].stride(0) == a4[1].stride(0)
+        lda3, lda4 = a3[0].stride(0), a4[0].stride(0)
+    assert x4[0].stride(0) == x4[1].stride(0)
     _ev = _begin()
     _lib.check(_corner_decode(_ptr(x4[0]), _ptr(x4[1]), c_int(x4[0].stride(0)), c_int(C4), _ptr(w5[0]), _ptr(w5[1]),
-                              c_float(b5[0]), c_float(b5[1]), _ptr(a3[0]), _ptr(a3[1]), c_int(a3[0].stride(0)),
-                              _ptr(a4[0]), _ptr(a4[1]), c_int(a4[0].stride(0)), c_int(B), c_int(S),
+                              c_float(b5[0]), c_float(b5[1]), _ptr(a3[0]), _ptr(a3[1]), c_int(lda3),
+                              _ptr(a4[0]), _ptr(a4[1]), c_int(lda4), c_int(B), c_int(S),
                               c_float(stride_px), c_float(img_sz), _ptr(score_maps), _ptr(xyxy), _ptr(cxcywh),
                               c_int(_is_bf16(x4[0])), _stream()), "mmt_corner_decode")
     _count(2, "corner_decode", _ev)
@@ -346,12 +388,21 @@ def mixattn(qkv0, qkv1, C, heads, tiles, max_keys, out, scale):
     return out
 
 
-def ce_scores(qkv, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, scores):
-    _need_cuda(qkv, partial_ws, scores)
+def ce_scores(qkv, C, heads, B, n_tok, Lt, Ls, scale, partial_ws, scores, q_src=None, q_seq_rows=0, k_row_off=None):
+    """q_src: buffer holding the template rows (queries) when they do not live in `qkv` (cached-template path):
+    q_seq_rows rows per sequence-modality block; k_row_off: first search row inside a block of `qkv` (default Lt)."""
+    _need_cuda(qkv, partial_ws, scores, q_src)
     _ev = _begin()
-    _lib.check(_ce_scores(_ptr(qkv), c_int(qkv.stride(0)), c_int(C), c_int(heads), c_int(B), c_int(n_tok), c_int(Lt),
-                          c_int(Ls), c_float(scale), _ptr(partial_ws), _ptr(scores), c_int(_is_bf16(qkv)), _stream()),
-               "mmt_ce_scores")
+    if q_src is None:
+        _lib.check(_ce_scores(_ptr(qkv), c_int(qkv.stride(0)), c_int(C), c_int(heads), c_int(B), c_int(n_tok), c_int(Lt),
+                              c_int(Ls), c_float(scale), _ptr(partial_ws), _ptr(scores), c_int(_is_bf16(qkv)), _stream()),
+                   "mmt_ce_scores")
+    else:
+        assert q_src.dtype == qkv.dtype and q_src.stride(0) == qkv.stride(0) and q_src.stride(1) == 1
+        _lib.check(_ce_scores_split(_ptr(q_src), c_int(q_seq_rows), _ptr(qkv), c_int(n_tok),
+                                    c_int(Lt if k_row_off is None else k_row_off), c_int(qkv.stride(0)), c_int(C),
+                                    c_int(heads), c_int(B), c_int(Lt), c_int(Ls), c_float(scale), _ptr(partial_ws),
+                                    _ptr(scores), c_int(_is_bf16(qkv)), _stream()), "mmt_ce_scores_split")
     _count(2, "ce_scores", _ev)
     return scores
 

@@ -196,8 +196,42 @@ def main_extra():
                             pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy())
 
 
+def main_corner_head():
+    """The plain Corner_Predictor (HEAD_TYPE = CORNER, lib/models/mixformer_cvt/head.py:23-94) behind the MixViT-B backbone:
+    the reference supports it through build_box_head (head.py:235-258) but ships MixViT YAMLs with CORNER_UP only, so the
+    reference model is built from experiments/mixformer_vit/baseline.yaml with MODEL.HEAD_TYPE overridden."""
+    variant, ov = "mixformer_vit", {"MODEL.HEAD_TYPE": "CORNER"}
+    model, cfg = synthetic.make_model(variant, WEIGHT_SEED, overrides=ov)
+    sd = model.state_dict()
+    inputs = synthetic.make_inputs(variant, cfg, BATCH, INPUT_SEED)
+    ref_model, _ = ref_shims.build_reference_model(variant, synthetic.DEFAULT_YAML[variant], overrides=ov)
+    missing, unexpected = ref_model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    cap = {}
+    orig = ref_model.box_head.get_score_map
+
+    def hooked(x):
+        tl, br = orig(x)
+        cap["maps"] = torch.stack([tl.flatten(1), br.flatten(1)], dim=1)
+        return tl, br
+    ref_model.box_head.get_score_map = hooked
+    with torch.no_grad():
+        out, _ = ref_model(*inputs)
+    ora = O.forward(variant, sd, cfg, *inputs)
+    d_box = (out["pred_boxes"] - ora["pred_boxes"]).abs().max().item()
+    d_map = (cap["maps"] - ora["score_maps"]).abs().max().item()
+    print(f"{variant} HEAD_TYPE=CORNER: oracle vs reference boxes {d_box:.3e} maps {d_map:.3e}; boxes {out['pred_boxes'].view(-1, 4).tolist()}")
+    assert d_box <= 1e-5 and d_map <= 2e-4
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}__head_corner_b{BATCH}.npz"),
+                        pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy())
+
+
 def main(variants):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "corner_head" in variants:
+        torch.set_num_threads(8)
+        main_corner_head()
+        variants = [v for v in variants if v != "corner_head"]
     for v in [v for v in variants if v.startswith("extra:")]:
         ONLY.append(tuple(v.split(":")[1:3]))
         variants = [x for x in variants if x != v] + (["extra"] if "extra" not in variants else [])

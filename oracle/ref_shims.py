@@ -242,14 +242,22 @@ VARIANTS = {
 }
 
 
-def build_reference_model(variant: str, yaml_name: str, cpu_model: bool | None = None):
+def build_reference_model(variant: str, yaml_name: str, cpu_model: bool | None = None, overrides: dict | None = None):
     """Construct the reference nn.Module for `variant` from its shipped YAML, in eval mode, on CPU (call .cuda() on the
-    result for the eager-GPU baseline; pass cpu_model=True when it will RUN on the CPU of a GPU box)."""
+    result for the eager-GPU baseline; pass cpu_model=True when it will RUN on the CPU of a GPU box).
+    overrides: {"MODEL.HEAD_TYPE": "CORNER", ...} applied to the reference's cfg after the YAML (configurations the
+    reference supports but ships no experiment file for)."""
     import importlib
     install(cpu_model)
     cfg_mod, model_mod, fn, exp_dir = VARIANTS[variant]
     cm = importlib.import_module(cfg_mod)
     cm.update_config_from_file(os.path.join(REFERENCE_ROOT, "experiments", exp_dir, yaml_name + ".yaml"))
+    for k, v in (overrides or {}).items():
+        node = cm.cfg
+        parts = k.split(".")
+        for p_ in parts[:-1]:
+            node = getattr(node, p_)
+        setattr(node, parts[-1], v)
     builder = getattr(importlib.import_module(model_mod), fn)
     model = builder(cm.cfg, train=False)
     model.eval()

@@ -63,9 +63,9 @@ def _ce_stage_matches(keeps_mine, g, j, m, B):
 
 # Relative distance from the keep boundary inside which a bf16 run may legitimately pick the other token: the CE score of
 # a search token is the mean over 2*Lt template rows and 12 heads of softmax probabilities computed from bf16 q/k that
-# themselves come out of bf16 GEMMs; measured spread of |bf16 score - fp32 score| on B200 is <= 1.5 % of the score, the
-# bound leaves 2x margin.  fp32 mode: only float summation order differs.
-CE_TIE_REL = {"bf16": 3e-2, "fp32": 1e-6}
+# themselves come out of bf16 GEMMs; the largest gap measured on B200 (bs = 2 goldens, bs = 128 live oracle) is 4.3e-4 of the
+# boundary score, the bound leaves 10x margin.  fp32 mode: only float summation order differs.
+CE_TIE_REL = {"bf16": 5e-3, "fp32": 1e-6}
 
 
 def _forced_keep_from(res, rows, B):
@@ -323,10 +323,12 @@ def test_online_score_model_large(built_lib, ONLINE, precision):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("variant", ["mixformer_vit", "mixformer_vit_rgbt", "mixformer_vit_rgbt_shared",
-                                     "mixformer_vit_rgbt_unibackbone"])
+                                     "mixformer_vit_rgbt_unibackbone", "asymmetric_shared", "asymmetric_shared_ce"])
 def test_template_cache_is_bit_identical(built_lib, variant, precision):
     """cache_templates() + forward_search() (search tokens only, cached template q/k/v as a second key source) must
-    reproduce forward() bit for bit in the symmetric variants: idempotence of the template side."""
+    reproduce forward() bit for bit: idempotence of the template side.  Cross-modal variants: the
+    search rows read the cached template rows of BOTH modalities; candidate elimination: the scores' template queries
+    come from the cache (mmt_ce_scores_split) and the kept sets must be identical too."""
     from mmt_b200 import synthetic
     model, cfg = synthetic.make_model(variant, 0)
     model = model.cuda().set_precision(precision)
@@ -339,17 +341,13 @@ def test_template_cache_is_bit_identical(built_lib, variant, precision):
     _, cached2 = model.forward_search(s2)
     torch.cuda.synchronize()
     assert torch.equal(full, cached) and torch.equal(full2, cached2)
+    if variant == "asymmetric_shared_ce":
+        eng = model.engine()
+        k_full = [k.clone() for k in eng.forward(t, ot, s2)["ce_keep"]]
+        k_cached = [k.clone() for k in eng.forward_search(s2)["ce_keep"]]
+        assert len(k_full) == 3 and all(torch.equal(a, b) for a, b in zip(k_full, k_cached))
     with pytest.raises(RuntimeError):
         model.forward_search([x[:2] for x in s] if isinstance(s, list) else s[:2])      # batch differs from the cache
-
-
-def test_template_cache_refused_for_cross_modal(built_lib):
-    from mmt_b200 import synthetic
-    model, cfg = synthetic.make_model("asymmetric_shared_ce", 0)
-    model = model.cuda()
-    t, ot, s = synthetic.make_inputs("asymmetric_shared_ce", cfg, 1, 5, device="cuda")
-    with pytest.raises(NotImplementedError):
-        model.cache_templates(t, ot)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -381,6 +379,31 @@ def test_other_fusion_classes(built_lib, variant, yaml_name, precision):
     elif variant == "asymmetric_shared_ce":       # bf16 may flip near-tied tokens across the keep boundary
         _check_ce_under_forced_keep(res, cfg, sharpen=True, precision="bf16", tol_box_px=2.0,
                                     tol_map=2e-2 * float(np.abs(g["score_maps"]).max()), yaml_name=yaml_name)
+    else:
+        # sharpened stress set (head gain x24): 2 px at the 288-px search crop, i.e. 6.9e-3 of the crop side - the bf16 error
+        # lives in normalised coordinates, so the 384-px crops of the -L models get the same normalised bound (2.67 px);
+        # profiles/r2_bf16_error_table.md has every variant with the LayerNorm fold on and off
+        assert d_box <= 2.0 * cfg.DATA.SEARCH.SIZE / 288.0 and d_map <= 2e-2 * np.abs(g["score_maps"]).max()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_plain_corner_head(built_lib, precision):
+    """HEAD_TYPE = CORNER (Corner_Predictor, lib/models/mixformer_cvt/head.py:23-94: conv tower at stride 16, 18 x 18 corner
+    maps) behind the MixViT-B backbone, against the reference's outputs (oracle/gen_golden.py main_corner_head)."""
+    from mmt_b200 import synthetic
+    variant = "mixformer_vit"
+    model, cfg = synthetic.make_model(variant, 0, overrides={"MODEL.HEAD_TYPE": "CORNER"})
+    model = model.cuda().set_precision(precision)
+    inputs = synthetic.make_inputs(variant, cfg, 2, 1, device="cuda")
+    res = model.engine().forward(*inputs)
+    torch.cuda.synchronize()
+    g = np.load(os.path.join(GOLDEN, f"{variant}__head_corner_b2.npz"))
+    assert res["score_maps"].shape == (2, 2, 18 * 18)
+    d_box = np.abs(res["pred_boxes"].cpu().numpy() - g["pred_boxes"]).max() * cfg.DATA.SEARCH.SIZE
+    d_map = np.abs(res["score_maps"].cpu().numpy() - g["score_maps"]).max()
+    print(f"{variant} HEAD_TYPE=CORNER {precision}: boxes {d_box:.3e} px  maps {d_map:.3e}")
+    if precision == "fp32":
+        assert d_box <= 1e-4 * cfg.DATA.SEARCH.SIZE and d_map <= 2e-4
     else:
         assert d_box <= 2.0 and d_map <= 2e-2 * np.abs(g["score_maps"]).max()
 

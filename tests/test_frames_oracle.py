@@ -3,6 +3,8 @@
     Preprocessor_Multimodal, MixFormer.track + clip_box) - tests/golden/frames_rgbt.npz,
   * OpenCV itself (the reference's third-party resize / colour-map implementation) where cv2 is importable,
 and the host logic of mmt_b200/frames.py that needs no GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -223,6 +225,41 @@ def test_run_sequences_slot_scheduler(built_lib, tmp_path):
     # sharding: rank 1 of 2 owns s1 and s3 only
     out1 = evaluation.run_sequences(None, None, seqs, batch=2, rank=1, world_size=2, tracker_factory=_RecordingTracker)
     assert sorted(out1) == ["s1", "s3"]
+
+
+def test_run_sequences_resume_and_prefetch(built_lib, tmp_path):
+    """skip-if-results-exist (running.py:157-171) and the decode-ahead thread pool: a second run over the same results
+    directory tracks nothing; deleting one result re-tracks exactly that sequence; prefetch on / off give the same rows
+    and read every frame exactly once, through the reader."""
+    from mmt_b200 import evaluation
+    import threading
+    reads, lock = [], threading.Lock()
+
+    def reader(path):
+        tag, t = path
+        with lock:
+            reads.append(path)
+        f = np.zeros((6, 8, 3), dtype=np.uint8)
+        f[0, 0, 0], f[0, 0, 1] = tag, t
+        return f
+
+    lengths = [3, 2, 4]
+    seqs = [evaluation.SequenceSpec(f"s{i}", "syn", [[(i + 1, t), (i + 1, t)] for t in range(n)], [i, i, 5, 5])
+            for i, n in enumerate(lengths)]
+    run = lambda **kw: evaluation.run_sequences(None, None, seqs, batch=2, tracker_factory=_RecordingTracker,
+                                                reader=reader, capacity_hw=(6, 8), **kw)
+    a = run(prefetch_workers=4)
+    n_reads = len(reads)
+    assert n_reads == 2 * sum(lengths) and len(set(reads)) == sum(lengths)       # both modalities, every frame once
+    b = run(prefetch_workers=0)
+    assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    first = run(results_dir=str(tmp_path))
+    assert sorted(first) == ["s0", "s1", "s2"]
+    assert run(results_dir=str(tmp_path)) == {}                                   # everything is there: nothing to do
+    os.remove(tmp_path / "syn" / "s1.txt")
+    again = run(results_dir=str(tmp_path))
+    assert sorted(again) == ["s1"] and np.array_equal(again["s1"], first["s1"])
+    assert sorted(run(results_dir=str(tmp_path), skip_existing=False)) == ["s0", "s1", "s2"]
 
 
 def test_online_tracker_oracle_online_size_3_matches_reference_fixture():

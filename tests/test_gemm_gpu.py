@@ -99,3 +99,97 @@ def test_gemm_rejects_bad_args(built_lib):
         ops.gemm(a, w)
     with pytest.raises(NotImplementedError):
         ops.gemm(torch.zeros(8, 16), torch.zeros(8, 16))
+
+
+# ---------------------------------------------------------------------------- folded LayerNorm (mmt_gemm_bf16_ex)
+def _fold(W, bias, gamma, beta):
+    """Host-side fold of LayerNorm(gamma, beta) into Linear(W, bias): (W' bf16, bias', colsum) - engine._pack_backbone."""
+    Wf = (W * gamma[None, :]).to(torch.bfloat16)
+    return Wf, bias + W @ beta, Wf.float().sum(dim=1)
+
+
+@pytest.mark.parametrize("M,dim,N,act", [(904, 768, 2304, 0), (19000, 768, 3072, 1), (700, 1024, 3072, 0), (133, 768, 64, 1)])
+def test_folded_layernorm_consumer(built_lib, M, dim, N, act):
+    """Linear(LayerNorm(x)) through the folded form: A = bf16(x), statistics from mmt_rowstats_cast, normalisation in the
+    GEMM epilogue - against torch fp32 LayerNorm + Linear (+ GELU) of the same fp32 rows.  Rows carry a per-row offset of
+    up to one standard deviation (the |mean|/std range the residual stream shows)."""
+    from mmt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, dim, device="cuda", generator=g) * 1.3 + torch.randn(M, 1, device="cuda", generator=g)
+    W = torch.randn(N, dim, device="cuda", generator=g) * dim ** -0.5
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = 1.0 + 0.1 * torch.randn(dim, device="cuda", generator=g)
+    beta = 0.05 * torch.randn(dim, device="cuda", generator=g)
+    Wf, bf, cs = _fold(W, bias, gamma, beta)
+    xb = torch.empty(M, dim, device="cuda", dtype=torch.bfloat16)
+    sums = torch.empty(dim // 128, M, 2, device="cuda")          # slot-major [slots, rows, 2]
+    ops.rowstats_cast(x, xb, sums)
+    out = ops.gemm(xb, Wf.contiguous(), bf.contiguous(), act, ln_stats=sums, ln_eps=1e-6, colsum=cs.contiguous(),
+                   out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert (sums[:, :, 0].sum(0) - x.sum(1)).abs().max().item() <= 1e-3
+    assert ((sums[:, :, 1].sum(0) - (x * x).sum(1)).abs() / (x * x).sum(1)).max().item() <= 1e-5
+    if M > 200:      # row-range call (modality-specific norms: one consumer launch per row range of the same buffers)
+        r0 = 96
+        part = ops.gemm(xb[r0:], Wf.contiguous(), bf.contiguous(), act, ln_stats=sums[:, r0:], ln_eps=1e-6,
+                        colsum=cs.contiguous(), out_dtype=torch.bfloat16)
+        assert torch.equal(part, out[r0:])
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (dim,), gamma, beta, 1e-6), W, bias)
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    err = (out.float() - ref).abs().max().item()
+    # bf16 rounding of x (2^-9 of |x| <= ~5 sigma), of W' and of the output: the same budget as bf16(LN(x)) @ bf16(W)
+    assert err <= 3e-2 * max(1.0, ref.abs().max().item()), err
+    # and the unfused bf16 pipeline (LayerNorm kernel -> bf16 -> plain GEMM) is no closer to fp32 than the folded one x 2
+    h = torch.empty(M, dim, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm(x, gamma.contiguous(), beta.contiguous(), None, None, 0, 1e-6, out_bf16=h)
+    unf = ops.gemm(h, W.to(torch.bfloat16).contiguous(), bias.contiguous(), act, out_dtype=torch.bfloat16)
+    e_unf = (unf.float() - ref).abs().mean().item()
+    e_fold = (out.float() - ref).abs().mean().item()
+    print(f"folded LN consumer M={M} N={N}: mean abs err folded {e_fold:.3e}  unfused {e_unf:.3e}  max folded {err:.3e}")
+    assert e_fold <= 2.0 * e_unf + 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(19000, 768, 768), (18945, 768, 3072), (904, 768, 768), (6500, 1024, 1024), (300, 256, 64)])
+def test_folded_layernorm_producer(built_lib, M, N, K):
+    """Residual GEMM that also leaves the bf16 copy and the per-row partial sums of its fp32 output (fused epilogue of
+    the CTA-pair kernel for the big shapes, mmt_rowstats_cast behind the other kernels): the fp32 output is bit-identical
+    to the plain call, xb is its bf16 rounding, the slot sums add up to the row sums."""
+    from mmt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    plain = x0.clone()
+    ops.gemm(a, w, bias, 0, plain, None, out=plain)
+    out = x0.clone()
+    xb = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    sums = torch.full((N // 128, M, 2), float("nan"), device="cuda")
+    ops.gemm(a, w, bias, 0, out, None, out=out, xb_out=xb, stats_out=sums)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    assert torch.equal(xb, out.to(torch.bfloat16))
+    assert torch.isfinite(sums).all()
+    s1, s2 = sums[:, :, 0].sum(0), sums[:, :, 1].sum(0)
+    assert (s1 - out.sum(1)).abs().max().item() <= 2e-3
+    assert ((s2 - (out * out).sum(1)).abs() / (out * out).sum(1)).max().item() <= 1e-5
+    # the stand-alone producer accumulates every slot in the fused epilogue's order: bit-identical partial sums
+    xb2 = torch.empty_like(xb)
+    sums2 = torch.full_like(sums, float("nan"))
+    ops.rowstats_cast(out, xb2, sums2)
+    torch.cuda.synchronize()
+    assert torch.equal(xb2, xb) and torch.equal(sums2, sums)
+
+
+def test_folded_layernorm_argument_checks(built_lib):
+    from mmt_b200 import ops
+    a = torch.zeros(64, 768, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(256, 768, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(256, device="cuda")
+    sums = torch.zeros(6, 64, 2, device="cuda")
+    with pytest.raises(RuntimeError):        # fp32 output with the consumer-side fold
+        ops.gemm(a, w, b, 0, ln_stats=sums, ln_eps=1e-6, colsum=b, out_dtype=torch.float32)
+    with pytest.raises(AssertionError):      # the fp32 parity kernel has no folded form
+        ops.gemm(a.float(), w.float(), b, 0, ln_stats=sums, ln_eps=1e-6, colsum=b)

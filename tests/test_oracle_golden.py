@@ -147,3 +147,16 @@ def test_oracle_matches_reference_vectors_sum_fusion_classes(yaml_name):
     g = np.load(os.path.join(GOLDEN, f"{variant}__{yaml_name}_b2.npz"))
     assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
     assert np.abs(out["score_maps"].numpy() - g["score_maps"]).max() <= 2e-4
+
+
+def test_oracle_matches_reference_vectors_plain_corner_head():
+    """HEAD_TYPE = CORNER (Corner_Predictor head.py:23-94): oracle against the reference's outputs."""
+    import mmt_b200  # noqa: F401
+    from mmt_b200 import synthetic
+    from oracle import mixformer_oracle as O
+    model, cfg = synthetic.make_model("mixformer_vit", 0, overrides={"MODEL.HEAD_TYPE": "CORNER"})
+    inputs = synthetic.make_inputs("mixformer_vit", cfg, 2, 1)
+    out = O.forward("mixformer_vit", model.state_dict(), cfg, *inputs)
+    g = np.load(os.path.join(GOLDEN, "mixformer_vit__head_corner_b2.npz"))
+    assert np.abs(out["pred_boxes"].numpy() - g["pred_boxes"]).max() <= 1e-5
+    assert np.abs(out["score_maps"].numpy() - g["score_maps"]).max() <= 2e-4

@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU job B: folded LayerNorm - unit + forward parity, then A/B of the bench step
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r2b_build.log 2>&1
+timeout 600 python -m pytest tests/test_gemm_gpu.py -x -q -s -k "folded" > gpurun_out/r2b_pytest_gemm.log 2>&1; echo "pytest gemm rc=$?"
+tail -8 gpurun_out/r2b_pytest_gemm.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2b_pytest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r2b_pytest.log
+for fold in 0 1 0 1; do
+  MMT_LN_FOLD=$fold timeout 600 python bench.py --steps 30 --warmup 5 --no-eager --no-variants --no-frame-path --cpu-budget 0 --breakdown \
+     > gpurun_out/r2b_bench_fold${fold}.json 2> gpurun_out/r2b_bench_fold${fold}.err; echo "bench fold=$fold rc=$?"
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/r2b_bench_fold${fold}.json"))
+print("fold=${fold}", round(d["value"],1), "frames/s", round(d["ms_per_step"],3), "ms/step e2e", round(d["e2e"]["value"],1), "bs1 p50", round(d["latency_bs1"]["device_p50_ms"],3), "roof", round(d["roofline"]["achieved"],1), round(d["roofline"]["share_of_step"],3), "launches", d["gpu_launches"], d["clocks"])
+PY
+done
+head -30 gpurun_out/r2b_bench_fold1.err

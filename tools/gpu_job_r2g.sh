@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r2g_build.log 2>&1
+timeout 300 python tools/bench_gemm_ln.py 28928 > gpurun_out/r2g_gemm_ln.txt 2>&1; cat gpurun_out/r2g_gemm_ln.txt | grep -v "^  \|Traceback\|File"
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2g_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2g_pytest.log
+for fold in 0 1 0 1; do
+  MMT_LN_FOLD=$fold timeout 600 python bench.py --steps 30 --warmup 5 --no-eager --no-variants --no-frame-path --cpu-budget 0 \
+     > gpurun_out/r2g_bench_fold${fold}.json 2> gpurun_out/r2g_bench_fold${fold}.err; echo "bench fold=$fold rc=$?"
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/r2g_bench_fold${fold}.json"))
+print("fold=${fold}", round(d["value"],1), "frames/s", round(d["ms_per_step"],3), "ms/step e2e", round(d["e2e"]["value"],1), "bs1 p50", round(d["latency_bs1"]["device_p50_ms"],3), "roof", round(d["roofline"]["achieved"],1), round(d["roofline"]["share_of_step"],3), "launches", d["gpu_launches"], d["clocks"])
+PY
+done

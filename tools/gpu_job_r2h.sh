@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r2h_build.log 2>&1
+for dbg in 0 1024 0 1024; do
+  echo "== dev lib MMT_GEMM_DBG=$dbg (1024 = residual L2 prefetch off)" >> gpurun_out/r2h_gemm_ln.txt
+  MMT_B200_DEV_LIB=1 MMT_GEMM_DBG=$dbg timeout 300 python tools/bench_gemm_ln.py 28928 2>&1 | grep -E "proj|fc2" >> gpurun_out/r2h_gemm_ln.txt
+done
+cat gpurun_out/r2h_gemm_ln.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2h_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2h_pytest.log
+for fold in 0 1 0 1; do
+  MMT_LN_FOLD=$fold timeout 600 python bench.py --steps 30 --warmup 5 --no-eager --no-variants --no-frame-path --cpu-budget 0 \
+     > gpurun_out/r2h_bench_fold${fold}.json 2> gpurun_out/r2h_bench_fold${fold}.err; echo "bench fold=$fold rc=$?"
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/r2h_bench_fold${fold}.json"))
+print("fold=${fold}", round(d["value"],1), "frames/s", round(d["ms_per_step"],3), "ms/step e2e", round(d["e2e"]["value"],1), "bs1 p50", round(d["latency_bs1"]["device_p50_ms"],3), "roof", round(d["roofline"]["achieved"],1), round(d["roofline"]["share_of_step"],3), "launches", d["gpu_launches"], d["clocks"])
+PY
+done
