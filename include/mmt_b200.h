@@ -33,6 +33,12 @@ extern "C" {
 /* Version / capability probe (host only). Returns the ABI version; *sm gets the compiled SM (100). */
 int mmt_abi_version(int* sm);
 
+/* Programmatic dependent launch (host only; returns the previous setting).  The GEMM, attention and LayerNorm-statistics
+ * kernels run their prologue (barrier initialisation, tensor-memory allocation, descriptor prefetch) before a
+ * griddepcontrol.wait and are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that prologue overlaps
+ * the tail of the previous kernel of the stream; results are unaffected.  enable = 0 launches them plainly (A/B). */
+int mmt_config_pdl(int enable);
+
 /*
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) + rowadd[row % period][N] + resid[M,N]
  * A, W bf16 row-major (K contiguous, lda/ldw in elements, multiples of 8, 16-byte aligned base);

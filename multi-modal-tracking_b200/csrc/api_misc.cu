@@ -6,3 +6,11 @@ extern "C" int mmt_abi_version(int* sm) {
   if (sm) *sm = 100;
   return 1;
 }
+
+namespace mmt { int g_pdl_enabled = 1; }
+
+extern "C" int mmt_config_pdl(int enable) {
+  const int prev = mmt::g_pdl_enabled;
+  mmt::g_pdl_enabled = enable ? 1 : 0;
+  return prev;
+}

@@ -5,8 +5,8 @@
 //   out[q, h*64:(h+1)*64] = softmax_k( q . k * scale ) v     over the key rows listed for the query tile
 // (the template/search asymmetry is WHICH key rows a query tile lists - there is no mask tensor).
 //
-// One CTA = one query tile (<= 128 rows) of one head; 2 CTAs are resident per SM (51 KB smem, 256 TMEM columns)
-// so that the softmax of one overlaps the loads / MMAs / epilogue of the other.  Keys are walked in super-blocks
+// A work item = one query tile (<= 128 rows) of one head; at most 2 persistent CTAs are resident per SM (70 KB smem, 256
+// TMEM columns each) so that the softmax of one overlaps the loads / MMAs / epilogue of the other.  Keys are walked in super-blocks
 // of 128 (two 64-row TMA boxes); per-block fixed costs (barrier round trips, TMEM load latency, proxy fence)
 // dominate this small problem, so blocks are as large as TMEM allows with two CTAs per SM.
 //   warp 0     TMA producer : Q tile (2 x [64 x 64] boxes) and a ring of 2 x 2 K / V boxes, straight out of the
@@ -46,7 +46,6 @@ constexpr int ATC_STAGES = 4;
 constexpr int ATC_BLK_BYTES = ATC_KB * ATC_HD * 2;  // 8 KB
 constexpr int ATC_Q_BYTES = 128 * ATC_HD * 2;       // 16 KB
 constexpr int ATC_THREADS = 320;
-constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 256 + 2048;
 constexpr uint32_t ATC_TMEM_COLS = 256;             // O: [0,64)  S: [64,192)  P: [192,256) (128 keys, bf16x2 per column)
 
 // kind::f16 instruction descriptor with B taken MN-major (bit 16): V blocks are [key][d] with d contiguous.
@@ -77,296 +76,11 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-// DBG: developer build of the same kernel that records clock64() at phase boundaries of the first softmax thread
-// (8 stamps per CTA) into `dbg`; the production instantiation (DBG = false) carries none of it.
-template <bool DBG>
-__global__ void __launch_bounds__(ATC_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int C,
-               const AttnTileTC* __restrict__ tiles, bf16* __restrict__ out, int ldo, float scale_log2e,
-               long long* __restrict__ dbg) {
-  auto stamp = [&](int slot) {
-    if (DBG && threadIdx.x == 64)
-      dbg[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = clock64();
-  };
-  stamp(0);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = smem_base;
-  const uint32_t ring_smem = q_smem + ATC_Q_BYTES;
-  const uint32_t bar_base = ring_smem + ATC_STAGES * ATC_BLK_BYTES;
-  auto kv_full = [&](int s) { return bar_base + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (ATC_STAGES + s); };
-  const uint32_t q_full = bar_base + 8u * (2 * ATC_STAGES);
-  const uint32_t s_full = bar_base + 8u * (2 * ATC_STAGES + 1);
-  const uint32_t s_empty = bar_base + 8u * (2 * ATC_STAGES + 3);
-  const uint32_t p_full = bar_base + 8u * (2 * ATC_STAGES + 5);
-  const uint32_t p_empty = bar_base + 8u * (2 * ATC_STAGES + 7);
-  const uint32_t o_full = bar_base + 8u * (2 * ATC_STAGES + 9);
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * ATC_STAGES + 10);
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
-  float* smax = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [2 parities][2 halves][128]
-
-  const AttnTileTC t = tiles[blockIdx.x];
-  const int h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // key blocks of this tile: segment s contributes ceil(k_len[s] / 64) blocks
-  int nblk_seg[3];
-  int nb = 0;
-#pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    nblk_seg[s] = s < t.nseg ? (t.k_len[s] + ATC_KB - 1) / ATC_KB : 0;
-    nb += nblk_seg[s];
-  }
-  const int nsb = (nb + 1) >> 1;   // super-blocks of two 64-key boxes
-  // box `blk` of the flattened list; a missing second box of the last super-block repeats the first one with len 0
-  // (its scores are masked out), so that every super-block is exactly two ring stages
-  auto locate = [&](int blk, int& row0, int& len, int& buf) {
-    const bool ghost = blk >= nb;
-    if (ghost) blk = nb - 1;
-    int s = 0;
-    if (blk >= nblk_seg[0]) { blk -= nblk_seg[0]; s = 1; if (blk >= nblk_seg[1]) { blk -= nblk_seg[1]; s = 2; } }
-    row0 = t.k_row0[s] + blk * ATC_KB;
-    len = ghost ? 0 : min(ATC_KB, t.k_len[s] - blk * ATC_KB);
-    buf = t.k_buf[s];
-  };
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm0);
-    prefetch_tmap(&tm1);
-    for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 8);   // one arrive per softmax warp
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, ATC_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_gen;
-  stamp(1);
-  const uint32_t tmem_o = tmem_base;
-  const uint32_t tmem_p = tmem_base + 192u;
-  const uint32_t tmem_s = tmem_base + 64u;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, ATC_Q_BYTES);
-      tma_load_2d(q_smem, &tm0, q_full, h * ATC_HD, t.q_row0);
-      tma_load_2d(q_smem + ATC_Q_BYTES / 2, &tm0, q_full, h * ATC_HD, t.q_row0 + 64);
-      int stage = 0;
-      uint32_t phase = 0;
-      auto load_blk = [&](int blk, int col) {
-        int row0, len, buf;
-        locate(blk, row0, len, buf);
-        mbar_wait(kv_empty(stage), phase ^ 1u);
-        mbar_expect_tx(kv_full(stage), ATC_BLK_BYTES);
-        tma_load_2d(ring_smem + stage * ATC_BLK_BYTES, buf ? &tm1 : &tm0, kv_full(stage), col, row0);
-        if (++stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
-      };
-      for (int sb = 0; sb <= nsb; ++sb) {                                     // K_sb, then V_(sb-1)
-        if (sb < nsb) { load_blk(2 * sb, C + h * ATC_HD); load_blk(2 * sb + 1, C + h * ATC_HD); }
-        if (sb >= 1) { load_blk(2 * sb - 2, 2 * C + h * ATC_HD); load_blk(2 * sb - 1, 2 * C + h * ATC_HD); }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 2 * ATC_KB);
-      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, ATC_HD);
-      const uint64_t qdesc = make_kmajor_sw128_desc(q_smem);
-      int stage = 0;           // always even here: a super-block is the stage pair (stage, stage + 1)
-      uint32_t phase = 0;
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      auto wait_pair = [&]() {
-        mbar_wait(kv_full(stage), phase);
-        mbar_wait(kv_full(stage + 1), phase);
-        tc_fence_after();
-      };
-      auto release_pair = [&]() {
-        mma_commit(kv_empty(stage));
-        mma_commit(kv_empty(stage + 1));
-        stage += 2;
-        if (stage == ATC_STAGES) { stage = 0; phase ^= 1u; }
-      };
-      auto issue_s = [&](int g) {   // g = running S-block counter over both passes
-        mbar_wait(s_empty, (g & 1u) ^ 1u);
-        wait_pair();
-        const uint64_t kdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);   // 128 key rows
-#pragma unroll
-        for (int k = 0; k < ATC_HD / 16; ++k) mma_bf16_ss(tmem_s, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k ? 1u : 0u);
-        mma_commit(s_full);
-        release_pair();
-      };
-      for (int sb = 0; sb <= nsb; ++sb) {
-        if (sb < nsb) issue_s(sb);
-        if (sb >= 1) {
-          const int j = sb - 1;
-          mbar_wait(p_full, j & 1u);
-          wait_pair();
-          const uint64_t vdesc = make_kmajor_sw128_desc(ring_smem + stage * ATC_BLK_BYTES);
-#pragma unroll
-          for (int k = 0; k < 2 * ATC_KB / 16; ++k)   // 16 keys per MMA: P advances 8 TMEM columns, V 16 rows = 2 KB
-            mma_bf16_ts(tmem_o, tmem_p + 8u * k, vdesc + 128u * k, idesc_o, (j | k) ? 1u : 0u);
-          mma_commit(p_empty);
-          release_pair();
-        }
-      }
-      mma_commit(o_full);
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps (two threads per query row)
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;               // which 32 of a block's 64 keys this thread handles
-    const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m_row = -INFINITY;      // lazy running maximum (raw score units)
-    float mc = 0.f;               // m_row * scale_log2e
-    float l_row = 0.f;            // this thread's part of the row sum
-    auto row_max = [&](const uint32_t (&v)[32], int lim0, float m) {
-      if (lim0 >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < lim0) m = fmaxf(m, __uint_as_float(v[j]));
-      }
-      return m;
-    };
-    // in place: word i of v becomes the packed pair (p[2i], p[2i+1]) - keeps the live register set at 64
-    auto probs = [&](uint32_t (&v)[32], int lim0) {
-      uint32_t* pk = v;
-      if (lim0 >= 32) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
-          const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
-          const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
-          l_row += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-      } else if (lim0 <= 0) {      // nothing valid in this 32-key chunk (segment tail / ghost box): no exponentials
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc));
-          if (2 * i >= lim0) p0 = 0.f;
-          if (2 * i + 1 >= lim0) p1 = 0.f;
-          l_row += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-      }
-    };
-    // a warp whose 32 query rows all lie beyond the tile's q_rows computes nothing (it still takes part in the
-    // barrier protocol and writes zero probabilities)
-    const bool warp_live = quad * 32 < t.q_rows;
-    const uint32_t s_addr = tmem_s + lane_off + 64u * half;
-    const uint32_t o_addr = tmem_o + lane_off + 32u * half;
-    for (int j = 0; j < nsb; ++j) {
-      int row0, len, buf;
-      locate(2 * j + half, row0, len, buf);
-      mbar_wait(s_full, j & 1u);
-      if (j == 0) stamp(2);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(s_addr, v0);
-      tmem_ld_32x32(s_addr + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      // block maximum of the row: this thread's 64 keys, then the partner thread's through shared memory
-      float bm = row_max(v0, len, -INFINITY);
-      bm = row_max(v1, len - 32, bm);
-      float* ex = smax + (j & 1) * 256;
-      ex[half * 128 + r] = bm;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
-      bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
-      // lazy maximum: move m only when the block exceeds it by more than 2^8 (always on the first block: m = -inf)
-      float factor = 1.f;
-      bool moved = false;
-      if ((bm - m_row) * scale_log2e > 8.f) {
-        factor = ex2_approx((m_row - bm) * scale_log2e);   // 0 on the first block
-        m_row = bm;
-        mc = m_row * scale_log2e;
-        l_row *= factor;
-        moved = warp_live;
-      }
-      // this thread's 64 keys: key 2c (low half) and 2c+1 (high half) in packed word c
-      probs(v0, warp_live ? len : 0);
-      mbar_wait(p_empty, (j & 1u) ^ 1u);          // the PV MMAs of the previous super-block have completed
-      tc_fence_after();
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {
-        // rescale this thread's 32 columns of the O row by its own factor (1 for rows that did not move)
-        uint32_t o[32];
-        tmem_ld_32x32(o_addr, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        tmem_st_32x32(o_addr, o);
-      }
-      tmem_st_32x16(tmem_p + lane_off + 32u * half, v0);
-      probs(v1, warp_live ? len - 32 : 0);
-      tmem_st_32x16(tmem_p + lane_off + 32u * half + 16u, v1);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (j == 0) stamp(3);
-    }
-    // epilogue: O / L -> bf16 -> out (this thread: 32 of the 64 head channels)
-    stamp(4);
-    mbar_wait(o_full, 0);
-    stamp(5);
-    tc_fence_after();
-    uint32_t o[32];
-    tmem_ld_32x32(tmem_o + lane_off + 32u * half, o);
-    float* exl = smax + (nsb & 1) * 256;             // the parity the last block did not use
-    exl[half * 128 + r] = l_row;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l_row += exl[(half ^ 1) * 128 + r];
-    tmem_ld_wait();
-    if (r < t.q_rows) {
-      const float inv = 1.f / l_row;
-      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD + 32 * half);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-        w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-        w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-        w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-        dst[c] = w;
-      }
-    }
-  }
-
-  stamp(6);
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ATC_TMEM_COLS);
-  stamp(7);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Persistent form of the same kernel: at most two CTAs per SM walk the work items (query tile, head) with a fixed
-// stride, so the per-CTA fixed costs of the one-shot kernel above - TMEM allocation, barrier initialisation, the first
-// TMA round trip, the epilogue / teardown tail: ~8 k of the ~22 k cycles of a search tile (profiles/
-// r1_attention_phases.md) - are paid once per CTA or hidden: the producer warp runs ahead into the next item (Q is
+// Persistent schedule: at most two CTAs per SM walk the work items (query tile, head) with a fixed stride, so the per-CTA
+// fixed costs - TMEM allocation, barrier initialisation, the first TMA round trip, the epilogue / teardown tail: ~8 k of
+// the ~22 k cycles a search tile cost in the one-CTA-per-item form this kernel replaced (profiles/r1_attention_phases.md;
+// that form was deleted in round 2) - are paid once per CTA or hidden: the producer warp runs ahead into the next item (Q is
 // double-buffered, the K/V ring simply continues), the MMA warp starts the next item's S = Q K^T while the softmax
 // warps are still in the previous item's epilogue.  Barrier phases run on counters that continue across items:
 //   q_full/q_empty[2]  Q buffer n & 1 of the CTA's n-th item (q_empty: committed after the item's last S MMA)
@@ -428,8 +142,11 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
   const uint32_t tmem_o = tmem_base;
   const uint32_t tmem_p = tmem_base + 192u;
   const uint32_t tmem_s = tmem_base + 64u;
+  // the prologue above touched only this CTA's shared / tensor memory: it may overlap the previous kernel (the qkv GEMM)
+  pdl_wait();
+  pdl_launch_dependents();
 
-  // key-box bookkeeping of one tile (same as the one-shot kernel)
+  // key-box bookkeeping of one tile
   struct Plan {
     int nblk_seg[3];
     int nb, nsb;
@@ -712,64 +429,24 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
   if (rc) return rc;
   rc = make_qkv_tmap(&tm1, qkv1, rows1, 3 * C, ld);
   if (rc) return rc;
-  static int persist = -1;     // MMT_ATTN_PERSIST=0 selects the one-shot kernel (A/B measurements)
-  if (persist < 0) {
-    const char* e = getenv("MMT_ATTN_PERSIST");
-    persist = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (persist) {
-    static bool attr_p = false;
-    static int n_sm = 0;
-    if (!attr_p) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATP_SMEM);
-      if (e != cudaSuccess) return (int)e;
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      attr_p = true;
-    }
-    const int n_items = n_tiles * heads;
-    const int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
-    attn_tc_persist_kernel<<<grid, ATC_THREADS, ATP_SMEM, stream>>>(
-        tm0, tm1, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), n_items, heads, reinterpret_cast<bf16*>(out), ldo,
-        scale * 1.4426950408889634f);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? MMT_OK : (int)e;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  static bool attr_p = false;
+  static int n_sm = 0;
+  if (!attr_p) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATP_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr_p = true;
   }
-  dim3 grid(n_tiles, heads);
-  attn_tc_kernel<false><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
-      tm0, tm1, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), reinterpret_cast<bf16*>(out), ldo,
-      scale * 1.4426950408889634f, nullptr);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? MMT_OK : (int)e;
-}
-
-// Developer hook (not part of the declared ABI): same launch with phase time stamps, dbg = [heads * n_tiles * 8] int64.
-int launch_attn_tc_dbg(const void* qkv0, int rows0, int ld, int C, int heads, const int* tiles_dev, int n_tiles, void* out,
-                       int ldo, float scale, long long* dbg, cudaStream_t stream) {
-  CUtensorMap tm0;
-  int rc = make_qkv_tmap(&tm0, qkv0, rows0, 3 * C, ld);
-  if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  const int n_items = n_tiles * heads;
+  const int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
+  cudaError_t e = launch_pdl(attn_tc_persist_kernel, dim3(grid), dim3(ATC_THREADS), ATP_SMEM, stream, tm0, tm1, C,
+                             reinterpret_cast<const AttnTileTC*>(tiles_dev), n_items, heads, reinterpret_cast<bf16*>(out), ldo,
+                             scale * 1.4426950408889634f);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(n_tiles, heads);
-  attn_tc_kernel<true><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(
-      tm0, tm0, C, reinterpret_cast<const AttnTileTC*>(tiles_dev), reinterpret_cast<bf16*>(out), ldo,
-      scale * 1.4426950408889634f, dbg);
   e = cudaGetLastError();
   return e == cudaSuccess ? MMT_OK : (int)e;
 }
 
 }  // namespace mmt
-
-extern "C" int mmt_dev_attn_timing(const void* qkv0, int rows0, int ld, int C, int heads, const int* tiles_dev,
-                                   int n_tiles, void* out, int ldo, float scale, long long* dbg, void* stream) {
-  return mmt::launch_attn_tc_dbg(qkv0, rows0, ld, C, heads, tiles_dev, n_tiles, out, ldo, scale, dbg,
-                                 reinterpret_cast<cudaStream_t>(stream));
-}

@@ -23,6 +23,27 @@
 
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch (ptx_sm100.cuh): kernels that call pdl_wait() before their first dependent access are
+// launched through this helper, which sets cudaLaunchAttributeProgrammaticStreamSerialization unless switched off
+// (mmt_config_pdl(0): A/B measurements, include/mmt_b200.h).
+namespace mmt {
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+}  // namespace mmt
+
 namespace mmt {
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -187,6 +187,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // everything above touched only this CTA's shared / tensor memory: it may overlap the previous kernel of the stream
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == W_PRODUCER) {
     // ------------------------------------------------------------ TMA producer
@@ -315,18 +318,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int LPR_H = CH / 8;               // bf16 out: lanes per row (8 columns each)
     constexpr int IT_H = LPR_H;
     auto key_of = [](int r) { return (r / KEYDIV) & (VPR - 1); };
-    // folded LayerNorm, consumer side: the partial sums of this thread's row are fetched ONE TILE AHEAD (raw values parked in
-    // registers, reduced when the tile starts), so their L2 latency never sits on the epilogue's critical path
+    // folded LayerNorm, consumer side.  CTA-pair kernel: the partial sums of this thread's row are fetched ONE TILE AHEAD with
+    // cp.async into a per-warp staging area (2 KB at +6144 of the warp's epilogue region) and reduced when the tile starts, so
+    // their L2 latency never sits on the epilogue's critical path.  (Parking them in registers instead made ptxas spill them
+    // right after the loads - the spill stores then waited for the loads: 11 % of the kernel's stall samples,
+    // profiles/r2_gemm_epilogue.md.)  Single-CTA kernel (small problems): plain loads at the start of the tile.
     const bool ln_active = !ep.out_fp32 && ep.vec_ok && ep.bias != nullptr && ep.ln_stats != nullptr && !cv.enabled;
     constexpr int LN_MAX_SLOTS = 8;
-    float2 ln_raw[LN_MAX_SLOTS];
+    float2* ln_stage = reinterpret_cast<float2*>(stg4 + 384);        // [slot][lane], CTA-pair kernel only
+    auto ln_row_of = [&](int t) { return (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + (warp & 3) * 32 + lane; };
     auto ln_fetch = [&](int t) {
-      const int g = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + (warp & 3) * 32 + lane;
+      if (!PAIR) return;
+      const int g = ln_row_of(t);
       const float2* sp = reinterpret_cast<const float2*>(ep.ln_stats) + g;
-#pragma unroll
-      for (int q = 0; q < LN_MAX_SLOTS; ++q)
-        ln_raw[q] = (q < ep.ln_slots && g < M && !(dbg_flags & 64)) ? __ldg(sp + static_cast<size_t>(q) * ep.ln_stride)
-                                                                    : make_float2(0.f, 0.f);
+      for (int q = 0; q < ep.ln_slots; ++q) {
+        if (g < M) cp_async_8(smem_u32(ln_stage + q * 32 + lane), sp + static_cast<size_t>(q) * ep.ln_stride);
+        else ln_stage[q * 32 + lane] = make_float2(0.f, 0.f);
+      }
+      cp_async_commit();
     };
     if (ln_active && worker < num_tiles) ln_fetch(worker);
     // (Measured and dropped: requesting a warp's residual tiles into L2 one tile ahead with cp.async.bulk.prefetch made proj
@@ -415,12 +424,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float st_s1 = 0.f, st_s2 = 0.f;
       if (ln_in) {
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < LN_MAX_SLOTS; ++q) { s1 += ln_raw[q].x; s2 += ln_raw[q].y; }      // fixed slot order: deterministic
+        if (PAIR) {
+          cp_async_wait_all();                                 // this thread's own copies (issued one tile ago)
+          for (int q = 0; q < ep.ln_slots; ++q) {              // fixed slot order: deterministic
+            const float2 t = ln_stage[q * 32 + lane];
+            s1 += t.x; s2 += t.y;
+          }
+          if (tile + n_workers < num_tiles) ln_fetch(tile + n_workers);      // consumed at the start of the next tile
+        } else {
+          const int g = ln_row_of(tile);
+          if (g < M) {
+            const float2* sp = reinterpret_cast<const float2*>(ep.ln_stats) + g;
+            for (int q = 0; q < ep.ln_slots; ++q) {
+              const float2 t = __ldg(sp + static_cast<size_t>(q) * ep.ln_stride);
+              s1 += t.x; s2 += t.y;
+            }
+          }
+        }
         ln_mu = s1 * ep.ln_inv_k;
         ln_rs = rsqrtf(fmaxf(fmaf(-ln_mu, ln_mu, s2 * ep.ln_inv_k), 0.f) + ep.ln_eps);
         if (dbg_flags & 64) { ln_mu = 0.f; ln_rs = 1.f; }
-        if (tile + n_workers < num_tiles) ln_fetch(tile + n_workers);      // consumed at the start of the next tile
       }
 
       const int grow_w = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM + lrow0;   // first global row of this warp
@@ -835,13 +858,15 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, cons
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_enabled ? 2 : 1;
   GemmConv cv = {};
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, tmR, tmX, M, N, K, ep, cv);
   if (e != cudaSuccess) return (int)e;
@@ -866,7 +891,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmC, const voi
   const int tiles = m_tiles * cdiv(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC, tmC, M, N, K, ep, cv);
+  cudaError_t e = launch_pdl(gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA,
+                             tmB, tmC, tmC, tmC, M, N, K, ep, cv);
+  if (e != cudaSuccess) return (int)e;
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -946,7 +973,9 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
   // (never below 64 columns; only for plain GEMMs whose N the narrower tile divides).  MMT_GEMM_NARROW=0 disables (A/B).
   if (narrow_enabled() && !cv.enabled && max_ctas <= 0) {
     const int m_tiles = cdiv(M, GEMM_BM);
-    while (bn > 64 && (bn % 2) == 0 && (N % (bn / 2)) == 0 && m_tiles * cdiv(N, bn) < num_sms()) bn /= 2;
+    // ... but never past ONE wave: a narrower tile that needs a second round of CTAs doubles the launch time (fc1 at one
+    // sequence: 192 tiles of 64 columns on 148 SMs took two rounds; 96 tiles of 128 columns take one)
+    while (bn > 64 && (bn % 2) == 0 && (N % (bn / 2)) == 0 && m_tiles * cdiv(N, bn / 2) <= num_sms()) bn /= 2;
   }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);

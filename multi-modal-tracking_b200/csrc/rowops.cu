@@ -3,6 +3,7 @@
 // soft-argmax decode.  All are coalesced + vectorised; activations are "T" = bf16 (fast mode) or
 // fp32 (parity mode); statistics and reductions are always fp32.
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 #include "../../include/mmt_b200.h"
 
 namespace mmt {
@@ -89,6 +90,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, f
                                  const float* __restrict__ g0, const float* __restrict__ b0,
                                  const float* __restrict__ g1, const float* __restrict__ b1, int period,
                                  float* out_f32, bf16* out_bf16) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -152,6 +155,8 @@ template <int MAXV>  // C <= MAXV * 128
 __global__ void rowstats_cast_kernel(const float* __restrict__ x, int rows, int C, bf16* __restrict__ xb, int ld_xb,
                                      float* __restrict__ stats, int slots, int slot_stride) {
   extern __shared__ float rs_smem[];
+  ptx::pdl_wait();                  // launched with programmatic stream serialization: the producer of x has completed
+  ptx::pdl_launch_dependents();     // the consumer GEMM may start its prologue
   const int wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,8 +207,9 @@ int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, f
   const int grid = cdiv(rows, wpb);
   bf16* o = reinterpret_cast<bf16*>(xb);
   auto smem = [&](int maxv) { return static_cast<size_t>(wpb) * (maxv * 128 + maxv * 4) * sizeof(float); };
-  if (C <= 512) rowstats_cast_kernel<4><<<grid, wpb * 32, smem(4), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
-  else if (C <= 1024) rowstats_cast_kernel<8><<<grid, wpb * 32, smem(8), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
+  cudaError_t le = cudaSuccess;
+  if (C <= 512) le = launch_pdl(rowstats_cast_kernel<4>, dim3(grid), dim3(wpb * 32), smem(4), s, x, rows, C, o, ld_xb, stats, slots, slot_stride);
+  else if (C <= 1024) le = launch_pdl(rowstats_cast_kernel<8>, dim3(grid), dim3(wpb * 32), smem(8), s, x, rows, C, o, ld_xb, stats, slots, slot_stride);
   else {
     static bool attr = false;
     if (!attr) {
@@ -211,8 +217,9 @@ int launch_rowstats_cast(const float* x, int rows, int C, void* xb, int ld_xb, f
       if (e != cudaSuccess) return (int)e;
       attr = true;
     }
-    rowstats_cast_kernel<16><<<grid, wpb * 32, smem(16), s>>>(x, rows, C, o, ld_xb, stats, slots, slot_stride);
+    le = launch_pdl(rowstats_cast_kernel<16>, dim3(grid), dim3(wpb * 32), smem(16), s, x, rows, C, o, ld_xb, stats, slots, slot_stride);
   }
+  if (le != cudaSuccess) return (int)le;
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -473,13 +480,32 @@ __global__ void corner_decode_kernel(CornerArgs a, int S, int C4, float stride_p
   const T* a3 = reinterpret_cast<const T*>(a.a3[cor]);
   const T* a4 = reinterpret_cast<const T*>(a.a4[cor]);
   const float* w5 = a.w5[cor];
+  __shared__ float w5s[256];                       // conv5 weights (C4 <= 256, checked by the launcher)
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) w5s[c] = __ldg(w5 + c);
+  __syncthreads();
+  const bool vec8 = (C4 % 8) == 0 && (a.ld4x % 8) == 0 && (reinterpret_cast<uintptr_t>(x4) & 15) == 0;
   const int S2 = S / 2, S4 = S / 4;
   float lmax = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int y = i / S, x = i % S;
     const T* row = x4 + (static_cast<size_t>(b) * n + i) * a.ld4x;
     float acc = 0.f;
-    for (int c = 0; c < C4; ++c) acc = fmaf(to_f<T>(row[c]), __ldg(w5 + c), acc);
+    if (sizeof(T) == 2 && vec8) {
+      // bf16 rows, 16-byte aligned, C4 a multiple of 8: eight channels per load (the scalar loop's 2-byte loads made this
+      // kernel 51 us at one sequence - a latency chain of 480 loads per thread)
+      const uint4* r8 = reinterpret_cast<const uint4*>(row);
+      for (int c8 = 0; c8 < C4 / 8; ++c8) {
+        const uint4 q = r8[c8];
+        const uint32_t w32[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc = fmaf(__uint_as_float(w32[k] << 16), w5s[c8 * 8 + 2 * k], acc);
+          acc = fmaf(__uint_as_float(w32[k] & 0xffff0000u), w5s[c8 * 8 + 2 * k + 1], acc);
+        }
+      }
+    } else {
+      for (int c = 0; c < C4; ++c) acc = fmaf(to_f<T>(row[c]), w5s[c], acc);
+    }
     acc += a.b5[cor];
     if (a3) acc += to_f<T>(a3[(static_cast<size_t>(b) * S4 * S4 + (y / 4) * S4 + x / 4) * a.lda3]);   // pyramid head only
     if (a4) acc += to_f<T>(a4[(static_cast<size_t>(b) * S2 * S2 + (y / 2) * S2 + x / 2) * a.lda4]);
@@ -598,9 +624,11 @@ extern "C" int mmt_layernorm(const float* x, int rows, int C, float eps, const f
   const int wpb = 8;  // warps per block
   const int grid = cdiv(rows, wpb);
   bf16* ob = reinterpret_cast<bf16*>(out_bf16);
-  if (C <= 512) layernorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
-  else if (C <= 1024) layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
-  else layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
+  cudaError_t le;
+  if (C <= 512) le = launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(wpb * 32), 0, s, x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
+  else if (C <= 1024) le = launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, s, x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
+  else le = launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(wpb * 32), 0, s, x, rows, C, eps, g0, b0, g1, b1, period, out_f32, ob);
+  if (le != cudaSuccess) return (int)le;
   MMT_RETURN_LAST_ERROR();
 }
 
@@ -702,7 +730,8 @@ extern "C" int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x,
   MMT_CHECK_ARG(x4_tl && x4_br && w5_tl && w5_br && xyxy && cxcywh);
   // a3 / a4 (the pyramid head's side maps) come in pairs or not at all (plain Corner_Predictor, head.py:23-94)
   MMT_CHECK_ARG((a3_tl != nullptr) == (a3_br != nullptr) && (a4_tl != nullptr) == (a4_br != nullptr));
-  MMT_CHECK_ARG(B > 0 && S > 0 && (S % 4 == 0 || (!a3_tl && !a4_tl)) && S * S * 4 <= 96 * 1024 && C4 > 0 && img_sz > 0);
+  MMT_CHECK_ARG(B > 0 && S > 0 && (S % 4 == 0 || (!a3_tl && !a4_tl)) && S * S * 4 <= 96 * 1024 && C4 > 0 && C4 <= 256 &&
+                img_sz > 0);
   CornerArgs a;
   a.x4[0] = x4_tl; a.x4[1] = x4_br; a.a3[0] = a3_tl; a.a3[1] = a3_br; a.a4[0] = a4_tl; a.a4[1] = a4_br;
   a.w5[0] = w5_tl; a.w5[1] = w5_br; a.b5[0] = b5_tl; a.b5[1] = b5_br;
@@ -712,10 +741,10 @@ extern "C" int mmt_corner_decode(const void* x4_tl, const void* x4_br, int ld4x,
   dim3 grid(B, 2);
   if (is_bf16) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(corner_decode_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    corner_decode_kernel<bf16><<<grid, 512, smem, s>>>(a, S, C4, stride_px, 1.0f / img_sz, score_maps, xyxy);
+    corner_decode_kernel<bf16><<<grid, 1024, smem, s>>>(a, S, C4, stride_px, 1.0f / img_sz, score_maps, xyxy);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(corner_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    corner_decode_kernel<float><<<grid, 512, smem, s>>>(a, S, C4, stride_px, 1.0f / img_sz, score_maps, xyxy);
+    corner_decode_kernel<float><<<grid, 1024, smem, s>>>(a, S, C4, stride_px, 1.0f / img_sz, score_maps, xyxy);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -53,6 +53,13 @@ class LaunchProfiler:
 _PAIR_MIN = None
 
 
+def config_pdl(enable: bool) -> bool:
+    """Programmatic dependent launch of the GEMM / attention / LayerNorm-statistics kernels on or off (mmt_config_pdl);
+    returns the previous setting.  Results do not depend on it."""
+    f = _lib.fn("mmt_config_pdl")
+    return bool(f(c_int(1 if enable else 0)))
+
+
 def _pair_min_tiles():
     global _PAIR_MIN
     if _PAIR_MIN is None:

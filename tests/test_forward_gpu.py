@@ -232,6 +232,31 @@ def test_cuda_graph_replay_matches_eager(built_lib):
             assert torch.equal(eager, graphed) and torch.equal(graphed, graphed2), (variant, batch)
 
 
+def test_programmatic_dependent_launch_is_result_neutral(built_lib):
+    """mmt_config_pdl: the kernels' prologues overlapping the previous kernel's tail (griddepcontrol) change no result -
+    eager launches and graph replay, two variants (two streams / one stream with candidate elimination)."""
+    from mmt_b200 import ops, synthetic
+    prev = ops.config_pdl(True)
+    try:
+        for variant in ("mixformer_vit_rgbt", "asymmetric_shared_ce"):
+            model, cfg = synthetic.make_model(variant, 0)
+            model = model.cuda()
+            for batch in (1, 3):
+                inputs = synthetic.make_inputs(variant, cfg, batch, 7, device="cuda")
+                ops.config_pdl(False)
+                _, plain = model(*inputs)
+                ops.config_pdl(True)
+                _, pdl = model(*inputs)
+                model.enable_cuda_graph(True)
+                _, graphed = model(*inputs)
+                _, graphed2 = model(*inputs)
+                model.enable_cuda_graph(False)
+                torch.cuda.synchronize()
+                assert torch.equal(plain, pdl) and torch.equal(plain, graphed) and torch.equal(plain, graphed2), (variant, batch)
+    finally:
+        ops.config_pdl(prev)
+
+
 ONLINE = "mixformer_vit_online"
 
 

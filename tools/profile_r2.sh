@@ -16,3 +16,9 @@ N1=$(grep -o "launches per forward: [0-9]*" gpurun_out/r2p_plain1.log | grep -o 
 echo "launches per forward: bs64 $N64 bs1 $N1"
 python tools/ncu_launch_table.py gpurun_out/r2p_step64.csv > gpurun_out/r2p_step64_table.md 2>&1; tail -25 gpurun_out/r2p_step64_table.md
 python tools/ncu_launch_table.py gpurun_out/r2p_bs1.csv > gpurun_out/r2p_bs1_table.md 2>&1; tail -25 gpurun_out/r2p_bs1_table.md
+# (3) ncu --set full of the qkv GEMM with the folded-LayerNorm epilogue and of the plain one (source-level stall reasons)
+python tools/gemm_case.py qkv ln > gpurun_out/r2p_plain_qkv.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o gpurun_out/r2p_qkv_ln python tools/gemm_case.py qkv ln > gpurun_out/r2p_ncu_qkv_ln.log 2>&1
+python tools/gemm_case.py qkv plain > gpurun_out/r2p_plain_qkv2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o gpurun_out/r2p_qkv_plain python tools/gemm_case.py qkv plain > gpurun_out/r2p_ncu_qkv_plain.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -3
