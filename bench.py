@@ -706,16 +706,17 @@ def main():
             n_l, gemm_ms, gemm_flops = prof.summary("gemm_bf16")
         a_l, a_ms, a_flops = prof.summary("gemm_bf16")
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = traffic_source = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
             if tj.get("variant") == variant and tj.get("batch") == B:
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_source = tj.get("source")
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel<256, PAIR> (cta_group::2; every launch of it in the timed region)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_source, "peak_source": peaks["source"],
                 "launches": n_l, "avg_launch_us": gemm_ms * 1e3 / max(1, n_l),
                 "share_of_step": gemm_ms / prof_ms, "gflop_per_launch_avg": gemm_flops / max(1, n_l) / 1e9,
                 "measured_over": f"{args.steps} steps right after the timed region, modality chains on ONE stream "

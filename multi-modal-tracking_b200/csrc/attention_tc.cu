@@ -331,7 +331,9 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
         bm = row_max(v1, len - 32, bm);
         float* ex = smax + (g & 1u) * 256;
         ex[half * 128 + r] = bm;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
+        // only the two warps that share this TMEM lane quadrant (the two threads of a row live in warps q and q + 4) meet:
+        // four independent 64-thread barriers instead of one over all eight softmax warps
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
         float factor = 1.f;
         bool moved = false;
@@ -368,7 +370,7 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
       tmem_ld_32x32(o_addr, o);
       float* exl = smax + 512;                      // dedicated row-sum exchange buffer
       exl[half * 128 + r] = l_row;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
       l_row += exl[(half ^ 1) * 128 + r];
       tmem_ld_wait();
       tc_fence_before();
