@@ -296,6 +296,13 @@ class _Fusion(nn.Module):
 
     def __init__(self, fusion_class, channels=768, d_model=512, layers=2):
         super().__init__()
+        if fusion_class == "Attention_Fusion_512":
+            # The reference's own builders cannot construct this class either: they call
+            # globals()[cfg.MODEL.FUSION_CLASS](768, d_model=512, num_feature_levels=2, num_encoder_layers=...)
+            # (asymmetric_shared.py:418, mixformer_shared.py:474, ...) and Attention_Fusion_512.__init__
+            # (fusion_utils.py:128-150) takes no num_encoder_layers - the same TypeError, verbatim (tests/test_boundary.py
+            # pins it against the reference's builder where the reference tree is present).
+            raise TypeError("Attention_Fusion_512.__init__() got an unexpected keyword argument 'num_encoder_layers'")
         if fusion_class not in FUSION_CLASSES:
             raise KeyError(f"FUSION_CLASS {fusion_class!r} is not on the accelerated path; supported: {FUSION_CLASSES}")
         self.fusion_class, self.d_model = fusion_class, d_model

@@ -295,6 +295,7 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
           for (int i = 0; i < 16; ++i) {
             const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
             const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
+            // every fourth exponential on the FMA pipe (re-measured in round 2: all-MUFU is 1 % slower, 100.0 vs 99.1 us)
             const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
             l_row += p0 + p1;
             pk[i] = pack_bf16x2(p0, p1);

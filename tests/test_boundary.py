@@ -125,9 +125,21 @@ def test_training_and_cpu_are_refused():
     x = synthetic.make_inputs("mixformer_vit", cfg, 1)
     with pytest.raises(NotImplementedError):
         model(*x)                                   # no CPU fallback
+    # Attention_Fusion_512: the reference's builders pass num_encoder_layers to a constructor that does not take it
+    # (fusion_utils.py:128-150 vs asymmetric_shared.py:418) - the drop-in builders fail the same way, and where the reference
+    # tree is present its own builder is shown to raise the same TypeError
     cfg2 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "Attention_Fusion_512"})
-    with pytest.raises(KeyError):                   # a fusion class no shipped YAML names: refused loudly, no fallback
+    with pytest.raises(TypeError, match="num_encoder_layers") as mine:
         builders.build_mixformer_vit_rgbt(cfg2)
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        with pytest.raises(TypeError) as theirs:
+            ref_shims.build_reference_model("asymmetric_shared", "attention_lasher_newfusion_2layer",
+                                            overrides={"MODEL.FUSION_CLASS": "Attention_Fusion_512"})
+        assert str(theirs.value) == str(mine.value)
+    cfg3 = synthetic.load_variant_config("mixformer_vit_rgbt", overrides={"MODEL.FUSION_CLASS": "No_Such_Fusion"})
+    with pytest.raises(KeyError):                   # unknown class names: KeyError like the reference's globals()[...] lookup
+        builders.build_mixformer_vit_rgbt(cfg3)
 
 
 def test_attention_tile_order_is_heavy_first_and_stable(built_lib):
