@@ -119,6 +119,198 @@ struct GemmCfg {
                                         : (2 * BN <= 256) ? 256 : 512;
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Lean epilogues of the CTA-pair kernel.  The backbone's four GEMMs (qkv, fc1: bias [+ folded LayerNorm] [+ GELU] -> bf16;
+// proj, fc2: bias + fp32 residual in place [+ shadow rows and partial sums]) take these specialised loops: compile-time
+// activation / LayerNorm switches, thread == row throughout, nothing of the generic path's bookkeeping (ragged tiles,
+// strided stores, positional adds, convolution geometry).  The generic loop in the kernel body cost ~390 warp instructions
+// per 32 x 32 chunk of which ~60 were the chunk's arithmetic (ncu source page, profiles/r2_gemm_epilogue.md); the epilogue
+// warps' instruction stream is what bounds the K = 768 GEMMs.
+struct EpiCtx {
+  uint32_t tmem_base;
+  uint32_t tfull0, tempty0;      // shared addresses of tmem_full[0] / tmem_empty[0] (slot 1 = + 8)
+  uint32_t rbar0;                // this warp's two residual-tile barriers
+  uint4* stg4;                   // this warp's epilogue region (Cfg::EPI_TILE_BYTES)
+  int worker, n_workers, num_tiles, n_tiles, M, N, warp, lane, cta_rank;
+};
+
+template <int BN, int ACT, bool LN>
+__device__ __forceinline__ void epi_pair_bf16(const EpiCtx& cx, const GemmEpi& ep, const CUtensorMap* tmC) {
+  constexpr int CH = 32, MAXC = BN / CH / 2;
+  const int quad = cx.warp & 3, half = cx.warp >> 2, lane = cx.lane;
+  float* bias_s = reinterpret_cast<float*>(cx.stg4) + 32 * 16;      // +2048 B: after staging tile 0
+  float* csum_s = bias_s + MAXC * CH;
+  float2* ln_stage = reinterpret_cast<float2*>(cx.stg4 + 384);      // +6144 B: [slot][lane]
+  auto ln_fetch = [&](int t) {
+    const int g = (t / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32 + lane;
+    const float2* sp = reinterpret_cast<const float2*>(ep.ln_stats) + g;
+    for (int q = 0; q < ep.ln_slots; ++q) {
+      if (g < cx.M) cp_async_8(smem_u32(ln_stage + q * 32 + lane), sp + static_cast<size_t>(q) * ep.ln_stride);
+      else ln_stage[q * 32 + lane] = make_float2(0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  if (LN && cx.worker < cx.num_tiles) ln_fetch(cx.worker);
+  uint32_t bk = 0;
+  int local = 0;
+  for (int tile = cx.worker; tile < cx.num_tiles; tile += cx.n_workers, ++local) {
+    const int as = local & 1;
+    const uint32_t aphase = (local >> 1) & 1u;
+    const int n0 = (tile % cx.n_tiles) * BN;
+    const int r0 = (tile / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
+    __syncwarp();
+    if (lane < MAXC * (CH / 4)) {          // this warp's bias (and column-sum) slices: chunk slot k = lane / 8
+      const int nbk = n0 + (half + 2 * (lane >> 3)) * CH;
+      reinterpret_cast<float4*>(bias_s)[lane] = __ldg(reinterpret_cast<const float4*>(ep.bias + nbk) + (lane & 7));
+      if (LN) reinterpret_cast<float4*>(csum_s)[lane] = __ldg(reinterpret_cast<const float4*>(ep.colsum + nbk) + (lane & 7));
+    }
+    __syncwarp();
+    float mu = 0.f, rs = 1.f;
+    if (LN) {
+      cp_async_wait_all();
+      float s1 = 0.f, s2 = 0.f;
+      for (int q = 0; q < ep.ln_slots; ++q) {       // fixed slot order: deterministic
+        const float2 t = ln_stage[q * 32 + lane];
+        s1 += t.x; s2 += t.y;
+      }
+      mu = s1 * ep.ln_inv_k;
+      rs = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * ep.ln_inv_k), 0.f) + ep.ln_eps);
+      if (tile + cx.n_workers < cx.num_tiles) ln_fetch(tile + cx.n_workers);
+    }
+    const float nmu = -mu;
+    mbar_wait(cx.tfull0 + 8u * as, aphase);
+    tc_fence_after();
+    const uint32_t t_row = cx.tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+    for (int kc = 0; kc < MAXC; ++kc) {
+      const int c = half + 2 * kc;
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * CH, v);
+      tmem_ld_wait();
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = reinterpret_cast<const float4*>(bias_s + kc * CH)[j];      // broadcast reads
+        float x0 = __uint_as_float(v[4 * j]), x1 = __uint_as_float(v[4 * j + 1]);
+        float x2 = __uint_as_float(v[4 * j + 2]), x3 = __uint_as_float(v[4 * j + 3]);
+        if (LN) {
+          const float4 cs = reinterpret_cast<const float4*>(csum_s + kc * CH)[j];
+          x0 = fmaf(rs, fmaf(nmu, cs.x, x0), b.x); x1 = fmaf(rs, fmaf(nmu, cs.y, x1), b.y);
+          x2 = fmaf(rs, fmaf(nmu, cs.z, x2), b.z); x3 = fmaf(rs, fmaf(nmu, cs.w, x3), b.w);
+        } else {
+          x0 += b.x; x1 += b.y; x2 += b.z; x3 += b.w;
+        }
+        if (ACT == MMT_ACT_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3); }
+        else if (ACT == MMT_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+        w[2 * j] = pack_bf16x2(x0, x1);
+        w[2 * j + 1] = pack_bf16x2(x2, x3);
+      }
+      // two staging tiles per warp: only the store of TWO chunks ago must have read its tile
+      uint4* stg = cx.stg4 + 256 * (bk++ & 1u);
+      if (lane == 0) bulk_wait_read_1();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)       // 64-byte rows, 16-byte chunk j of row `lane` at j ^ ((lane >> 1) & 3): TMA SWIZZLE_64B
+        stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      fence_proxy_async_shared();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, smem_u32(stg), n0 + c * CH, r0);       // rows beyond M are clipped by the TMA
+        bulk_commit_group();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster((cx.tempty0 + 8u * as) & kPeerBitMask);     // the leader's barrier counts both CTAs
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+template <int BN, bool LNOUT>
+__device__ __forceinline__ void epi_pair_f32(const EpiCtx& cx, const GemmEpi& ep, const CUtensorMap* tmC,
+                                             const CUtensorMap* tmR, const CUtensorMap* tmX) {
+  constexpr int CH = 32, MAXC = BN / CH / 2;
+  const int quad = cx.warp & 3, half = cx.warp >> 2, lane = cx.lane;
+  uint4* xtile = cx.stg4 + 512;        // bf16 shadow tile (+8192 B)
+  uint32_t rk = 0;
+  int local = 0;
+  for (int tile = cx.worker; tile < cx.num_tiles; tile += cx.n_workers, ++local) {
+    const int as = local & 1;
+    const uint32_t aphase = (local >> 1) & 1u;
+    const int n0 = (tile % cx.n_tiles) * BN;
+    const int r0 = (tile / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
+    auto issue_resid = [&](int c, uint32_t k) {     // TMA load of the residual tile of chunk c into buffer k & 1
+      if (lane == 0) {
+        bulk_wait_read_all();                       // the store that last used this buffer has read it
+        const uint32_t bar = cx.rbar0 + 8u * (k & 1u);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(smem_u32(cx.stg4) + 4096u * (k & 1u), tmR, bar, n0 + c * CH, r0);
+      }
+    };
+    issue_resid(half, rk);
+    mbar_wait(cx.tfull0 + 8u * as, aphase);
+    tc_fence_after();
+    const uint32_t t_row = cx.tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+    float st_s1 = 0.f, st_s2 = 0.f;
+#pragma unroll 1
+    for (int kc = 0; kc < MAXC; ++kc) {
+      const int c = half + 2 * kc;
+      const int nb = n0 + c * CH;
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * CH, v);
+      const uint32_t k = rk++;
+      if (kc + 1 < MAXC) issue_resid(c + 2, k + 1);
+      uint4* tile_s = cx.stg4 + 256 * (k & 1u);
+      float4 bq[8];                                  // the chunk's 32 bias values: 8 warp-uniform (broadcast) L1 loads
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bq[j] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tmem_ld_wait();
+      mbar_wait(cx.rbar0 + 8u * (k & 1u), (k >> 1) & 1u);
+      uint32_t xbp[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int slot = lane * 8 + (j ^ (lane & 7));      // 128-byte rows, SWIZZLE_128B
+        const uint4 rw = tile_s[slot];
+        const float4 b = bq[j];
+        const float y0 = (__uint_as_float(v[4 * j]) + b.x) + __uint_as_float(rw.x);
+        const float y1 = (__uint_as_float(v[4 * j + 1]) + b.y) + __uint_as_float(rw.y);
+        const float y2 = (__uint_as_float(v[4 * j + 2]) + b.z) + __uint_as_float(rw.z);
+        const float y3 = (__uint_as_float(v[4 * j + 3]) + b.w) + __uint_as_float(rw.w);
+        tile_s[slot] = make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3));
+        if (LNOUT) {
+          st_s1 += (y0 + y1) + (y2 + y3);
+          st_s2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, st_s2))));
+          xbp[2 * j] = pack_bf16x2(y0, y1);
+          xbp[2 * j + 1] = pack_bf16x2(y2, y3);
+        }
+      }
+      if (LNOUT) {
+        if (lane == 0) bulk_wait_read_all();         // the previous chunk's shadow-tile store has read it
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          xtile[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(xbp[4 * j], xbp[4 * j + 1], xbp[4 * j + 2], xbp[4 * j + 3]);
+      }
+      fence_proxy_async_shared();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, smem_u32(tile_s), nb, r0);
+        if (LNOUT) tma_store_2d(tmX, smem_u32(xtile), nb, r0);
+        bulk_commit_group();
+      }
+    }
+    if (LNOUT && r0 + lane < cx.M) {
+      // slot = (256-column tile, epilogue half): every (slot, row) is written by exactly one thread of the grid
+      const int slot = (n0 / BN) * (BN / 128) + half;
+      reinterpret_cast<float2*>(ep.stats_out)[static_cast<size_t>(slot) * ep.stats_stride + r0 + lane] = make_float2(st_s1, st_s2);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster((cx.tempty0 + 8u * as) & kPeerBitMask);
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
 // 320 threads are allocated as 384 (warps come in groups of four), so a thread may hold 65 536 / 384 = 170 -> 168 registers:
 // that is what __launch_bounds__(320, 1) makes ptxas target; a higher cap (__maxnreg__) compiles but the launch is refused
 // (cudaErrorLaunchOutOfResources).  The few spilled words are the epilogue's one-tile-ahead prefetch registers (written and
@@ -308,6 +500,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint4* stg4 = reinterpret_cast<uint4*>(smem_raw + (staging_base - smem_u32(smem_raw))) +
                   warp * (Cfg::EPI_TILE_BYTES / 16);
     const uint32_t rbar0 = bar_base + 256u + 16u * warp;          // this warp's two residual-tile barriers (PAIR)
+    bool lean_done = false;
+    if constexpr (PAIR) {
+      // the backbone's shapes: every tile complete, plain GEMM, TMA epilogues available -> specialised loops (above)
+      if (!cv.enabled && dbg_flags == 0 && (N % BN) == 0 && ep.vec_ok && !ep.rowadd) {
+        const EpiCtx cx{tmem_base, tfull_bar(0), tempty_bar(0), rbar0, stg4, worker, n_workers, num_tiles, n_tiles, M, N,
+                        warp, lane, static_cast<int>(cta_rank)};
+        const bool ln = ep.ln_stats != nullptr;
+        if (!ep.out_fp32 && ep.tma_store && ep.bias && (ep.act != MMT_ACT_RELU || !ln)) {
+          if (ep.act == MMT_ACT_GELU) { if (ln) epi_pair_bf16<BN, MMT_ACT_GELU, true>(cx, ep, &tmC); else epi_pair_bf16<BN, MMT_ACT_GELU, false>(cx, ep, &tmC); }
+          else if (ep.act == MMT_ACT_RELU) epi_pair_bf16<BN, MMT_ACT_RELU, false>(cx, ep, &tmC);
+          else { if (ln) epi_pair_bf16<BN, MMT_ACT_NONE, true>(cx, ep, &tmC); else epi_pair_bf16<BN, MMT_ACT_NONE, false>(cx, ep, &tmC); }
+          lean_done = true;
+        } else if (ep.out_fp32 && ep.tma_f32 && ep.act == MMT_ACT_NONE) {
+          if (ep.xb_out) epi_pair_f32<BN, true>(cx, ep, &tmC, &tmR, &tmX); else epi_pair_f32<BN, false>(cx, ep, &tmC, &tmR, &tmX);
+          lean_done = true;
+        }
+      }
+    }
     uint32_t rk = 0;                                               // running chunk counter of the TMA fp32 epilogue
     uint32_t bk = 0;                                               // running chunk counter of the TMA bf16 epilogue
     constexpr int CH = Cfg::CH;
@@ -337,11 +547,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       cp_async_commit();
     };
-    if (ln_active && worker < num_tiles) ln_fetch(worker);
+    if (ln_active && worker < num_tiles && !lean_done) ln_fetch(worker);
     // (Measured and dropped: requesting a warp's residual tiles into L2 one tile ahead with cp.async.bulk.prefetch made proj
     // 50 -> 56 us and fc2 120 -> 130 us at M = 28 928 - like the A-operand prefetch of round 1, profiles/r2_gemm_epilogue.md.)
     int local = 0;
-    for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
+    for (int tile = lean_done ? num_tiles : worker; tile < num_tiles; tile += n_workers, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
       const int mt = tile / n_tiles;
