@@ -82,7 +82,8 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False, 
 def _build_dev(verbose, force, ptxas_info):
     dev_dir = os.path.join(CSRC, "dev")
     srcs = _sources() + sorted(os.path.join(dev_dir, f) for f in os.listdir(dev_dir) if f.endswith(".cu"))
-    return _compile_and_link(srcs, list(NVCC_FLAGS) + ["-DMMT_GEMM_DEV"], os.path.join(CSRC, "_obj", "dev"),
+    extra = os.environ.get("MMT_DEV_EXTRA_FLAGS", "").split()        # one-off experiment macros (developer library only)
+    return _compile_and_link(srcs, list(NVCC_FLAGS) + ["-DMMT_GEMM_DEV"] + extra, os.path.join(CSRC, "_obj", "dev"),
                              os.path.join(CSRC, "libmmt_b200_dev.so"), verbose, force, ptxas_info, stamp=False)
 
 

@@ -107,7 +107,11 @@ struct GemmCfg {
   // epilogue shared memory per warp: one 4 KB staging tile; PAIR: two 4 KB tiles (fp32 residual / output tiles of the
   // TMA epilogue, double-buffered; the bf16 epilogue uses 2 KB of it for the packed rows + 512 B for its bias slices)
   // (+ 2 KB: the bf16 shadow tile of the folded-LayerNorm producer, mmt_gemm_bf16_ex)
+#ifdef MMT_EXP_EPI8K     // developer experiment: 8 KB per warp -> 5 ring stages (the shadow-tile producer is unusable in this build)
+  static constexpr int EPI_TILE_BYTES = PAIR ? 8192 : GEMM_STAGING_WORDS * 4;
+#else
   static constexpr int EPI_TILE_BYTES = PAIR ? 8192 + 2048 : GEMM_STAGING_WORDS * 4;
+#endif
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_TILE_BYTES;
   static constexpr int BAR_BYTES = 512;
   // the dynamic shared memory is declared __align__(1024) (checked at kernel start): no alignment slack is reserved

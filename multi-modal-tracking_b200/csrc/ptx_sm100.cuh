@@ -23,25 +23,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) expires,
+// instead of returning after its short default - a waiting warp then issues a handful of instructions per wait instead
+// of spinning through try_wait / branch (a quarter of the lean GEMM's instruction stream was such spinning: the eight
+// epilogue warps wait for the accumulator most of the time).
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok;
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (an error code at the
-// C-ABI), never as a hung GPU.  ~2^31 polls is far beyond any legitimate wait.
+// C-ABI), never as a hung GPU.  2^20 polls of up to 20 us each (50 ms at least, 21 s at most) is far beyond any
+// legitimate wait - every barrier here is completed by the same kernel within microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 0x40000000u) __trap();
+    if (++spins == 0x00100000u) __trap();
   }
 }
 
