@@ -39,6 +39,11 @@ int mmt_abi_version(int* sm);
  * the tail of the previous kernel of the stream; results are unaffected.  enable = 0 launches them plainly (A/B). */
 int mmt_config_pdl(int enable);
 
+/* Clusters of four CTAs for the big backbone GEMMs (host only; returns the previous setting): two CTA pairs work on two
+ * 256-row blocks of the same 256-column tile and share the weight tile by TMA multicast (3/4 of the L2 -> SM operand bytes
+ * of the CTA-pair launch).  Same arithmetic per output element - results are bit-identical.  enable = 0: CTA pairs only. */
+int mmt_config_cluster4(int enable);
+
 /*
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) + rowadd[row % period][N] + resid[M,N]
  * A, W bf16 row-major (K contiguous, lda/ldw in elements, multiples of 8, 16-byte aligned base);

@@ -14,3 +14,11 @@ extern "C" int mmt_config_pdl(int enable) {
   mmt::g_pdl_enabled = enable ? 1 : 0;
   return prev;
 }
+
+namespace mmt { extern int g_cluster4_enabled; }
+
+extern "C" int mmt_config_cluster4(int enable) {
+  const int prev = mmt::g_cluster4_enabled;
+  mmt::g_cluster4_enabled = enable ? 1 : 0;
+  return prev;
+}

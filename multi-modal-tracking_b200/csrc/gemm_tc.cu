@@ -136,6 +136,7 @@ struct EpiCtx {
   uint32_t rbar0;                // this warp's two residual-tile barriers
   uint4* stg4;                   // this warp's epilogue region (Cfg::EPI_TILE_BYTES)
   int worker, n_workers, num_tiles, n_tiles, M, N, warp, lane, cta_rank;
+  int mt_mul, mt_add;            // 256-row block of scheduler tile t: (t / n_tiles) * mt_mul + mt_add (cluster of two pairs: 2, pair index)
 };
 
 template <int BN, int ACT, bool LN>
@@ -146,7 +147,7 @@ __device__ __forceinline__ void epi_pair_bf16(const EpiCtx& cx, const GemmEpi& e
   float* csum_s = bias_s + MAXC * CH;
   float2* ln_stage = reinterpret_cast<float2*>(cx.stg4 + 384);      // +6144 B: [slot][lane]
   auto ln_fetch = [&](int t) {
-    const int g = (t / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32 + lane;
+    const int g = ((t / cx.n_tiles) * cx.mt_mul + cx.mt_add) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32 + lane;
     const float2* sp = reinterpret_cast<const float2*>(ep.ln_stats) + g;
     for (int q = 0; q < ep.ln_slots; ++q) {
       if (g < cx.M) cp_async_8(smem_u32(ln_stage + q * 32 + lane), sp + static_cast<size_t>(q) * ep.ln_stride);
@@ -161,7 +162,7 @@ __device__ __forceinline__ void epi_pair_bf16(const EpiCtx& cx, const GemmEpi& e
     const int as = local & 1;
     const uint32_t aphase = (local >> 1) & 1u;
     const int n0 = (tile % cx.n_tiles) * BN;
-    const int r0 = (tile / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
+    const int r0 = ((tile / cx.n_tiles) * cx.mt_mul + cx.mt_add) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
     __syncwarp();
     if (lane < MAXC * (CH / 4)) {          // this warp's bias (and column-sum) slices: chunk slot k = lane / 8
       const int nbk = n0 + (half + 2 * (lane >> 3)) * CH;
@@ -242,7 +243,7 @@ __device__ __forceinline__ void epi_pair_f32(const EpiCtx& cx, const GemmEpi& ep
     const int as = local & 1;
     const uint32_t aphase = (local >> 1) & 1u;
     const int n0 = (tile % cx.n_tiles) * BN;
-    const int r0 = (tile / cx.n_tiles) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
+    const int r0 = ((tile / cx.n_tiles) * cx.mt_mul + cx.mt_add) * 2 * GEMM_BM + cx.cta_rank * GEMM_BM + quad * 32;
     auto issue_resid = [&](int c, uint32_t k) {     // TMA load of the residual tile of chunk c into buffer k & 1
       if (lane == 0) {
         bulk_wait_read_all();                       // the store that last used this buffer has read it
@@ -319,16 +320,26 @@ __device__ __forceinline__ void epi_pair_f32(const EpiCtx& cx, const GemmEpi& ep
 // that is what __launch_bounds__(320, 1) makes ptxas target; a higher cap (__maxnreg__) compiles but the launch is refused
 // (cudaErrorLaunchOutOfResources).  The few spilled words are the epilogue's one-tile-ahead prefetch registers (written and
 // read once per tile, L1-resident).
-template <int BN, bool PAIR>
+// CL4 (PAIR only): a cluster of FOUR CTAs = two CTA pairs that work on two 256-row blocks of the SAME 256-column tile.  Every
+// CTA still loads its own 128 A rows, but only a QUARTER of the W tile, multicast to the CTA of the other pair that needs the
+// same half: a k-slice costs the L2 96 KB per two tiles instead of 128 KB.  The backbone GEMMs at 64 sequences sit exactly on
+// the L2 -> SM delivery rate (10 TB/s x 128 FLOP/B = 1.28 PFLOP/s: qkv 1.29, fc1 1.25, profiles/r2_gemm_epilogue.md), so
+// operand bytes per FLOP are what is left to remove.  Stage reuse is gated on BOTH pairs (empty barriers count two commits,
+// multicast to all four CTAs); accumulator barriers stay pair-local.
+template <int BN, bool PAIR, bool CL4 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                          const __grid_constant__ CUtensorMap tmX, int M, int N, int K, GemmEpi ep, GemmConv cv) {
+  static_assert(PAIR || !CL4, "clusters of four are two CTA pairs");
   using Cfg = GemmCfg<BN, PAIR>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = leader of the pair
-  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;     // tile-scheduler slot (a pair is one worker)
-  const int n_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;         // rank in the cluster (0..1, or 0..3 with CL4)
+  const uint32_t cta_rank = crank & 1u;                         // rank in the CTA pair: 0 = leader
+  const int cpair = CL4 ? static_cast<int>(crank >> 1) : 0;     // which pair of the cluster
+  constexpr int CSZ = CL4 ? 4 : 2;
+  const int worker = PAIR ? (blockIdx.x / CSZ) : blockIdx.x;    // tile-scheduler slot (a cluster is one worker)
+  const int n_workers = PAIR ? (gridDim.x / CSZ) : gridDim.x;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if (PAIR && (smem_u32(smem_raw) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -353,8 +364,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int n_tiles = (N + BN - 1) / BN;
   const int tiles_per_img = cv.tiles_x * cv.tiles_y;
   constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;
-  const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * tiles_per_img : (M + TILE_M - 1) / TILE_M;
+  const int m_blocks = cv.enabled ? (M / (cv.H * cv.W)) * tiles_per_img : (M + TILE_M - 1) / TILE_M;
+  const int m_tiles = CL4 ? (m_blocks + 1) / 2 : m_blocks;      // CL4: a scheduler tile = two 256-row blocks x one column tile
   const int num_tiles = n_tiles * m_tiles;
+  constexpr int MT_MUL = CL4 ? 2 : 1;
   const int num_kb = cv.enabled ? 9 * cv.cchunks : (K + GEMM_BK - 1) / GEMM_BK;
   const int dbg_flags = kDev ? ep.dbg_flags : 0;          // compile-time 0 in the shipped build
   long long* const dbg = kDev ? ep.dbg : nullptr;
@@ -364,7 +377,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     prefetch_tmap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL4 ? 2 : 1);       // CL4: the other pair's CTA writes into this stage too
     }
     if (PAIR)
       for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(bar_base + 256u + 8u * i, 1);   // residual tiles landed
@@ -393,10 +406,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += n_workers) {
-        const int mt = tile / n_tiles;
+        const int mt = (tile / n_tiles) * MT_MUL + cpair;
         const int m0 = mt * TILE_M + static_cast<int>(cta_rank) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN;
-        if (PAIR) {
+        if (CL4) {
+          // this CTA: its 128 A rows (rows beyond M arrive as zeros: the odd last block of a cluster tile) and ONE QUARTER of
+          // the W tile, multicast to the CTA of the other pair that holds the same half (ranks h and h + 2); per pair and
+          // stage the leader's barrier still counts 2 x 16 KB of A + 4 x 8 KB of W
+          const int nq0 = n0 + static_cast<int>(cta_rank) * (BN / 2) + cpair * (BN / 4);
+          const uint16_t mc_mask = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2)));
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);          // BOTH pairs have consumed this stage
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kb * GEMM_BK, m0);
+            tma_load_2d_pair_mc(a_dst + Cfg::A_BYTES + cpair * (Cfg::B_BYTES / 2), &tmB, full_bar(stage), kb * GEMM_BK, nq0,
+                                mc_mask);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        } else if (PAIR) {
           // each CTA: its 128 A rows and its half of the W rows; all four boxes are counted on the leader's barrier
           const int nb0 = n0 + static_cast<int>(cta_rank) * (BN / 2);
           const int next_tile = tile + n_workers;
@@ -473,12 +501,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (PAIR) mma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             else mma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (PAIR) mma_commit_pair(empty_bar(stage));      // frees the slot in both CTAs
+          if (CL4) mma_commit_pair(empty_bar(stage), 0xF);  // one of the two commits that free the slot in all four CTAs
+          else if (PAIR) mma_commit_pair(empty_bar(stage)); // frees the slot in both CTAs
           else mma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (PAIR) mma_commit_pair(tfull_bar(as));           // both CTAs' epilogues read their own 128 TMEM lanes
-        else mma_commit(tfull_bar(as));
+        if (PAIR) mma_commit_pair(tfull_bar(as), static_cast<uint16_t>(3u << (2 * cpair)));   // this pair's two CTAs: their
+        else mma_commit(tfull_bar(as));                                                         // epilogues read their own lanes
       }
       if (dbg) {
         dbg[blockIdx.x * 4 + 0] = clock64() - t_total;
@@ -509,7 +538,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // the backbone's shapes: every tile complete, plain GEMM, TMA epilogues available -> specialised loops (above)
       if (!cv.enabled && dbg_flags == 0 && (N % BN) == 0 && ep.vec_ok && !ep.rowadd) {
         const EpiCtx cx{tmem_base, tfull_bar(0), tempty_bar(0), rbar0, stg4, worker, n_workers, num_tiles, n_tiles, M, N,
-                        warp, lane, static_cast<int>(cta_rank)};
+                        warp, lane, static_cast<int>(cta_rank), MT_MUL, cpair};
         const bool ln = ep.ln_stats != nullptr;
         if (!ep.out_fp32 && ep.tma_store && ep.bias && (ep.act != MMT_ACT_RELU || !ln)) {
           if (ep.act == MMT_ACT_GELU) { if (ln) epi_pair_bf16<BN, MMT_ACT_GELU, true>(cx, ep, &tmC); else epi_pair_bf16<BN, MMT_ACT_GELU, false>(cx, ep, &tmC); }
@@ -555,7 +584,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // (Measured and dropped: requesting a warp's residual tiles into L2 one tile ahead with cp.async.bulk.prefetch made proj
     // 50 -> 56 us and fc2 120 -> 130 us at M = 28 928 - like the A-operand prefetch of round 1, profiles/r2_gemm_epilogue.md.)
     int local = 0;
-    for (int tile = lean_done ? num_tiles : worker; tile < num_tiles; tile += n_workers, ++local) {
+    if (CL4 && !lean_done) __trap();      // the cluster-of-four launch is only made for the lean epilogues' shapes
+    for (int tile = (lean_done || CL4) ? num_tiles : worker; tile < num_tiles; tile += n_workers, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1u;
       const int mt = tile / n_tiles;
@@ -1049,40 +1079,55 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles
+// CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles.
+// CL4: clusters of four (two pairs sharing the W tile by TMA multicast) for the lean epilogues' shapes.
+int g_cluster4_enabled = 1;      // mmt_config_cluster4 (A/B measurements)
+
+template <bool CL4>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const CUtensorMap& tmX,
                             const void* W, int ldw, int M, int N, int K, const GemmEpi& ep, cudaStream_t stream) {
   constexpr int BN = 256;
+  constexpr int CSZ = CL4 ? 4 : 2;
   using Cfg = GemmCfg<BN, true>;
   CUtensorMap tmB;
-  int rc = make_tmap_2d(&tmB, W, N, K, ldw, BN / 2);
+  int rc = make_tmap_2d(&tmB, W, N, K, ldw, CL4 ? BN / 4 : BN / 2);      // CL4: every CTA loads a quarter of the W tile
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const int tiles = cdiv(M, 2 * GEMM_BM) * cdiv(N, BN);
-  int pairs = num_sms() / 2;
-  if (tiles < pairs) pairs = tiles;
+  auto kernel = gemm_bf16_tcgen05_kernel<BN, true, CL4>;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CSZ;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    // how many clusters fit at once (148 SMs are 8 GPCs of 16-20: clusters of four leave a few SMs out)
+    cfg.gridDim = dim3(CSZ * (num_sms() / CSZ));
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters <= 0) {
+      cudaGetLastError();
+      max_clusters = CL4 ? 0 : num_sms() / 2;
+    }
+    attr_set = true;
+  }
+  if (CL4 && max_clusters <= 0) return MMT_ERR_UNSUPPORTED;
+  const int blocks256 = cdiv(M, 2 * GEMM_BM);
+  const int tiles = (CL4 ? cdiv(blocks256, 2) : blocks256) * cdiv(N, BN);
+  int clusters = max_clusters < num_sms() / CSZ ? max_clusters : num_sms() / CSZ;
+  if (tiles < clusters) clusters = tiles;
+  cfg.gridDim = dim3(CSZ * clusters);
   cfg.numAttrs = g_pdl_enabled ? 2 : 1;
   GemmConv cv = {};
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, tmA, tmB, tmC, tmR, tmX, M, N, K, ep, cv);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, tmR, tmX, M, N, K, ep, cv);
   if (e != cudaSuccess) return (int)e;
   MMT_RETURN_LAST_ERROR();
 }
@@ -1177,7 +1222,17 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
     if (ep.tma_f32 && ep.xb_out && make_tmap_out(&tmX, ep.xb_out, M, N, ep.ld_xb) != MMT_OK) ep.tma_f32 = 0;
     if (!ep.tma_f32) { ep.xb_out = nullptr; ep.stats_out = nullptr; }
     else if (ln_produced && ep.xb_out) *ln_produced = 1;
-    return launch_gemm_pair(tmA, tmC, tmR, tmX, W, ldw, M, N, K, ep, s);
+    // clusters of four for the shapes of the lean epilogues (the conditions of the kernel's own dispatch), with at least two
+    // waves of cluster tiles
+    const bool lean_bf16 = !ep.out_fp32 && ep.tma_store && ep.bias && (ep.act != MMT_ACT_RELU || !ep.ln_stats);
+    const bool lean_f32 = ep.out_fp32 && ep.tma_f32 && ep.act == MMT_ACT_NONE;
+    const bool dev_flags = kDev && ep.dbg_flags != 0;
+    if (g_cluster4_enabled && ep.vec_ok && !ep.rowadd && (lean_bf16 || lean_f32) && !dev_flags &&
+        cdiv(cdiv(M, 2 * GEMM_BM), 2) * (N / 256) >= 2 * (num_sms() / 4)) {
+      const int rc4 = launch_gemm_pair<true>(tmA, tmC, tmR, tmX, W, ldw, M, N, K, ep, s);
+      if (rc4 != MMT_ERR_UNSUPPORTED) return rc4;
+    }
+    return launch_gemm_pair<false>(tmA, tmC, tmR, tmX, W, ldw, M, N, K, ep, s);
   }
   ep.xb_out = nullptr;
   ep.stats_out = nullptr;

@@ -149,6 +149,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same, MULTICAST to the CTAs of `mask` (cluster ranks): one L2 read lands at the same CTA-relative offset in every
+// destination CTA and signals the mbarrier at `bar`'s offset in the leader of EACH destination's pair.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                    uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -171,8 +181,7 @@ __device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t adesc
       : "memory");
 }
 // arrive on the mbarrier at this offset in BOTH CTAs of the pair once all prior MMAs of this thread completed
-__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
-  const uint16_t mask = 3;
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(bar), "h"(mask)

@@ -60,6 +60,13 @@ def config_pdl(enable: bool) -> bool:
     return bool(f(c_int(1 if enable else 0)))
 
 
+def config_cluster4(enable: bool) -> bool:
+    """Clusters of four CTAs (two pairs, multicast weight tile) for the big backbone GEMMs on or off (mmt_config_cluster4);
+    returns the previous setting.  Results do not depend on it."""
+    f = _lib.fn("mmt_config_cluster4")
+    return bool(f(c_int(1 if enable else 0)))
+
+
 def _pair_min_tiles():
     global _PAIR_MIN
     if _PAIR_MIN is None:

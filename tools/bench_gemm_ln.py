@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mmt_b200  # noqa
 from mmt_b200 import ops
+if os.environ.get("MMT_CL4") == "0":
+    ops.config_cluster4(False)
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 28928
 

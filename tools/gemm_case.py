@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mmt_b200  # noqa
 from mmt_b200 import ops
+if os.environ.get("MMT_CL4") == "0":
+    ops.config_cluster4(False)
 
 name, mode = sys.argv[1], sys.argv[2]
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 28928
