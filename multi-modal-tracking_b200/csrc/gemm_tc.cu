@@ -322,10 +322,10 @@ __device__ __forceinline__ void epi_pair_f32(const EpiCtx& cx, const GemmEpi& ep
 // read once per tile, L1-resident).
 // CL4 (PAIR only): a cluster of FOUR CTAs = two CTA pairs that work on two 256-row blocks of the SAME 256-column tile.  Every
 // CTA still loads its own 128 A rows, but only a QUARTER of the W tile, multicast to the CTA of the other pair that needs the
-// same half: a k-slice costs the L2 96 KB per two tiles instead of 128 KB.  The backbone GEMMs at 64 sequences sit exactly on
-// the L2 -> SM delivery rate (10 TB/s x 128 FLOP/B = 1.28 PFLOP/s: qkv 1.29, fc1 1.25, profiles/r2_gemm_epilogue.md), so
-// operand bytes per FLOP are what is left to remove.  Stage reuse is gated on BOTH pairs (empty barriers count two commits,
-// multicast to all four CTAs); accumulator barriers stay pair-local.
+// same half: a k-slice costs the L2 96 KB per two tiles instead of 128 KB.  An EXPERIMENT (off by default, see
+// g_cluster4_enabled): the backbone GEMMs deliver operands at ~10 TB/s x 128 FLOP/B = 1.28 PFLOP/s (qkv 1.29, fc1 1.25), which
+// looked like the L2 read rate being the bound - the measurement says otherwise.  Stage reuse is gated on BOTH pairs (empty
+// barriers count two commits, multicast to all four CTAs); accumulator barriers stay pair-local.
 template <int BN, bool PAIR, bool CL4 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -1081,7 +1081,10 @@ static int num_sms() {
 
 // CTA-pair launch (cluster of 2, cta_group::2 MMAs): plain GEMMs with N a multiple of 256 and enough 256-row tiles.
 // CL4: clusters of four (two pairs sharing the W tile by TMA multicast) for the lean epilogues' shapes.
-int g_cluster4_enabled = 1;      // mmt_config_cluster4 (A/B measurements)
+// Measured (profiles/r2_gemm_epilogue.md): correct, but NOT faster - qkv 82 -> 85.5 us, fc1 113.5 -> 118.5 us, fc2 121-126 -> 142 us
+// at M = 28 928, neutral in the step: clusters of four leave SMs out (GPCs of 16-20 SMs) and every SM still ingests the same
+// 32 KB per k-slice, so the bound is per SM, not the L2's read rate.  Off by default; mmt_config_cluster4(1) selects it.
+int g_cluster4_enabled = 0;
 
 template <bool CL4>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const CUtensorMap& tmX,

@@ -193,3 +193,37 @@ def test_folded_layernorm_argument_checks(built_lib):
         ops.gemm(a, w, b, 0, ln_stats=sums, ln_eps=1e-6, colsum=b, out_dtype=torch.float32)
     with pytest.raises(AssertionError):      # the fp32 parity kernel has no folded form
         ops.gemm(a.float(), w.float(), b, 0, ln_stats=sums, ln_eps=1e-6, colsum=b)
+
+
+@pytest.mark.parametrize("case", [(19000, 2304, 768, 0, False), (18945, 768, 768, 0, True), (13000, 3072, 768, 1, False)])
+def test_cluster_of_four_is_bit_identical(built_lib, case):
+    """mmt_config_cluster4: two CTA pairs per cluster sharing the weight tile by TMA multicast (off by default) must
+    reproduce the CTA-pair launch bit for bit - qkv-like, proj-like (in-place residual + shadow rows, odd row count: the
+    last cluster tile has one real and one empty 256-row block) and fc1-like (GELU) shapes."""
+    from mmt_b200 import ops
+    M, N, K, act, resid = case
+    g = torch.Generator(device="cuda").manual_seed(M)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g) if resid else None
+
+    def run():
+        if resid:
+            out = x0.clone()
+            xb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            sums = torch.empty(N // 128, M, 2, device="cuda")
+            ops.gemm(a, w, bias, act, out, None, out=out, xb_out=xb, stats_out=sums)
+            return out, xb, sums
+        return (ops.gemm(a, w, bias, act, out_dtype=torch.bfloat16),)
+
+    prev = ops.config_cluster4(False)
+    try:
+        ref = run()
+        ops.config_cluster4(True)
+        got = run()
+        torch.cuda.synchronize()
+    finally:
+        ops.config_cluster4(prev)
+    for r, g_ in zip(ref, got):
+        assert torch.equal(r, g_)
