@@ -1,4 +1,6 @@
-"""Micro-benchmark of the tcgen05 GEMM on the backbone shapes (CUDA events, L2-busting rotation)."""
+"""Micro-benchmark of the tcgen05 GEMM on the backbone shapes (CUDA events, L2-busting rotation).
+The `timing` mode (MMA-thread stall counters) and the MMT_GEMM_DBG isolation switches exist only in the developer library:
+build it with `python multi-modal-tracking_b200/build.py --dev` and run with MMT_B200_DEV_LIB=1."""
 import json
 import sys
 import os
