@@ -232,6 +232,34 @@ def test_cuda_graph_replay_matches_eager(built_lib):
             assert torch.equal(eager, graphed) and torch.equal(graphed, graphed2), (variant, batch)
 
 
+def test_in_place_parameter_edits_repack_the_weights(built_lib):
+    """The packed device arena follows the module's parameters: an in-place edit after the first forward (which
+    load_state_dict / .cuda() hooks cannot see) is picked up through the parameters' version counters, or explicitly by
+    invalidate() - no stale weights, eager or graphed."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model("mixformer_vit", 0)
+    model = model.cuda()
+    inputs = synthetic.make_inputs("mixformer_vit", cfg, 2, 3, device="cuda")
+    _, a = model(*inputs)
+    with torch.no_grad():
+        model.box_head.conv5_tl.bias.add_(3.0)                      # invisible to load_state_dict / _apply hooks
+        model.box_head.conv5_tl.weight.mul_(1.5)
+    _, b = model(*inputs)
+    fresh, _ = synthetic.make_model("mixformer_vit", 0)
+    fresh.load_state_dict(model.state_dict())
+    _, want = fresh.cuda()(*inputs)
+    torch.cuda.synchronize()
+    assert not torch.equal(a, b) and torch.equal(b, want)
+    model.enable_cuda_graph(True)
+    _, g1 = model(*inputs)
+    with torch.no_grad():
+        model.box_head.conv5_tl.weight.mul_(1.0 / 1.5)
+        model.box_head.conv5_tl.bias.sub_(3.0)
+    _, g2 = model.invalidate()(*inputs)
+    torch.cuda.synchronize()
+    assert torch.equal(g1, want) and torch.allclose(g2, a, atol=1e-6)
+
+
 def test_programmatic_dependent_launch_is_result_neutral(built_lib):
     """mmt_config_pdl: the kernels' prologues overlapping the previous kernel's tail (griddepcontrol) change no result -
     eager launches and graph replay, two variants (two streams / one stream with candidate elimination)."""
