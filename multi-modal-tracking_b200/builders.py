@@ -389,13 +389,11 @@ class _EngineModule(nn.Module):
     def invalidate(self):
         """Re-pack the device weight arena (and drop captured CUDA graphs) at the next forward.  load_state_dict on the
         model, .cuda() / .to() and set_precision do this by themselves; call it after what they cannot see: in-place edits
-        of parameters (`p.data.copy_()`), or load_state_dict on a SUB-module (`model.backbone.load_state_dict(...)`)."""
+        of parameters (`p.data.copy_()`), or load_state_dict on a SUB-module (`model.backbone.load_state_dict(...)`).
+        (An automatic check - comparing every parameter's version counter per forward - was measured at 0.5 ms of host time
+        per call, 40 % of the single-sequence latency, and is therefore not done.)"""
         self._version += 1
         return self
-
-    def _param_fingerprint(self):
-        """Cheap staleness check of engine(): torch bumps a tensor's `_version` on every in-place write."""
-        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
 
     def set_precision(self, precision: str):
         if precision not in ("bf16", "fp32"):
@@ -417,11 +415,7 @@ class _EngineModule(nn.Module):
         if dev.type != "cuda":
             # same convention as the reference's native ops (prroi_pool/functional.py:62-63)
             raise NotImplementedError("mmt_b200 models run on CUDA only: call .cuda() first (no CPU fallback)")
-        fp = self._param_fingerprint()
-        if self._engine is not None and fp != getattr(self, "_packed_fp", None):
-            self._version += 1            # a parameter was written in place since the arena was packed
         if self._engine is None or self._packed_version != self._version:
-            self._packed_fp = fp
             self._graphs = {}
             self._engine = ForwardEngine(self.variant, self._cfg, self.state_dict(), dev, self.precision)
             self._packed_version = self._version

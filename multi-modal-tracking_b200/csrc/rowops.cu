@@ -301,6 +301,88 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int HW, int C, int
     }
 }
 
+// The same with the CTA's [HW x 8 groups] slab held in registers (one HBM pass instead of three, every load of a thread in
+// flight at once): HW <= MAXR * slices rows.  Same arithmetic and the same fixed-order reductions as groupnorm_kernel -
+// bit-identical results; the three dependent passes made the small launches latency chains (20 us at one sequence,
+// profiles/r2_launches.md).
+template <int MAXR>
+__global__ void groupnorm_reg_kernel(const float* __restrict__ x, int HW, int C, int G, float eps,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* out_f32,
+                                     bf16* out_bf16, int out_seq_rows, int out_row_off) {
+  const int cpg = C / G;
+  const int lanes = 8 * cpg / 4;
+  const int slices = blockDim.x / lanes;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * 8 * cpg;
+  const int l = threadIdx.x % lanes, sl = threadIdx.x / lanes;
+  const int grp = (l * 4) / cpg;
+  __shared__ float part[512];
+  __shared__ float stat[2][8];
+  const float* xb = x + static_cast<size_t>(b) * HW * C + c0 + l * 4;
+  const float cnt = static_cast<float>(HW) * cpg;
+  const int lpg = cpg / 4;
+  auto group_total = [&](float v) -> float {
+    part[threadIdx.x] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (threadIdx.x < 8) {
+      for (int s2 = 0; s2 < slices; ++s2)
+        for (int j = 0; j < lpg; ++j) t += part[s2 * lanes + threadIdx.x * lpg + j];
+    }
+    return t;
+  };
+  float4 v[MAXR];
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i) {
+    const int r = sl + i * slices;
+    v[i] = r < HW ? *reinterpret_cast<const float4*>(xb + static_cast<size_t>(r) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i)
+    if (sl + i * slices < HW) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  {
+    const float t = group_total(s);
+    if (threadIdx.x < 8) stat[0][threadIdx.x] = t / cnt;
+  }
+  __syncthreads();
+  const float mean = stat[0][grp];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i)
+    if (sl + i * slices < HW) {
+      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + bq * bq + c * c + d * d;
+    }
+  {
+    const float t = group_total(q);
+    if (threadIdx.x < 8) stat[1][threadIdx.x] = rsqrtf(t / cnt + eps);
+  }
+  __syncthreads();
+  const float rstd = stat[1][grp];
+  const float4 gg = *reinterpret_cast<const float4*>(gamma + c0 + l * 4);
+  const float4 be = *reinterpret_cast<const float4*>(beta + c0 + l * 4);
+#pragma unroll
+  for (int i = 0; i < MAXR; ++i) {
+    const int r = sl + i * slices;
+    if (r < HW) {
+      const size_t off = (static_cast<size_t>(b) * out_seq_rows + out_row_off + r) * C + c0 + l * 4;
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gg.x + be.x;
+      o.y = (v[i].y - mean) * rstd * gg.y + be.y;
+      o.z = (v[i].z - mean) * rstd * gg.z + be.z;
+      o.w = (v[i].w - mean) * rstd * gg.w + be.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = o;
+      if (out_bf16) {
+        uint2 p;
+        p.x = pack_bf16x2(o.x, o.y);
+        p.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(out_bf16 + off) = p;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // copy_rows: dst[s*rows_per_seq + r, :] = src[s*seq_stride + row_off + r, :]  (fp32 -> T), e.g. the search
 // tokens of every sequence out of the [t, ot, s] token layout (mixformer.py:208-214).
@@ -649,7 +731,12 @@ extern "C" int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float 
   int slices = 512 / lanes;
   if (slices > 16) slices = 16;
   dim3 grid(G / 8, B);
-  groupnorm_kernel<<<grid, lanes * slices, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t gs = reinterpret_cast<cudaStream_t>(stream);
+  if (HW <= 24 * slices)       // the slab fits in registers: one pass over HBM
+    groupnorm_reg_kernel<24><<<grid, lanes * slices, 0, gs>>>(
+      x, HW, C, G, eps, gamma, beta, out_f32, reinterpret_cast<bf16*>(out_bf16), out_seq_rows, out_row_off);
+  else
+    groupnorm_kernel<<<grid, lanes * slices, 0, gs>>>(
       x, HW, C, G, eps, gamma, beta, out_f32, reinterpret_cast<bf16*>(out_bf16), out_seq_rows, out_row_off);
   MMT_RETURN_LAST_ERROR();
 }

@@ -233,9 +233,8 @@ def test_cuda_graph_replay_matches_eager(built_lib):
 
 
 def test_in_place_parameter_edits_repack_the_weights(built_lib):
-    """The packed device arena follows the module's parameters: an in-place edit after the first forward (which
-    load_state_dict / .cuda() hooks cannot see) is picked up through the parameters' version counters, or explicitly by
-    invalidate() - no stale weights, eager or graphed."""
+    """In-place parameter edits after the first forward (which the load_state_dict / .cuda() hooks cannot see) reach the
+    packed device arena - and the captured CUDA graphs - through invalidate()."""
     from mmt_b200 import synthetic
     model, cfg = synthetic.make_model("mixformer_vit", 0)
     model = model.cuda()
@@ -244,7 +243,9 @@ def test_in_place_parameter_edits_repack_the_weights(built_lib):
     with torch.no_grad():
         model.box_head.conv5_tl.bias.add_(3.0)                      # invisible to load_state_dict / _apply hooks
         model.box_head.conv5_tl.weight.mul_(1.5)
-    _, b = model(*inputs)
+    _, stale = model(*inputs)
+    assert torch.equal(stale, a)                                     # documented: not seen until invalidate()
+    _, b = model.invalidate()(*inputs)
     fresh, _ = synthetic.make_model("mixformer_vit", 0)
     fresh.load_state_dict(model.state_dict())
     _, want = fresh.cuda()(*inputs)
