@@ -306,7 +306,7 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int HW, int C, int
 // bit-identical results; the three dependent passes made the small launches latency chains (20 us at one sequence,
 // profiles/r2_launches.md).
 template <int MAXR>
-__global__ void groupnorm_reg_kernel(const float* __restrict__ x, int HW, int C, int G, float eps,
+__global__ void __launch_bounds__(512) groupnorm_reg_kernel(const float* __restrict__ x, int HW, int C, int G, float eps,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* out_f32,
                                      bf16* out_bf16, int out_seq_rows, int out_row_off) {
   const int cpg = C / G;
@@ -732,8 +732,8 @@ extern "C" int mmt_groupnorm(const float* x, int B, int HW, int C, int G, float 
   if (slices > 16) slices = 16;
   dim3 grid(G / 8, B);
   cudaStream_t gs = reinterpret_cast<cudaStream_t>(stream);
-  if (HW <= 24 * slices)       // the slab fits in registers: one pass over HBM
-    groupnorm_reg_kernel<24><<<grid, lanes * slices, 0, gs>>>(
+  if (HW <= 21 * slices && lanes * slices <= 512)       // the slab fits in registers (84 per thread): one pass over HBM
+    groupnorm_reg_kernel<21><<<grid, lanes * slices, 0, gs>>>(
       x, HW, C, G, eps, gamma, beta, out_f32, reinterpret_cast<bf16*>(out_bf16), out_seq_rows, out_row_off);
   else
     groupnorm_kernel<<<grid, lanes * slices, 0, gs>>>(
