@@ -11,7 +11,9 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MMT_B200_DEV_LIB=1 (tools/ only): the developer build with the GEMM experiment switches (build.py --dev)
-LIB_PATH = os.path.join(_HERE, "csrc", "libmmt_b200_dev.so" if os.environ.get("MMT_B200_DEV_LIB") == "1" else "libmmt_b200.so")
+_DEV = os.environ.get("MMT_B200_DEV_LIB", "")
+LIB_PATH = os.path.join(_HERE, "csrc", "libmmt_b200.so" if _DEV in ("", "0") else
+                        "libmmt_b200_dev.so" if _DEV == "1" else f"libmmt_b200_{_DEV}.so")   # named experiment builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mmt_b200.h")
 
 

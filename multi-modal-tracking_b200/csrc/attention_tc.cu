@@ -40,6 +40,9 @@ struct AttnTileTC {      // same 16-int record as AttnTile (attention.cu); q_row
   int pad[3];
 };
 
+#ifndef MMT_ATTN_EXP
+#define MMT_ATTN_EXP 0       // developer timing experiments (tools/ only; results are WRONG with any bit set)
+#endif
 constexpr int ATC_HD = 64;
 constexpr int ATC_KB = 64;                          // keys per block
 constexpr int ATC_STAGES = 4;
@@ -89,17 +92,20 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //                      item's first P V MMA overwrites it)
 // Items are ordered tile-major with the head fastest; the host sorts the tile table by key count (heavy first), so a
 // stride walk gives every CTA the same mix of 4-block search tiles and 1-block template tiles.
-constexpr int ATP_SMEM = 2 * ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + 1024 + 256 + 3072;
+constexpr int ATP_STG_BYTES = 8 * 2048;   // one 32 x 32 bf16 staging tile per softmax warp (epilogue TMA stores)
+constexpr int ATP_SMEM = 2 * ATC_Q_BYTES + ATC_STAGES * ATC_BLK_BYTES + ATP_STG_BYTES + 1024 + 256 + 3072;
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
-attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int C,
+attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                       const __grid_constant__ CUtensorMap tmo, int C,
                        const AttnTileTC* __restrict__ tiles, int n_items, int heads, bf16* __restrict__ out, int ldo,
                        float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = smem_base;                                  // two Q buffers
   const uint32_t ring_smem = q_smem + 2 * ATC_Q_BYTES;
-  const uint32_t bar_base = ring_smem + ATC_STAGES * ATC_BLK_BYTES;
+  const uint32_t stg_smem = ring_smem + ATC_STAGES * ATC_BLK_BYTES;  // 64 KB past the 1024-aligned base
+  const uint32_t bar_base = stg_smem + ATP_STG_BYTES;
   auto kv_full = [&](int s) { return bar_base + 8u * s; };
   auto kv_empty = [&](int s) { return bar_base + 8u * (ATC_STAGES + s); };
   auto q_full = [&](int b) { return bar_base + 8u * (2 * ATC_STAGES + b); };
@@ -121,6 +127,7 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm0);
     prefetch_tmap(&tm1);
+    prefetch_tmap(&tmo);
     for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(q_full(b), 1); mbar_init(q_empty(b), 1); }
     mbar_init(s_full, 1);
@@ -296,7 +303,11 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
             const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
             const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
             // every fourth exponential on the FMA pipe (re-measured in round 2: all-MUFU is 1 % slower, 100.0 vs 99.1 us)
+#if MMT_ATTN_EXP & 2
+            const float p0 = x0 * 0.001f, p1 = x1 * 0.001f;
+#else
             const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
+#endif
             l_row += p0 + p1;
             pk[i] = pack_bf16x2(p0, p1);
           }
@@ -334,8 +345,10 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
         ex[half * 128 + r] = bm;
         // only the two warps that share this TMEM lane quadrant (the two threads of a row live in warps q and q + 4) meet:
         // four independent 64-thread barriers instead of one over all eight softmax warps
+#if !(MMT_ATTN_EXP & 1)
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
+#endif
         float factor = 1.f;
         bool moved = false;
         if ((bm - m_row) * scale_log2e > 8.f) {
@@ -377,20 +390,36 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);          // O may be overwritten by the next item's first P V
-      if (r < t.q_rows) {
+      // A warp whose 32 rows are all valid leaves through a 64B-swizzled staging tile and ONE TMA store of a 32 x 32 box
+      // (per-thread 16-byte stores of the thread == row layout fill half a 32-byte sector each: measured at 20 % of the
+      // launch, profiles/r2_attention.md); the warp that straddles the end of a short tile stores its valid rows directly.
+      const bool warp_full = quad * 32 + 32 <= t.q_rows;
+      if ((warp_full || r < t.q_rows) && !(MMT_ATTN_EXP & 4)) {
         const float inv = 1.f / l_row;
-        uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD + 32 * half);
+        uint32_t w[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
-          dst[c] = w;
+        for (int c = 0; c < 16; ++c) w[c] = pack_bf16x2(__uint_as_float(o[2 * c]) * inv, __uint_as_float(o[2 * c + 1]) * inv);
+        if (warp_full) {
+          uint4* stg = reinterpret_cast<uint4*>(smem_raw + (stg_smem - smem_u32(smem_raw))) + (warp - 2) * 128;
+          if (lane == 0) bulk_wait_read_all();       // the previous item's store has read this warp's tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)     // 64-byte rows, 16-byte chunk j of row `lane` at j ^ ((lane >> 1) & 3): SWIZZLE_64B
+            stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmo, smem_u32(stg), h * ATC_HD + 32 * half, t.out_row0 + quad * 32);
+            bulk_commit_group();
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t.out_row0 + r) * ldo + h * ATC_HD + 32 * half);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         }
       }
     }
+    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -425,12 +454,30 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, i
   return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
 }
 
+// bf16 output [rows, cols]: 32 x 32 boxes, 64-byte swizzle (the epilogue's per-warp staging tile)
+static int make_out_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld) {
+  auto fn = attn_encode_fn();
+  if (!fn) return MMT_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
+}
+
 int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int ld, int C, int heads,
                    const int* tiles_dev, int n_tiles, void* out, int ldo, float scale, cudaStream_t stream) {
-  CUtensorMap tm0, tm1;
+  CUtensorMap tm0, tm1, tmo;
   int rc = make_qkv_tmap(&tm0, qkv0, rows0, 3 * C, ld);
   if (rc) return rc;
   rc = make_qkv_tmap(&tm1, qkv1, rows1, 3 * C, ld);
+  if (rc) return rc;
+  // output rows are addressed through the tile table: the map's row bound is nominal (only groups of 32 valid rows are
+  // stored through it, so its clipping is never relied upon)
+  rc = make_out_tmap(&tmo, out, 1 << 30, C, ldo);
   if (rc) return rc;
   static bool attr_p = false;
   static int n_sm = 0;
@@ -443,8 +490,12 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
     attr_p = true;
   }
   const int n_items = n_tiles * heads;
+#if MMT_ATTN_EXP & 8
+  const int grid = n_items < n_sm ? n_items : n_sm;              // one CTA per SM
+#else
   const int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
-  cudaError_t e = launch_pdl(attn_tc_persist_kernel, dim3(grid), dim3(ATC_THREADS), ATP_SMEM, stream, tm0, tm1, C,
+#endif
+  cudaError_t e = launch_pdl(attn_tc_persist_kernel, dim3(grid), dim3(ATC_THREADS), ATP_SMEM, stream, tm0, tm1, tmo, C,
                              reinterpret_cast<const AttnTileTC*>(tiles_dev), n_items, heads, reinterpret_cast<bf16*>(out), ldo,
                              scale * 1.4426950408889634f);
   if (e != cudaSuccess) return (int)e;
