@@ -43,6 +43,14 @@ struct AttnTileTC {      // same 16-int record as AttnTile (attention.cu); q_row
 #ifndef MMT_ATTN_EXP
 #define MMT_ATTN_EXP 0       // developer timing experiments (tools/ only; results are WRONG with any bit set)
 #endif
+#if MMT_ATTN_EXP & 16
+__device__ unsigned long long g_attn_stamp[512][12];     // per-CTA phase cycle sums of softmax warp 4, lane 0
+#define ATTN_STAMP(i, a, b) do { if (stamping) acc[i] += (unsigned long long)((b) - (a)); } while (0)
+#define ATTN_CLK() clock64()
+#else
+#define ATTN_STAMP(i, a, b) do { } while (0)
+#define ATTN_CLK() 0ll
+#endif
 constexpr int ATC_HD = 64;
 constexpr int ATC_KB = 64;                          // keys per block
 constexpr int ATC_STAGES = 4;
@@ -77,6 +85,22 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.6931472f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Two 2^x at once with packed fp32 instructions (fma.rn.f32x2 / add.f32x2: one issue slot for two lanes of work).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 tm = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(tm, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0555041f, 0.0555041f), make_float2(0.2402265f, 0.2402265f));
+  p = __ffma2_rn(p, f, make_float2(0.6931472f, 0.6931472f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -277,13 +301,19 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
     const uint32_t o_addr = tmem_o + lane_off + 32u * half;
     uint32_t g = 0;               // super-blocks processed so far (all items)
     int n = 0;
+#if MMT_ATTN_EXP & 16
+    const bool stamping = warp == 4 && lane == 0;
+    unsigned long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tk0 = clock64();
+#endif
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const AttnTileTC t = tiles[item / heads];
       const int h = item % heads;
       const Plan pl = make_plan(t);
       float m_row = -INFINITY;      // lazy running maximum (raw score units)
       float mc = 0.f;               // m_row * scale_log2e
-      float l_row = 0.f;            // this thread's part of the row sum
+      float l_row = 0.f;            // this thread's part of the row sum (partially valid column groups)
+      float2 l2 = make_float2(0.f, 0.f);   // ... and of the fully valid ones, as two packed partial sums
       auto row_max = [&](const uint32_t (&v)[32], int lim0, float m) {
         if (lim0 >= 32) {
 #pragma unroll
@@ -300,16 +330,17 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
         if (lim0 >= 32) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float x0 = fmaf(__uint_as_float(v[2 * i]), scale_log2e, -mc);
-            const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -mc);
-            // every fourth exponential on the FMA pipe (re-measured in round 2: all-MUFU is 1 % slower, 100.0 vs 99.1 us)
+            // packed fp32 arithmetic (the softmax warps are issue-bound: profiles/r2_attention.md); every fourth PAIR of
+            // exponentials on the FMA pipe instead of the MUFU unit
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                        make_float2(scale_log2e, scale_log2e), make_float2(-mc, -mc));
 #if MMT_ATTN_EXP & 2
-            const float p0 = x0 * 0.001f, p1 = x1 * 0.001f;
+            const float2 pp = __fmul2_rn(x, make_float2(0.001f, 0.001f));
 #else
-            const float p0 = ex2_approx(x0), p1 = (i & 1) ? ex2_poly(x1) : ex2_approx(x1);
+            const float2 pp = (i & 3) == 3 ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
 #endif
-            l_row += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            l2 = __fadd2_rn(l2, pp);
+            pk[i] = pack_bf16x2(pp.x, pp.y);
           }
         } else if (lim0 <= 0) {
 #pragma unroll
@@ -330,17 +361,31 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
       for (int j = 0; j < pl.nsb; ++j, ++g) {
         int row0, len, buf;
         locate(t, pl, 2 * j + half, row0, len, buf);
+        const long long t0 = ATTN_CLK();
         mbar_wait(s_full, g & 1u);
         tc_fence_after();
+        const long long t1 = ATTN_CLK();
+        // tensor-memory reads are the scarcest resource of this kernel at head dimension 64 (64 KB of S per 128 x 128 block
+        // against 512 MMA cycles): warps without a valid row and column groups without a valid key are not read at all
+        if (!warp_live) {          // no valid row in this TMEM lane quadrant (both warps of the pair): keep the barrier protocol only;
+          __syncwarp();            // P / O rows of dead lanes hold stale finite-or-not values that no valid row ever sees
+          if (lane == 0) mbar_arrive(s_empty);
+          mbar_wait(p_empty, (g & 1u) ^ 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+          continue;
+        }
         uint32_t v0[32], v1[32];
+        const bool two = len > 32;                 // warp-uniform: the second column group holds at least one valid key
         tmem_ld_32x32(s_addr, v0);
-        tmem_ld_32x32(s_addr + 32, v1);
+        if (two) tmem_ld_32x32(s_addr + 32, v1);
         tmem_ld_wait();
+        const long long t2 = ATTN_CLK();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
         float bm = row_max(v0, len, -INFINITY);
-        bm = row_max(v1, len - 32, bm);
+        if (two) bm = row_max(v1, len - 32, bm);
         float* ex = smax + (g & 1u) * 256;
         ex[half * 128 + r] = bm;
         // only the two warps that share this TMEM lane quadrant (the two threads of a row live in warps q and q + 4) meet:
@@ -349,6 +394,7 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         bm = fmaxf(bm, ex[(half ^ 1) * 128 + r]);
 #endif
+        const long long t3 = ATTN_CLK();
         float factor = 1.f;
         bool moved = false;
         if ((bm - m_row) * scale_log2e > 8.f) {
@@ -356,11 +402,14 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
           m_row = bm;
           mc = m_row * scale_log2e;
           l_row *= factor;
+          l2 = __fmul2_rn(l2, make_float2(factor, factor));
           moved = warp_live;
         }
         probs(v0, warp_live ? len : 0);
+        const long long t4 = ATTN_CLK();
         mbar_wait(p_empty, (g & 1u) ^ 1u);          // the PV MMAs of the previous super-block (any item) have completed
         tc_fence_after();
+        const long long t5 = ATTN_CLK();
         if (j > 0 && __any_sync(0xffffffffu, moved)) {
           uint32_t o[32];
           tmem_ld_32x32(o_addr, o);
@@ -373,16 +422,22 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
         probs(v1, warp_live ? len - 32 : 0);
         tmem_st_32x16(tmem_p + lane_off + 32u * half + 16u, v1);
         tmem_st_wait();
+        const long long t6 = ATTN_CLK();
+        ATTN_STAMP(0, t0, t1); ATTN_STAMP(1, t1, t2); ATTN_STAMP(2, t2, t3); ATTN_STAMP(3, t3, t4);
+        ATTN_STAMP(4, t4, t5); ATTN_STAMP(5, t5, t6); ATTN_STAMP(8, 0, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
       // epilogue: O / L -> bf16 -> out (this thread: 32 of the 64 head channels)
+      const long long t7 = ATTN_CLK();
       mbar_wait(o_full, n & 1u);
       tc_fence_after();
+      const long long t8 = ATTN_CLK();
       uint32_t o[32];
       tmem_ld_32x32(o_addr, o);
       float* exl = smax + 512;                      // dedicated row-sum exchange buffer
+      l_row += l2.x + l2.y;
       exl[half * 128 + r] = l_row;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
       l_row += exl[(half ^ 1) * 128 + r];
@@ -418,8 +473,16 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
           for (int c = 0; c < 4; ++c) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         }
       }
+      const long long t9 = ATTN_CLK();
+      ATTN_STAMP(6, t7, t8); ATTN_STAMP(7, t8, t9); ATTN_STAMP(9, 0, 1);
     }
     if (lane == 0) bulk_wait_all();
+#if MMT_ATTN_EXP & 16
+    if (stamping && blockIdx.x < 512) {
+      acc[10] = (unsigned long long)(clock64() - tk0);
+      for (int i = 0; i < 12; ++i) g_attn_stamp[blockIdx.x][i] = acc[i];
+    }
+#endif
   }
 
   tc_fence_before();
@@ -504,3 +567,9 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
 }
 
 }  // namespace mmt
+
+#if MMT_ATTN_EXP & 16
+extern "C" int mmt_dev_attn_stamps(unsigned long long* host_out) {     // [512][12], developer builds only
+  return (int)cudaMemcpyFromSymbol(host_out, mmt::g_attn_stamp, sizeof(mmt::g_attn_stamp));
+}
+#endif
