@@ -48,7 +48,7 @@ __device__ unsigned long long g_attn_stamp[512][12];     // per-CTA phase cycle 
 #define ATTN_STAMP(i, a, b) do { if (stamping) acc[i] += (unsigned long long)((b) - (a)); } while (0)
 #define ATTN_CLK() clock64()
 #else
-#define ATTN_STAMP(i, a, b) do { } while (0)
+#define ATTN_STAMP(i, a, b) do { (void)(a); (void)(b); } while (0)
 #define ATTN_CLK() 0ll
 #endif
 constexpr int ATC_HD = 64;
@@ -490,6 +490,7 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, ATC_TMEM_COLS);
 }
 
+
 static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -517,17 +518,18 @@ static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, i
   return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
 }
 
-// bf16 output [rows, cols]: 32 x 32 boxes, 64-byte swizzle (the epilogue's per-warp staging tile)
-static int make_out_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld) {
+// bf16 output [rows, cols]: 32-row boxes of the epilogue's per-warp staging tile (32 columns / 64-byte swizzle in the
+// half-row form, 64 columns / 128-byte swizzle in the row form)
+static int make_out_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_cols) {
   auto fn = attn_encode_fn();
   if (!fn) return MMT_ERR_UNSUPPORTED;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MMT_OK : MMT_ERR_BAD_ARG;
 }
 
@@ -540,7 +542,7 @@ int launch_attn_tc(const void* qkv0, int rows0, const void* qkv1, int rows1, int
   if (rc) return rc;
   // output rows are addressed through the tile table: the map's row bound is nominal (only groups of 32 valid rows are
   // stored through it, so its clipping is never relied upon)
-  rc = make_out_tmap(&tmo, out, 1 << 30, C, ldo);
+  rc = make_out_tmap(&tmo, out, 1 << 30, C, ldo, 32);
   if (rc) return rc;
   static bool attr_p = false;
   static int n_sm = 0;
