@@ -87,6 +87,22 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two gelu_fast at once on the packed fp32 pipe (fmul2 / ffma2: one issue slot for two lanes; the same operations in the same
+// order per lane, so the result is bit-identical to gelu_fast).
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 u = __fmul2_rn(x, x);
+  u.x = fminf(u.x, 64.0f);
+  u.y = fminf(u.y, 64.0f);
+  float2 p = __ffma2_rn(u, make_float2(-3.58004386e-04f, -3.58004386e-04f), make_float2(3.70462776e-02f, 3.70462776e-02f));
+  p = __ffma2_rn(p, u, make_float2(7.97462465e-01f, 7.97462465e-01f));
+  const float2 g = __fmul2_rn(p, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(g.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(g.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

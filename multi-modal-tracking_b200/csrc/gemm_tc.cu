@@ -195,20 +195,23 @@ __device__ __forceinline__ void epi_pair_bf16(const EpiCtx& cx, const GemmEpi& e
       uint32_t w[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        // packed fp32 arithmetic (fma.rn.f32x2 / add.f32x2): the same operations per element, half the issue slots
         const float4 b = reinterpret_cast<const float4*>(bias_s + kc * CH)[j];      // broadcast reads
-        float x0 = __uint_as_float(v[4 * j]), x1 = __uint_as_float(v[4 * j + 1]);
-        float x2 = __uint_as_float(v[4 * j + 2]), x3 = __uint_as_float(v[4 * j + 3]);
+        float2 xa = make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]));
+        float2 xb = make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         if (LN) {
           const float4 cs = reinterpret_cast<const float4*>(csum_s + kc * CH)[j];
-          x0 = fmaf(rs, fmaf(nmu, cs.x, x0), b.x); x1 = fmaf(rs, fmaf(nmu, cs.y, x1), b.y);
-          x2 = fmaf(rs, fmaf(nmu, cs.z, x2), b.z); x3 = fmaf(rs, fmaf(nmu, cs.w, x3), b.w);
+          const float2 rs2 = make_float2(rs, rs), nmu2 = make_float2(nmu, nmu);
+          xa = __ffma2_rn(rs2, __ffma2_rn(nmu2, make_float2(cs.x, cs.y), xa), make_float2(b.x, b.y));
+          xb = __ffma2_rn(rs2, __ffma2_rn(nmu2, make_float2(cs.z, cs.w), xb), make_float2(b.z, b.w));
         } else {
-          x0 += b.x; x1 += b.y; x2 += b.z; x3 += b.w;
+          xa = __fadd2_rn(xa, make_float2(b.x, b.y));
+          xb = __fadd2_rn(xb, make_float2(b.z, b.w));
         }
-        if (ACT == MMT_ACT_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3); }
-        else if (ACT == MMT_ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-        w[2 * j] = pack_bf16x2(x0, x1);
-        w[2 * j + 1] = pack_bf16x2(x2, x3);
+        if (ACT == MMT_ACT_GELU) { xa = gelu_fast2(xa); xb = gelu_fast2(xb); }
+        else if (ACT == MMT_ACT_RELU) { xa.x = fmaxf(xa.x, 0.f); xa.y = fmaxf(xa.y, 0.f); xb.x = fmaxf(xb.x, 0.f); xb.y = fmaxf(xb.y, 0.f); }
+        w[2 * j] = pack_bf16x2(xa.x, xa.y);
+        w[2 * j + 1] = pack_bf16x2(xb.x, xb.y);
       }
       // two staging tiles per warp: only the store of TWO chunks ago must have read its tile
       uint4* stg = cx.stg4 + 256 * (bk++ & 1u);
@@ -277,10 +280,14 @@ __device__ __forceinline__ void epi_pair_f32(const EpiCtx& cx, const GemmEpi& ep
         const int slot = lane * 8 + (j ^ (lane & 7));      // 128-byte rows, SWIZZLE_128B
         const uint4 rw = tile_s[slot];
         const float4 b = bq[j];
-        const float y0 = (__uint_as_float(v[4 * j]) + b.x) + __uint_as_float(rw.x);
-        const float y1 = (__uint_as_float(v[4 * j + 1]) + b.y) + __uint_as_float(rw.y);
-        const float y2 = (__uint_as_float(v[4 * j + 2]) + b.z) + __uint_as_float(rw.z);
-        const float y3 = (__uint_as_float(v[4 * j + 3]) + b.w) + __uint_as_float(rw.w);
+        // (accumulator + bias) + residual, two lanes per instruction (add.f32x2: same rounding as the scalar adds)
+        const float2 ya = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                                make_float2(b.x, b.y)),
+                                     make_float2(__uint_as_float(rw.x), __uint_as_float(rw.y)));
+        const float2 yb = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                                make_float2(b.z, b.w)),
+                                     make_float2(__uint_as_float(rw.z), __uint_as_float(rw.w)));
+        const float y0 = ya.x, y1 = ya.y, y2 = yb.x, y3 = yb.y;
         tile_s[slot] = make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3));
         if (LNOUT) {
           st_s1 += (y0 + y1) + (y2 + y3);
