@@ -192,8 +192,18 @@ def main_extra():
         d_map = (cap["maps"] - ora["score_maps"]).abs().max().item()
         print(f"{variant}/{yaml_name} ({cfg.MODEL.get('FUSION_CLASS')}): oracle vs reference boxes {d_box:.3e} maps {d_map:.3e}")
         assert d_box <= 1e-5 and d_map <= 2e-4
+        fp32_maps = cap["maps"]
+        # yardstick for the bf16 tests on this stress set: the UNMODIFIED reference in its own reduced-precision mode
+        # (torch.autocast(bfloat16) on the CPU) - how far the reference's boxes move when only the precision changes
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            out_ac, _ = ref_model(*inputs)
+        ac_maps = cap["maps"].float()
+        print(f"  reference under autocast(bf16): boxes move {(out_ac['pred_boxes'].float() - out['pred_boxes']).abs().max().item() * cfg.DATA.SEARCH.SIZE:.3f} px, "
+              f"maps {(ac_maps - fp32_maps).abs().max().item():.3e}")
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{variant}__{yaml_name}_b{BATCH}.npz"),
-                            pred_boxes=out["pred_boxes"].numpy(), score_maps=cap["maps"].numpy())
+                            pred_boxes=out["pred_boxes"].numpy(), score_maps=fp32_maps.numpy(),
+                            pred_boxes_autocast_bf16=out_ac["pred_boxes"].float().numpy(),
+                            score_maps_autocast_bf16=ac_maps.numpy())
 
 
 def main_corner_head():

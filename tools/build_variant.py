@@ -8,7 +8,9 @@ b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
 name, src, flags = sys.argv[1], sys.argv[2], sys.argv[3:]
 b.build()
 obj = os.path.join(b.OBJ, f"{src[:-3]}__{name}.o")
-subprocess.run([b._nvcc(), *b.NVCC_FLAGS, *flags, "-c", os.path.join(b.CSRC, src), "-o", obj], check=True)
+# VARIANT_SRC=<path>: compile that file (e.g. an older revision written to /tmp) in place of csrc/<src>
+path = os.environ.get("VARIANT_SRC") or os.path.join(b.CSRC, src)
+subprocess.run([b._nvcc(), *b.NVCC_FLAGS, *flags, "-c", path, "-o", obj], check=True)
 objs = [os.path.join(b.OBJ, f) for f in sorted(os.listdir(b.OBJ)) if f.endswith(".o") and "__" not in f and f != src[:-3] + ".o"]
 out = os.path.join(b.CSRC, f"libmmt_b200_{name}.so")
 subprocess.run([b._nvcc(), "-shared", "-o", out, *objs, obj, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], check=True)
