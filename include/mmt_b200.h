@@ -45,6 +45,12 @@ int mmt_config_pdl(int enable);
  * 4-15 % slower per launch on B200: clusters of four leave SMs idle and the per-SM operand ingest is unchanged). */
 int mmt_config_cluster4(int enable);
 
+/* SM budget of the small-GEMM tile rule (host only; returns the previous setting; 0 = the whole GPU).  Small problems (one
+ * sequence: 452 rows) get the narrowest tile whose grid still fits ONE wave of `sms` CTAs.  A caller that runs two independent
+ * chains of such GEMMs on two streams (the two modality backbones) sets half the SM count so that the chains run side by side
+ * instead of alternating - every CTA of the GEMM kernel owns its SM.  Tile width never changes a result (same K order). */
+int mmt_config_small_gemm_sms(int sms);
+
 /*
  * out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) + rowadd[row % period][N] + resid[M,N]
  * A, W bf16 row-major (K contiguous, lda/ldw in elements, multiples of 8, 16-byte aligned base);

@@ -15,7 +15,13 @@ extern "C" int mmt_config_pdl(int enable) {
   return prev;
 }
 
-namespace mmt { extern int g_cluster4_enabled; }
+namespace mmt { extern int g_cluster4_enabled; extern int g_small_gemm_sms; }
+
+extern "C" int mmt_config_small_gemm_sms(int sms) {
+  const int prev = mmt::g_small_gemm_sms;
+  mmt::g_small_gemm_sms = sms > 0 ? sms : 0;
+  return prev;
+}
 
 extern "C" int mmt_config_cluster4(int enable) {
   const int prev = mmt::g_cluster4_enabled;

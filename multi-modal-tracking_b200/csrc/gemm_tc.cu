@@ -1092,6 +1092,11 @@ static int num_sms() {
 // at M = 28 928, neutral in the step: clusters of four leave SMs out (GPCs of 16-20 SMs) and every SM still ingests the same
 // 32 KB per k-slice, so the bound is per SM, not the L2's read rate.  Off by default; mmt_config_cluster4(1) selects it.
 int g_cluster4_enabled = 0;
+// SM budget of the one-wave tile-narrowing rule (0 = the whole GPU).  When two independent chains of small GEMMs run on two
+// streams (the two modality backbones at one sequence), a grid that covers every SM serialises them - every CTA of this kernel
+// owns its SM's shared memory; with half the SMs as budget each launch picks the narrowest tile that fits HALF a wave and
+// the two chains run side by side.  mmt_config_small_gemm_sms.
+int g_small_gemm_sms = 0;
 
 template <bool CL4>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmC, const CUtensorMap& tmR, const CUtensorMap& tmX,
@@ -1254,7 +1259,8 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
     const int m_tiles = cdiv(M, GEMM_BM);
     // ... but never past ONE wave: a narrower tile that needs a second round of CTAs doubles the launch time (fc1 at one
     // sequence: 192 tiles of 64 columns on 148 SMs took two rounds; 96 tiles of 128 columns take one)
-    while (bn > 64 && (bn % 2) == 0 && (N % (bn / 2)) == 0 && m_tiles * cdiv(N, bn / 2) <= num_sms()) bn /= 2;
+    const int budget = (g_small_gemm_sms > 0 && g_small_gemm_sms < num_sms()) ? g_small_gemm_sms : num_sms();
+    while (bn > 64 && (bn % 2) == 0 && (N % (bn / 2)) == 0 && m_tiles * cdiv(N, bn / 2) <= budget) bn /= 2;
   }
   switch (bn) {
     case 256: return launch_gemm<256>(tmA, tmC, W, ldw, M, N, K, ep, cv, max_ctas, s);

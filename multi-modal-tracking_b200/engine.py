@@ -477,6 +477,8 @@ class ForwardEngine:
             self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
             self._two_streams = os.environ.get("MMT_TWO_STREAMS", "1") != "0"
             self._head_lanes = os.environ.get("MMT_HEAD_LANES", "1") != "0"      # A/B switch of _run_head's two lanes
+            self._half_sm_small = os.environ.get("MMT_HALF_SM_SMALL", "1") != "0"  # A/B switch of the small-GEMM SM budget
+            self._n_sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         return self._side
 
     def set_two_streams(self, on: bool):
@@ -502,16 +504,24 @@ class ForwardEngine:
         side.wait_event(self._fork_ev)
         lanes = (main, side)
         sts = []
-        for m in range(2):
-            with torch.cuda.stream(lanes[m]):
-                xm = x[m * M1:(m + 1) * M1]
-                wait(m)
-                self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm, lane=m)
-                sts.append(self._backbone_begin(xm, B, False))
-        for i in range(self.depth):
+        # few rows per modality (single-sequence latency): every GEMM is one partial wave of CTAs that each own an SM, so two
+        # whole-GPU grids would alternate instead of overlapping - give each chain half the SMs (ops.config_small_gemm_sms)
+        small = self.bf16 and self._half_sm_small and M1 <= 8 * 128
+        prev_budget = ops.config_small_gemm_sms(self._n_sm // 2) if small else None
+        try:
             for m in range(2):
                 with torch.cuda.stream(lanes[m]):
-                    self._backbone_block(self.bbs[m], sts[m], i, B, ("bb", B, m))
+                    xm = x[m * M1:(m + 1) * M1]
+                    wait(m)
+                    self._embed(self.bbs[m], B, t[m], ot[m], s[m], xm, lane=m)
+                    sts.append(self._backbone_begin(xm, B, False))
+            for i in range(self.depth):
+                for m in range(2):
+                    with torch.cuda.stream(lanes[m]):
+                        self._backbone_block(self.bbs[m], sts[m], i, B, ("bb", B, m))
+        finally:
+            if small:
+                ops.config_small_gemm_sms(prev_budget)
         feats = []
         for m in range(2):
             with torch.cuda.stream(lanes[m]):

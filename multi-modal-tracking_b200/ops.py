@@ -67,6 +67,12 @@ def config_cluster4(enable: bool) -> bool:
     return bool(f(c_int(1 if enable else 0)))
 
 
+def config_small_gemm_sms(sms: int) -> int:
+    """SM budget of the small-GEMM one-wave tile rule (mmt_config_small_gemm_sms; 0 = whole GPU); returns the previous one."""
+    f = _lib.fn("mmt_config_small_gemm_sms")
+    return int(f(c_int(int(sms))))
+
+
 def _pair_min_tiles():
     global _PAIR_MIN
     if _PAIR_MIN is None:
