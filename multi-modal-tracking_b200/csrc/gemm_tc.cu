@@ -1255,8 +1255,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* W, int ldw, int M, 
   // Small problems (bs = 1 latency: M = 452 rows per modality) leave most SMs idle with wide tiles - 4 x 3 tiles for
   // fc2 - and then the serial K loop of one CTA is the launch time.  Narrow the tile until the grid covers the machine
   // (never below 64 columns; only for plain GEMMs whose N the narrower tile divides).  MMT_GEMM_NARROW=0 disables (A/B).
-  if (narrow_enabled() && !cv.enabled && max_ctas <= 0) {
-    const int m_tiles = cdiv(M, GEMM_BM);
+  if (narrow_enabled() && max_ctas <= 0) {
+    // (implicit-GEMM convolutions included: the head at one sequence is 3 pixel boxes x 7 tiles of 192 columns walking 108
+    // k-slices each - 35 us - against 84 CTAs of 48 columns)
+    const int m_tiles = cv.enabled ? (M / (cv.H * cv.W)) * cv.tiles_x * cv.tiles_y : cdiv(M, GEMM_BM);
     // ... but never past ONE wave: a narrower tile that needs a second round of CTAs doubles the launch time (fc1 at one
     // sequence: 192 tiles of 64 columns on 148 SMs took two rounds; 96 tiles of 128 columns take one)
     const int budget = (g_small_gemm_sms > 0 && g_small_gemm_sms < num_sms()) ? g_small_gemm_sms : num_sms();
