@@ -116,3 +116,55 @@ def test_mixattn_growing_maxima(built_lib):
     ref = _reference(qkv, segs, HD ** -0.5)
     assert bool(torch.isfinite(out.float()).all())
     assert (out.float() - ref).abs().max().item() <= 4e-2
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_mixattn_large_model_shapes_and_guard_rows(built_lib, monkeypatch, cross):
+    """MixViT-L / ConvMAE-L geometry (16 heads, 288 template + 576 search tokens: query tiles of 32 and 64 rows at the tails,
+    a 32-key block in the MIDDLE of the key list) - the tail warps take the direct-store path, full 32-row groups the TMA
+    store, warps without a valid row only keep the barrier protocol.  Guard rows after the last (partial) tile stay untouched."""
+    import sys
+    from mmt_b200 import ops
+    me = sys.modules[__name__]
+    monkeypatch.setattr(me, "HEADS", 16)
+    monkeypatch.setattr(me, "C", 16 * HD)
+    heads, c = 16, 16 * HD
+    nseq, Lt, Ls = 2, 288, 576
+    N = Lt + Ls
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(nseq * N, 3 * c, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    tiles, segs = _tiles(nseq, N, Lt, Ls, cross)
+    max_keys = max(sum(l for _, l in s[2]) for s in segs)
+    guard = 96
+    buf = torch.full((nseq * N + guard, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = buf[: nseq * N]
+    ops.mixattn(qkv, None, c, heads, tiles.cuda(), max_keys, out, HD ** -0.5)
+    torch.cuda.synchronize()
+    ref = _reference(qkv, segs, HD ** -0.5)
+    assert bool(torch.isfinite(out.float()).all()), "unwritten or non-finite output rows"
+    assert bool(torch.isnan(buf[nseq * N:].float()).all()), "rows past the last tile were written"
+    assert (out.float() - ref).abs().max().item() <= 2.5e-2
+
+
+def test_mixattn_partial_tiles_do_not_touch_neighbour_rows(built_lib):
+    """A tile table that covers only SOME query tiles (every second one): rows of the tiles that are not in the table must
+    keep their previous contents - a 32 x 32 TMA store box or a straddling warp may not spill into them."""
+    from mmt_b200 import ops
+    nseq, Lt, Ls = 2, 128, 324
+    N = Lt + Ls
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = (torch.randn(nseq * N, 3 * C, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    tiles, segs = _tiles(nseq, N, Lt, Ls, False)
+    keep = list(range(0, tiles.shape[0], 2)) + [tiles.shape[0] - 1]       # incl. the 68-row tail tile of the last sequence
+    keep = sorted(set(keep))
+    sub = tiles[keep].contiguous()
+    out = torch.full((nseq * N, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.mixattn(qkv, None, C, HEADS, sub.cuda(), N, out, HD ** -0.5)
+    torch.cuda.synchronize()
+    ref = _reference(qkv, [segs[i] for i in keep], HD ** -0.5)
+    written = torch.zeros(nseq * N, dtype=torch.bool, device="cuda")
+    for i in keep:
+        q0, qn, _ = segs[i]
+        written[q0:q0 + qn] = True
+    assert bool(torch.isnan(out[~written].float()).all()), "rows of tiles that were not launched were written"
+    assert (out[written].float() - ref[written]).abs().max().item() <= 2.5e-2

@@ -261,6 +261,26 @@ def test_in_place_parameter_edits_repack_the_weights(built_lib):
     assert torch.equal(g1, want) and torch.allclose(g2, a, atol=1e-6)
 
 
+def test_single_sequence_sm_budget_is_result_neutral(built_lib):
+    """engine._run_two_backbones gives each modality chain half the SMs at small batch (mmt_config_small_gemm_sms): tile widths
+    change, results do not - eager and graph replay."""
+    from mmt_b200 import synthetic
+    model, cfg = synthetic.make_model("mixformer_vit_rgbt", 0)
+    model = model.cuda()
+    for batch in (1, 2):
+        inputs = synthetic.make_inputs("mixformer_vit_rgbt", cfg, batch, 4, device="cuda")
+        _, ref = model(*inputs)
+        eng = model.engine()
+        assert eng._half_sm_small
+        eng._half_sm_small = False
+        try:
+            _, whole = model(*inputs)
+        finally:
+            eng._half_sm_small = True
+        torch.cuda.synchronize()
+        assert torch.equal(ref, whole), batch
+
+
 def test_programmatic_dependent_launch_is_result_neutral(built_lib):
     """mmt_config_pdl: the kernels' prologues overlapping the previous kernel's tail (griddepcontrol) change no result -
     eager launches and graph replay, two variants (two streams / one stream with candidate elimination)."""

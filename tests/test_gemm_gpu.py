@@ -227,3 +227,28 @@ def test_cluster_of_four_is_bit_identical(built_lib, case):
         ops.config_cluster4(prev)
     for r, g_ in zip(ref, got):
         assert torch.equal(r, g_)
+
+
+def test_small_gemm_sm_budget_changes_no_result(built_lib):
+    """mmt_config_small_gemm_sms: with half the SMs as budget the one-wave rule picks wider tiles for the single-sequence
+    GEMMs (M = 452) - the K order per output element is the same, so every result is bit-identical."""
+    from mmt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M = 452
+    for N, K, act, resid in ((2304, 768, ops.ACT_NONE, False), (3072, 768, ops.ACT_GELU, False), (768, 3072, ops.ACT_NONE, True),
+                             (768, 768, ops.ACT_NONE, True)):
+        a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda", generator=g)
+        r = torch.randn(M, N, device="cuda", generator=g) if resid else None
+        outs = []
+        for budget in (0, 74, 37):
+            prev = ops.config_small_gemm_sms(budget)
+            try:
+                o = torch.empty(M, N, device="cuda", dtype=torch.float32 if resid else torch.bfloat16)
+                ops.gemm(a, w, b, act, r, None, out=o)
+                torch.cuda.synchronize()
+                outs.append(o)
+            finally:
+                ops.config_small_gemm_sms(prev)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (N, K)
