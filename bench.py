@@ -58,28 +58,63 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clocks / throttle reasons of this rank's GPU while the timed region runs.  Two sources, both stamped on arrival:
+    `nvidia-smi --query-gpu=... -lms 50` started EARLY (construct before the warm-up: on an 8-GPU box nvidia-smi needs longer
+    to start than a short timed region lasts) and an NVML polling thread (10 ms).  Only samples that arrived between
+    __enter__ and __exit__ count; nvidia-smi rows are preferred, NVML fills in when none arrived in the window."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+    def __init__(self, index, uuid=None):
+        self.index, self.rows, self.proc, self.t = index, [], None, None
+        self.t0 = self.t1 = None
+        self.nvml_rows, self._stop, self.nt, self.h, self.max_mhz = [], threading.Event(), None, None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(uuid or index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
-        return self
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def _poll(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self.h)) if reasons_fn else 0
+                self.nvml_rows.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                break
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        self.t0 = time.perf_counter()
+        if self.h is not None:
+            self.nt = threading.Thread(target=self._poll, daemon=True)
+            self.nt.start()
+        return self
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
+        self._stop.set()
+        if self.nt is not None:
+            self.nt.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -90,21 +125,31 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
+        for ts, r in self.rows:
+            if len(r) < 6 or self.t0 is None or not (self.t0 <= ts <= self.t1):
                 continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, r[2:6]):
+            for n, v in zip(self.NAMES, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if sm:
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                    "source": "nvidia-smi"}
+        # NVML bit masks (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        rows = [r for r in self.nvml_rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        if rows:
+            for _, _, mask in rows:
+                for n, bit in bits.items():
+                    if mask & bit:
+                        reasons.add(n)
+            return {"sm_mhz": statistics.median([r[1] for r in rows]), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(rows), "source": "nvml (no nvidia-smi row arrived inside the timed region)"}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
 
 
 def cpu_baseline_frames_per_s(variant, yaml_name, budget_s, batch=8, threads=None):
@@ -514,6 +559,11 @@ def main():
 
     if args.graph:
         model.enable_cuda_graph(True)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    clock_sampler = ClockSampler(local_rank, gpu_uuid)        # started before the warm-up: see the class
     # L2: one step touches >= 2 x 104.7 M bf16 weights (two streams) + ~1 GB of activations, far beyond the 126 MB L2
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -521,7 +571,7 @@ def main():
 
     ops.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with clock_sampler as clocks:
         barrier()
         e0.record()
         for k in range(args.steps):
