@@ -337,7 +337,10 @@ attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_con
 #if MMT_ATTN_EXP & 2
             const float2 pp = __fmul2_rn(x, make_float2(0.001f, 0.001f));
 #else
-            const float2 pp = (i & 3) == 3 ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
+#ifndef MMT_ATTN_POLY_SET
+#define MMT_ATTN_POLY_SET 0x8888      // bit i set: pair i of the 16 goes to the FMA-pipe cubic instead of the MUFU unit
+#endif
+            const float2 pp = ((MMT_ATTN_POLY_SET >> i) & 1) ? ex2_poly2(x) : make_float2(ex2_approx(x.x), ex2_approx(x.y));
 #endif
             l2 = __fadd2_rn(l2, pp);
             pk[i] = pack_bf16x2(pp.x, pp.y);
