@@ -53,7 +53,10 @@ __device__ unsigned long long g_attn_stamp[512][12];     // per-CTA phase cycle 
 #endif
 constexpr int ATC_HD = 64;
 constexpr int ATC_KB = 64;                          // keys per block
-constexpr int ATC_STAGES = 4;
+#ifndef MMT_ATTN_STAGES
+#define MMT_ATTN_STAGES 4      // K/V ring depth in 64-key blocks (even); 6: 84.8 vs 82.8 us (profiles/r2_attention.md)
+#endif
+constexpr int ATC_STAGES = MMT_ATTN_STAGES;
 constexpr int ATC_BLK_BYTES = ATC_KB * ATC_HD * 2;  // 8 KB
 constexpr int ATC_Q_BYTES = 128 * ATC_HD * 2;       // 16 KB
 constexpr int ATC_THREADS = 320;
