@@ -508,23 +508,28 @@ __global__ void im2col3x3_kernel(const T* __restrict__ src1, int ld1, int s1, co
 // upsample_add: out(b, y, x, :) = src1[b, y / s1, x / s1, :] (+ src2[b, y / s2, x / s2, :]) on NHWC maps, bf16, the
 // add in fp32 with one rounding (F.interpolate(scale_factor=2|4) + add, lib/models/mixformer_cvt/head.py:166-178).
 // Materialises the input of the implicit-GEMM 3x3 convolutions of the pyramid head once (instead of 9 im2col copies).
+// One CTA per output row (b, y): the source rows are fixed per CTA, the per-element index arithmetic is two 32-bit
+// operations (the first form decomposed a 64-bit linear index with five divisions per 16-byte element: 33 us per launch for
+// 30-60 MB, three times what the traffic costs).
 __global__ void upsample_add_kernel(const bf16* __restrict__ src1, int ld1, int s1, const bf16* __restrict__ src2,
                                     int ld2, int s2, int B, int H, int W, int C, bf16* __restrict__ out) {
   const int cvn = C / 8;
-  const size_t total = static_cast<size_t>(B) * H * W * cvn;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cv = i % cvn;
-    size_t r = i / cvn;
-    const int x = r % W;
-    r /= W;
-    const int y = r % H;
-    const int b = r / H;
-    const int H1 = H / s1, W1 = W / s1;
-    uint4 v = *reinterpret_cast<const uint4*>(src1 + (static_cast<size_t>(b) * H1 * W1 + (y / s1) * W1 + x / s1) * ld1 + cv * 8);
-    if (src2) {
-      const int H2 = H / s2, W2 = W / s2;
-      const uint4 w = *reinterpret_cast<const uint4*>(src2 + (static_cast<size_t>(b) * H2 * W2 + (y / s2) * W2 + x / s2) * ld2 + cv * 8);
+  const int y = blockIdx.x % H, b = blockIdx.x / H;
+  const int W1 = W / s1, H1 = H / s1;
+  const bf16* r1 = src1 + (static_cast<size_t>(b) * H1 * W1 + static_cast<size_t>(y / s1) * W1) * ld1;
+  const bf16* r2 = nullptr;
+  int W2 = 0;
+  if (src2) {
+    W2 = W / s2;
+    r2 = src2 + (static_cast<size_t>(b) * (H / s2) * W2 + static_cast<size_t>(y / s2) * W2) * ld2;
+  }
+  uint4* orow = reinterpret_cast<uint4*>(out) + (static_cast<size_t>(b) * H + y) * W * cvn;
+  const int n = W * cvn;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {      // (four elements per trip with the loads issued first: no faster)
+    const int x = e / cvn, cv = e - x * cvn;
+    uint4 v = *reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x / s1) * ld1 + cv * 8);
+    if (r2) {
+      const uint4 w = *reinterpret_cast<const uint4*>(r2 + static_cast<size_t>(x / s2) * ld2 + cv * 8);
       __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&v);
       const __nv_bfloat162* c = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
@@ -533,7 +538,7 @@ __global__ void upsample_add_kernel(const bf16* __restrict__ src1, int ld1, int 
         a[k] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
       }
     }
-    reinterpret_cast<uint4*>(out)[i] = v;
+    orow[e] = v;
   }
 }
 
@@ -802,8 +807,8 @@ extern "C" int mmt_upsample_add(const void* src1, int ld1, int s1, const void* s
   MMT_CHECK_ARG(C % 8 == 0 && ld1 % 8 == 0 && (!src2 || ld2 % 8 == 0));
   MMT_CHECK_ARG((reinterpret_cast<uintptr_t>(src1) & 15) == 0 && (reinterpret_cast<uintptr_t>(src2) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
-  upsample_add_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  MMT_CHECK_ARG(static_cast<long long>(B) * H < (1ll << 31));
+  upsample_add_kernel<<<B * H, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(src1), ld1, s1, reinterpret_cast<const bf16*>(src2), ld2, s2, B, H, W, C,
       reinterpret_cast<bf16*>(out));
   MMT_RETURN_LAST_ERROR();
