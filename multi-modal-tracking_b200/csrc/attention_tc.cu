@@ -40,8 +40,13 @@ struct AttnTileTC {      // same 16-int record as AttnTile (attention.cu); q_row
   int pad[3];
 };
 
+// Developer builds only (tools/build_variant.py -> csrc/libmmt_b200_<name>.so, loaded by MMT_B200_DEV_LIB=<name>; the shipped
+// library is compiled with 0): timing experiments of profiles/r2_attention.md.  Bits 1-8 make the RESULTS WRONG by construction.
+//   1  no row-maximum exchange between the two threads of a row     2  no exponentials (a multiply instead)
+//   4  no global stores in the epilogue                            8  one CTA per SM instead of two
+//  16  phase cycle stamps of softmax warp 4 lane 0 (results stay correct; read back with mmt_dev_attn_stamps, tools/attn_stamps.py)
 #ifndef MMT_ATTN_EXP
-#define MMT_ATTN_EXP 0       // developer timing experiments (tools/ only; results are WRONG with any bit set)
+#define MMT_ATTN_EXP 0
 #endif
 #if MMT_ATTN_EXP & 16
 __device__ unsigned long long g_attn_stamp[512][12];     // per-CTA phase cycle sums of softmax warp 4, lane 0
